@@ -1,0 +1,162 @@
+/*
+ * ottocov.h -- C ABI of libottocov.so, the B200-native co-visitation (co-event) counting engine.
+ *
+ * The reference (nicolaivicol/otto-recommender) has no FFI: its stage boundary is the Python
+ * module model/count_co_events.py plus parquet files.  Each entry point below names the
+ * reference code it replaces (file:line into the reference tree); INTEGRATION.md shows the
+ * ctypes stub a maintainer would add to model/count_co_events.py.
+ *
+ * Conventions
+ *   - every function returns 0 (OTTOCOV_OK) or a negative ottocov_status; nothing throws;
+ *     ottocov_last_error(ctx) gives the message of the last failure on that context.
+ *   - plain pointers and sizes only.  `where` says whether a caller buffer is host
+ *     (OTTOCOV_HOST) or device (OTTOCOV_DEVICE) memory; the caller owns every buffer it passes.
+ *   - the library owns its scratch and every ottocov_table; one context per device, one thread
+ *     per context.  All work is enqueued on the context's stream (ottocov_set_stream); only
+ *     the *_fetch / *_info calls and calls that must size an allocation synchronise it.
+ *   - there is no CPU fallback: without a CUDA device ottocov_create fails with
+ *     OTTOCOV_ERR_CUDA.
+ *
+ * Key format of a table row: key = (uint64)aid << 32 | (uint32)aid_next, count = uint32.
+ * Rows of a table are always sorted by key and keys are distinct.
+ */
+#ifndef OTTOCOV_H
+#define OTTOCOV_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OTTOCOV_VERSION 100
+
+typedef enum {
+    OTTOCOV_OK = 0,
+    OTTOCOV_ERR_CUDA = -1,        /* a CUDA runtime call failed (message has the CUDA error)   */
+    OTTOCOV_ERR_ARG = -2,         /* bad argument (NULL, negative size, k out of range ...)     */
+    OTTOCOV_ERR_DATA = -3,        /* input violates the schema (type not in 0..2, aid < 0 ...)  */
+    OTTOCOV_ERR_STATE = -4,       /* call order wrong (count before load_events ...)            */
+    OTTOCOV_ERR_CAPACITY = -5,    /* caller buffer too small                                    */
+    OTTOCOV_ERR_NOMEM = -6        /* device allocation failed                                   */
+} ottocov_status;
+
+enum { OTTOCOV_HOST = 0, OTTOCOV_DEVICE = 1 };
+enum { OTTOCOV_ORDER_KEY = 0,          /* (aid, aid_next) ascending                              */
+       OTTOCOV_ORDER_COUNT_DESC = 1 }; /* count desc, then aid asc, aid_next asc (file order)   */
+
+typedef struct ottocov_ctx ottocov_ctx;
+typedef struct ottocov_table ottocov_table;
+
+/* One co-event kind = one entry of config.MAP_NAME_COUNT_TYPE + MAP_MAX_TIME_TO_NEXT
+ * (reference config.py:43-49, 81-88). */
+typedef struct {
+    int32_t type_this;       /* source event type: 0 click, 1 cart, 2 order                       */
+    uint32_t next_mask;      /* bit t set <=> events of type t are "next" events                  */
+    int64_t window;          /* |ts_next - ts| <= window, seconds, inclusive; clamped to 86400     */
+                             /* (the +-24 h pre-filter of count_co_events.py:33-36)                */
+    int64_t pair_budget;     /* max co-event pairs expanded at once (HBM footprint); 0 = auto     */
+} ottocov_spec;
+
+typedef struct {
+    int64_t n_rows_in;       /* rows handed to ottocov_load_events                                 */
+    int64_t n_events;        /* after exact-duplicate removal (count_co_events.py:92)              */
+    int64_t n_by_type[3];    /* deduplicated events per type                                       */
+    int32_t session_min, session_max, ts_min, ts_max, aid_max;
+    int32_t aid_bits;        /* significant bits of aid_max                                        */
+    int32_t was_sorted;      /* input was already ordered by (session, ts): sort skipped           */
+} ottocov_events_info;
+
+typedef struct {
+    int64_t n_pairs;         /* co-event pairs emitted by the last ottocov_count (sum of counts)   */
+    int64_t n_unique;        /* rows of the table it produced                                      */
+    int32_t n_chunks;        /* pair-budget chunks it ran                                          */
+    int32_t sort_passes;     /* radix passes per chunk                                             */
+} ottocov_count_info;
+
+/* Per-kernel-family accounting for roofline reports (bench.py). */
+enum { OTTOCOV_K_LOAD = 0, OTTOCOV_K_WINDOW, OTTOCOV_K_EXPAND, OTTOCOV_K_HIST, OTTOCOV_K_SORT_PASS,
+       OTTOCOV_K_RLE, OTTOCOV_K_FILTER, OTTOCOV_K_TOPK, OTTOCOV_K_ORDER, OTTOCOV_K_PARTITION,
+       OTTOCOV_K_MISC, OTTOCOV_K_FAMILIES };
+typedef struct {
+    int64_t launches;        /* kernel launches since the last reset                               */
+    double ms;               /* summed CUDA-event time (only while profiling is on)                */
+    double algo_bytes;       /* algorithmic bytes those launches moved            */
+} ottocov_kernel_stat;
+
+/* ---- context ------------------------------------------------------------------------------ */
+int ottocov_version(void);
+int ottocov_create(int device, ottocov_ctx** out);
+int ottocov_destroy(ottocov_ctx* ctx);
+const char* ottocov_last_error(const ottocov_ctx* ctx);      /* ctx may be NULL (create failures) */
+int ottocov_set_stream(ottocov_ctx* ctx, void* cuda_stream); /* cudaStream_t; NULL = default       */
+int ottocov_synchronize(ottocov_ctx* ctx);
+int ottocov_set_profiling(ottocov_ctx* ctx, int on);         /* CUDA-event timing per family       */
+int ottocov_kernel_stats(ottocov_ctx* ctx, ottocov_kernel_stat* out /*[OTTOCOV_K_FAMILIES]*/, int reset);
+const char* ottocov_kernel_family_name(int family);
+
+/* ---- (1) loader: replaces pl.read_parquet(...).unique() and the session grouping the self-join
+ * does implicitly (model/count_co_events.py:91-92, :19, :41-57).  Rows may come in any order.
+ * Sorts by (session, ts), drops exact duplicates, splits by type into sorted columnar arrays. */
+int ottocov_load_events(ottocov_ctx* ctx, const int32_t* session, const int32_t* aid,
+                        const int32_t* ts, const int8_t* type, int64_t n, int where);
+int ottocov_get_events_info(ottocov_ctx* ctx, ottocov_events_info* out);
+
+/* ---- (2)+(3) pair expansion + reduce-by-key: replaces self_merge + the filter/groupby of
+ * count_co_events (model/count_co_events.py:17-38, :60-77) for ONE co-event kind over the loaded
+ * events.  The n^2 join is never materialised.  *out is a new table (caller frees it). */
+int ottocov_count(ottocov_ctx* ctx, const ottocov_spec* spec, ottocov_table** out);
+int ottocov_get_count_info(ottocov_ctx* ctx, ottocov_count_info* out);
+
+/* ---- tables: the (aid, aid_next, count) frames the reference writes per part and re-reads in
+ * concat_files_w_stats (model/count_co_events.py:97-100, :112-115). */
+int ottocov_table_from_arrays(ottocov_ctx* ctx, const int32_t* aid, const int32_t* aid_next,
+                              const uint32_t* count, int64_t n, int where, ottocov_table** out);
+int ottocov_table_from_packed(ottocov_ctx* ctx, const uint64_t* keys, const uint32_t* count,
+                              int64_t n, int where, ottocov_table** out);
+int ottocov_table_free(ottocov_ctx* ctx, ottocov_table* t);
+int ottocov_table_rows(const ottocov_table* t, int64_t* n_rows);
+int ottocov_table_total(ottocov_ctx* ctx, const ottocov_table* t, int64_t* sum_of_counts);
+
+/* groupby(['aid','aid_next']).sum('count') over the concatenation of tables
+ * (model/count_co_events.py:168; also :154-155).  Inputs stay valid. */
+int ottocov_table_merge(ottocov_ctx* ctx, ottocov_table* const* tabs, int n_tabs, ottocov_table** out);
+
+/* filter(count >= min_count) (model/count_co_events.py:131-132, :156, :172). */
+int ottocov_table_filter(ottocov_ctx* ctx, const ottocov_table* t, uint32_t min_count, ottocov_table** out);
+
+/* Copy rows out, optionally in the file order of model/count_co_events.py:173-175
+ * (count descending, first `head` rows, count as int32).  Returns rows written in *n_out. */
+int ottocov_table_fetch(ottocov_ctx* ctx, const ottocov_table* t, int order, int64_t head,
+                        int32_t* aid, int32_t* aid_next, int32_t* count, int64_t cap, int where,
+                        int64_t* n_out);
+/* Raw packed view (device pointers owned by the table; valid until it is freed). */
+int ottocov_table_device_ptrs(const ottocov_table* t, const uint64_t** keys, const uint32_t** count);
+
+/* ---- (4) segmented top-K per aid: replaces sort('aid') + rank('ordinal', reverse=True).over('aid')
+ * <= first_n of model/retrieve.py:41-47.  Order inside an aid: count desc, then aid_next asc
+ * (canonical rule; the reference's tie order is unspecified).  1 <= k <= 32.
+ * Result: n_aids segments; row i has aid_x[i], n_valid[i] = min(k, segment size) and k slots
+ * aid_y[i*k..], cnt[i*k..] (unused slots are -1 / 0). */
+int ottocov_table_topk(ottocov_ctx* ctx, const ottocov_table* t, int k, int64_t* n_aids);
+int ottocov_topk_fetch(ottocov_ctx* ctx, int32_t* aid_x, int32_t* n_valid, int32_t* aid_y,
+                       int32_t* cnt, int64_t cap_aids, int where);
+
+/* ---- multi-GPU exchange support: stable partition of a table's rows by
+ * dest = ottocov_hash_dest(aid, n_ranks) into caller-owned DEVICE buffers (the send buffers of
+ * the all-to-all); rows_per_dest is a HOST array [n_ranks].  No reference counterpart (the
+ * reference is single-process); counts shard by key because sum is associative. */
+int ottocov_table_partition(ottocov_ctx* ctx, const ottocov_table* t, int n_ranks,
+                            uint64_t* keys_out_dev, uint32_t* count_out_dev, int64_t* rows_per_dest);
+uint32_t ottocov_hash_dest(uint32_t aid, uint32_t n_ranks);
+
+/* ---- building blocks exposed for tests and micro-benchmarks ---------------------------------- */
+/* LSD radix sort of device-resident 64-bit keys on bits [lo_bit, hi_bit), optional 32-bit
+ * payload (vals may be NULL).  Sorted data ends in keys/vals (in place from the caller's view). */
+int ottocov_sort_u64(ottocov_ctx* ctx, uint64_t* keys_dev, uint32_t* vals_dev, int64_t n,
+                     int lo_bit, int hi_bit);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OTTOCOV_H */

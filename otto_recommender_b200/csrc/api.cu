@@ -1,0 +1,337 @@
+// api.cu -- the C ABI of libottocov.so (include/ottocov.h): argument checks, exception -> status
+// translation, context life cycle, per-family launch accounting.
+#include "internal.cuh"
+#include <cstring>
+
+static thread_local std::string g_create_error;
+
+static const char* k_family_names[OTTOCOV_K_FAMILIES] = {
+    "load", "window", "expand", "histogram", "sort_pass", "rle", "filter", "topk", "order", "partition", "misc"};
+
+void ottocov_ctx::begin(int family) {
+    stats[family].launches += 1;
+    if (!profiling) return;
+    ProfEvent pe;
+    pe.family = family;
+    auto grab = [&]() {
+        cudaEvent_t e;
+        if (!event_pool.empty()) { e = event_pool.back(); event_pool.pop_back(); }
+        else if (cudaEventCreate(&e) != cudaSuccess) { e = nullptr; }
+        return e;
+    };
+    pe.a = grab(); pe.b = grab();
+    if (pe.a) cudaEventRecord(pe.a, stream);
+    prof_pending.push_back(pe);
+}
+
+void ottocov_ctx::end(int family, double algo_bytes) {
+    stats[family].algo_bytes += algo_bytes;
+    if (!profiling || prof_pending.empty()) return;
+    ProfEvent& pe = prof_pending.back();
+    if (pe.family == family && pe.b) cudaEventRecord(pe.b, stream);
+}
+
+static void resolve_profile(ottocov_ctx* ctx) {
+    if (ctx->prof_pending.empty()) return;
+    cudaStreamSynchronize(ctx->stream);
+    for (ProfEvent& pe : ctx->prof_pending) {
+        float ms = 0.f;
+        if (pe.a && pe.b && cudaEventElapsedTime(&ms, pe.a, pe.b) == cudaSuccess) ctx->stats[pe.family].ms += ms;
+        else (void)cudaGetLastError();
+        if (pe.a) ctx->event_pool.push_back(pe.a);
+        if (pe.b) ctx->event_pool.push_back(pe.b);
+    }
+    ctx->prof_pending.clear();
+}
+
+#define API_BEGIN(ctx_)                                                          \
+    if (!(ctx_)) return OTTOCOV_ERR_ARG;                                         \
+    try {                                                                        \
+        CUDA_CHECK(cudaSetDevice((ctx_)->device));
+
+#define API_END(ctx_)                                                            \
+        return OTTOCOV_OK;                                                       \
+    } catch (const CovError& e) {                                                \
+        (ctx_)->err = e.msg;                                                     \
+        (void)cudaGetLastError();                                                \
+        return e.code;                                                           \
+    } catch (const std::bad_alloc&) {                                            \
+        (ctx_)->err = "host allocation failed";                                  \
+        return OTTOCOV_ERR_NOMEM;                                                \
+    } catch (...) {                                                              \
+        (ctx_)->err = "unknown internal error";                                  \
+        return OTTOCOV_ERR_CUDA;                                                 \
+    }
+
+extern "C" {
+
+int ottocov_version(void) { return OTTOCOV_VERSION; }
+
+const char* ottocov_kernel_family_name(int family) {
+    return (family >= 0 && family < OTTOCOV_K_FAMILIES) ? k_family_names[family] : "?";
+}
+
+int ottocov_create(int device, ottocov_ctx** out) {
+    if (!out) return OTTOCOV_ERR_ARG;
+    *out = nullptr;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                         " (libottocov has no CPU fallback)";
+        (void)cudaGetLastError();
+        return OTTOCOV_ERR_CUDA;
+    }
+    if (device < 0 || device >= n_dev) {
+        g_create_error = "device index out of range";
+        return OTTOCOV_ERR_ARG;
+    }
+    ottocov_ctx* ctx = nullptr;
+    try {
+        ctx = new ottocov_ctx();
+        ctx->device = device;
+        memset(ctx->stats, 0, sizeof(ctx->stats));
+        memset(&ctx->info, 0, sizeof(ctx->info));
+        memset(&ctx->last_count, 0, sizeof(ctx->last_count));
+        CUDA_CHECK(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10) COV_THROW(OTTOCOV_ERR_CUDA, "device %d is sm_%d%d; libottocov is built for sm_100a only", device, prop.major, prop.minor);
+        ctx->num_sms = prop.multiProcessorCount;
+        // keep freed blocks in the stream-ordered pool: the pipeline re-allocates the same sizes
+        cudaMemPool_t pool;
+        CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t thr = UINT64_MAX;
+        CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    } catch (const CovError& e2) {
+        g_create_error = e2.msg;
+        delete ctx;
+        (void)cudaGetLastError();
+        return e2.code;
+    } catch (...) {
+        g_create_error = "unknown error in ottocov_create";
+        delete ctx;
+        return OTTOCOV_ERR_CUDA;
+    }
+    *out = ctx;
+    return OTTOCOV_OK;
+}
+
+int ottocov_destroy(ottocov_ctx* ctx) {
+    if (!ctx) return OTTOCOV_OK;
+    cudaSetDevice(ctx->device);
+    free_events(ctx);
+    free_topk(ctx);
+    if (ctx->sweep_status) cudaFreeAsync(ctx->sweep_status, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->sweep_ticket) cudaFree(ctx->sweep_ticket);
+    for (ProfEvent& pe : ctx->prof_pending) { if (pe.a) cudaEventDestroy(pe.a); if (pe.b) cudaEventDestroy(pe.b); }
+    for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
+    (void)cudaGetLastError();
+    delete ctx;
+    return OTTOCOV_OK;
+}
+
+const char* ottocov_last_error(const ottocov_ctx* ctx) {
+    return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+int ottocov_set_stream(ottocov_ctx* ctx, void* cuda_stream) {
+    API_BEGIN(ctx)
+    if ((cudaStream_t)cuda_stream != ctx->stream) {
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));   // pool frees are ordered on the old stream
+        ctx->stream = (cudaStream_t)cuda_stream;
+    }
+    API_END(ctx)
+}
+
+int ottocov_synchronize(ottocov_ctx* ctx) {
+    API_BEGIN(ctx)
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    API_END(ctx)
+}
+
+int ottocov_set_profiling(ottocov_ctx* ctx, int on) {
+    API_BEGIN(ctx)
+    resolve_profile(ctx);
+    ctx->profiling = on != 0;
+    API_END(ctx)
+}
+
+int ottocov_kernel_stats(ottocov_ctx* ctx, ottocov_kernel_stat* out, int reset) {
+    API_BEGIN(ctx)
+    resolve_profile(ctx);
+    if (out) memcpy(out, ctx->stats, sizeof(ctx->stats));
+    if (reset) memset(ctx->stats, 0, sizeof(ctx->stats));
+    API_END(ctx)
+}
+
+int ottocov_load_events(ottocov_ctx* ctx, const int32_t* session, const int32_t* aid, const int32_t* ts,
+                        const int8_t* type, int64_t n, int where) {
+    API_BEGIN(ctx)
+    if (n < 0) COV_THROW(OTTOCOV_ERR_ARG, "n < 0");
+    if (n > 0 && (!session || !aid || !ts || !type)) COV_THROW(OTTOCOV_ERR_ARG, "NULL column");
+    if (where != OTTOCOV_HOST && where != OTTOCOV_DEVICE) COV_THROW(OTTOCOV_ERR_ARG, "bad `where`");
+    load_events_impl(ctx, session, aid, ts, type, n, where);
+    API_END(ctx)
+}
+
+int ottocov_get_events_info(ottocov_ctx* ctx, ottocov_events_info* out) {
+    API_BEGIN(ctx)
+    if (!out) COV_THROW(OTTOCOV_ERR_ARG, "NULL out");
+    if (!ctx->loaded) COV_THROW(OTTOCOV_ERR_STATE, "no events loaded");
+    *out = ctx->info;
+    API_END(ctx)
+}
+
+int ottocov_count(ottocov_ctx* ctx, const ottocov_spec* spec, ottocov_table** out) {
+    API_BEGIN(ctx)
+    if (!spec || !out) COV_THROW(OTTOCOV_ERR_ARG, "NULL argument");
+    *out = nullptr;
+    *out = count_impl(ctx, spec);
+    API_END(ctx)
+}
+
+int ottocov_get_count_info(ottocov_ctx* ctx, ottocov_count_info* out) {
+    API_BEGIN(ctx)
+    if (!out) COV_THROW(OTTOCOV_ERR_ARG, "NULL out");
+    *out = ctx->last_count;
+    API_END(ctx)
+}
+
+int ottocov_table_from_arrays(ottocov_ctx* ctx, const int32_t* aid, const int32_t* aid_next, const uint32_t* count,
+                              int64_t n, int where, ottocov_table** out) {
+    API_BEGIN(ctx)
+    if (!out || n < 0 || (n > 0 && (!aid || !aid_next || !count))) COV_THROW(OTTOCOV_ERR_ARG, "bad argument");
+    *out = nullptr;
+    *out = table_from_arrays_impl(ctx, aid, aid_next, count, n, where);
+    API_END(ctx)
+}
+
+int ottocov_table_from_packed(ottocov_ctx* ctx, const uint64_t* keys, const uint32_t* count, int64_t n, int where,
+                              ottocov_table** out) {
+    API_BEGIN(ctx)
+    if (!out || n < 0 || (n > 0 && (!keys || !count))) COV_THROW(OTTOCOV_ERR_ARG, "bad argument");
+    *out = nullptr;
+    *out = table_from_packed_impl(ctx, (const u64*)keys, count, n, where);
+    API_END(ctx)
+}
+
+int ottocov_table_free(ottocov_ctx* ctx, ottocov_table* t) {
+    API_BEGIN(ctx)
+    if (t) {
+        dev_free(ctx, t->keys);
+        dev_free(ctx, t->count);
+        delete t;
+    }
+    API_END(ctx)
+}
+
+int ottocov_table_rows(const ottocov_table* t, int64_t* n_rows) {
+    if (!t || !n_rows) return OTTOCOV_ERR_ARG;
+    *n_rows = t->n;
+    return OTTOCOV_OK;
+}
+
+int ottocov_table_total(ottocov_ctx* ctx, const ottocov_table* t, int64_t* sum_of_counts) {
+    API_BEGIN(ctx)
+    if (!t || !sum_of_counts) COV_THROW(OTTOCOV_ERR_ARG, "NULL argument");
+    *sum_of_counts = table_total_impl(ctx, t);
+    API_END(ctx)
+}
+
+int ottocov_table_merge(ottocov_ctx* ctx, ottocov_table* const* tabs, int n_tabs, ottocov_table** out) {
+    API_BEGIN(ctx)
+    if (!out || n_tabs < 0 || (n_tabs > 0 && !tabs)) COV_THROW(OTTOCOV_ERR_ARG, "bad argument");
+    *out = nullptr;
+    *out = merge_tables_impl(ctx, tabs, n_tabs);
+    API_END(ctx)
+}
+
+int ottocov_table_filter(ottocov_ctx* ctx, const ottocov_table* t, uint32_t min_count, ottocov_table** out) {
+    API_BEGIN(ctx)
+    if (!t || !out) COV_THROW(OTTOCOV_ERR_ARG, "NULL argument");
+    *out = nullptr;
+    *out = filter_table_impl(ctx, t, min_count);
+    API_END(ctx)
+}
+
+int ottocov_table_fetch(ottocov_ctx* ctx, const ottocov_table* t, int order, int64_t head, int32_t* aid,
+                        int32_t* aid_next, int32_t* count, int64_t cap, int where, int64_t* n_out) {
+    API_BEGIN(ctx)
+    if (!t) COV_THROW(OTTOCOV_ERR_ARG, "NULL table");
+    if (cap > 0 && (!aid || !aid_next || !count)) COV_THROW(OTTOCOV_ERR_ARG, "NULL output");
+    fetch_table_impl(ctx, t, order, head, aid, aid_next, count, cap, where, n_out);
+    API_END(ctx)
+}
+
+int ottocov_table_device_ptrs(const ottocov_table* t, const uint64_t** keys, const uint32_t** count) {
+    if (!t) return OTTOCOV_ERR_ARG;
+    if (keys) *keys = (const uint64_t*)t->keys;
+    if (count) *count = t->count;
+    return OTTOCOV_OK;
+}
+
+int ottocov_table_topk(ottocov_ctx* ctx, const ottocov_table* t, int k, int64_t* n_aids) {
+    API_BEGIN(ctx)
+    if (!t) COV_THROW(OTTOCOV_ERR_ARG, "NULL table");
+    topk_impl(ctx, t, k);
+    if (n_aids) *n_aids = ctx->topk_n;
+    API_END(ctx)
+}
+
+int ottocov_topk_fetch(ottocov_ctx* ctx, int32_t* aid_x, int32_t* n_valid, int32_t* aid_y, int32_t* cnt,
+                       int64_t cap_aids, int where) {
+    API_BEGIN(ctx)
+    if (ctx->topk_k == 0) COV_THROW(OTTOCOV_ERR_STATE, "ottocov_topk_fetch before ottocov_table_topk");
+    const int64_t n = ctx->topk_n;
+    const int k = ctx->topk_k;
+    if (cap_aids < n) COV_THROW(OTTOCOV_ERR_CAPACITY, "top-k fetch needs room for %lld aids", (long long)n);
+    if (n > 0) {
+        if (!aid_x || !n_valid || !aid_y || !cnt) COV_THROW(OTTOCOV_ERR_ARG, "NULL output");
+        const cudaMemcpyKind kind = (where == OTTOCOV_HOST) ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+        CUDA_CHECK(cudaMemcpyAsync(aid_x, ctx->topk_aid_x, n * 4, kind, ctx->stream));
+        CUDA_CHECK(cudaMemcpyAsync(n_valid, ctx->topk_nvalid, n * 4, kind, ctx->stream));
+        CUDA_CHECK(cudaMemcpyAsync(aid_y, ctx->topk_aid_y, n * k * 4, kind, ctx->stream));
+        CUDA_CHECK(cudaMemcpyAsync(cnt, ctx->topk_cnt, n * k * 4, kind, ctx->stream));
+    }
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    API_END(ctx)
+}
+
+int ottocov_table_partition(ottocov_ctx* ctx, const ottocov_table* t, int n_ranks, uint64_t* keys_out_dev,
+                            uint32_t* count_out_dev, int64_t* rows_per_dest) {
+    API_BEGIN(ctx)
+    if (!t || !rows_per_dest || n_ranks < 1 || n_ranks > 1024) COV_THROW(OTTOCOV_ERR_ARG, "bad argument");
+    if (t->n > 0 && (!keys_out_dev || !count_out_dev)) COV_THROW(OTTOCOV_ERR_ARG, "NULL send buffer");
+    partition_table_impl(ctx, t, n_ranks, (u64*)keys_out_dev, count_out_dev, rows_per_dest);
+    if (t->n == 0) for (int r = 0; r < n_ranks; ++r) rows_per_dest[r] = 0;
+    API_END(ctx)
+}
+
+uint32_t ottocov_hash_dest(uint32_t aid, uint32_t n_ranks) {
+    uint32_t h = aid * 0x9E3779B1u;
+    h ^= h >> 15;
+    return n_ranks ? h % n_ranks : 0;
+}
+
+int ottocov_sort_u64(ottocov_ctx* ctx, uint64_t* keys_dev, uint32_t* vals_dev, int64_t n, int lo_bit, int hi_bit) {
+    API_BEGIN(ctx)
+    if (n < 0 || lo_bit < 0 || hi_bit > 64 || lo_bit > hi_bit) COV_THROW(OTTOCOV_ERR_ARG, "bad argument");
+    if (n > 1 && hi_bit > lo_bit) {
+        if (!keys_dev) COV_THROW(OTTOCOV_ERR_ARG, "NULL keys");
+        DevBuf<u64> alt(ctx, n);
+        DevBuf<u32> valt;
+        if (vals_dev) valt.alloc(ctx, n);
+        u64* k = (u64*)keys_dev; u64* ka = alt.p; u32* v = vals_dev; u32* va = valt.p;
+        BitField f[1] = {{lo_bit, hi_bit}};
+        radix_sort_pairs(ctx, k, ka, v, va, n, f, 1);
+        if (k != (u64*)keys_dev) {
+            CUDA_CHECK(cudaMemcpyAsync(keys_dev, k, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+            if (vals_dev) CUDA_CHECK(cudaMemcpyAsync(vals_dev, v, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+    }
+    API_END(ctx)
+}
+
+}  // extern "C"

@@ -1,0 +1,246 @@
+// events.cu -- the columnar loader: rows (session, aid, ts, type) in any order -> per-type arrays
+// sorted by (session, ts), exact duplicates removed.
+//
+// Replaces, for the GPU path, pl.read_parquet(...).unique() (model/count_co_events.py:91-92) and the
+// hash-join's implicit grouping by session (:19).  Input schema: etl/jsonl_to_parquet.py:23-29.
+//
+// Layout produced (struct of arrays, one set per event type t in {click, cart, order}):
+//   skey[t][j]   u64   (session - session_min) << 32 | (ts - ts_min)   ascending
+//   aid[t][j]    u32
+//   xrank[t][0/1][j] u32  number of type-(t+1)%3 / (t+2)%3 events that precede event j in the
+//                         combined (session, ts) order = where a window search into that other
+//                         type starts.
+// Because each type is sorted by (session, ts), "same session and |dt| <= W" is one contiguous index
+// range per source event: this is the CSR-by-session the expansion kernel walks.
+#include "internal.cuh"
+#include "scan.cuh"
+
+struct EvStats {
+    int smin, smax, tmin, tmax, amin, amax;
+    unsigned int bad_type;     // some type outside 0..2
+    unsigned int unsorted;     // some adjacent row pair out of (session, ts) order
+    unsigned long long n_type[3];
+};
+
+__global__ void ev_stats_init_kernel(EvStats* st) {
+    st->smin = st->tmin = st->amin = 2147483647;
+    st->smax = st->tmax = st->amax = -2147483647 - 1;
+    st->bad_type = 0; st->unsorted = 0;
+    st->n_type[0] = st->n_type[1] = st->n_type[2] = 0;
+}
+
+__global__ void __launch_bounds__(256) ev_stats_kernel(const int32_t* __restrict__ session,
+                                                       const int32_t* __restrict__ aid,
+                                                       const int32_t* __restrict__ ts,
+                                                       const int8_t* __restrict__ type, int64_t n,
+                                                       EvStats* st) {
+    int smin = 2147483647, smax = -2147483647 - 1, tmin = smin, tmax = smax, amin = smin, amax = smax;
+    unsigned bad = 0, uns = 0;
+    unsigned c0 = 0, c1 = 0, c2 = 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int s = session[i], t = ts[i], a = aid[i], y = type[i];
+        smin = min(smin, s); smax = max(smax, s);
+        tmin = min(tmin, t); tmax = max(tmax, t);
+        amin = min(amin, a); amax = max(amax, a);
+        if (y < 0 || y > 2) bad = 1;
+        c0 += (y == 0); c1 += (y == 1); c2 += (y == 2);
+        if (i > 0) {
+            const int ps = session[i - 1], pt = ts[i - 1];
+            if (ps > s || (ps == s && pt > t)) uns = 1;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        smin = min(smin, __shfl_xor_sync(0xffffffffu, smin, o));
+        smax = max(smax, __shfl_xor_sync(0xffffffffu, smax, o));
+        tmin = min(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
+        tmax = max(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+        amin = min(amin, __shfl_xor_sync(0xffffffffu, amin, o));
+        amax = max(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+        uns |= __shfl_xor_sync(0xffffffffu, uns, o);
+        c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+        c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+        c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&st->smin, smin); atomicMax(&st->smax, smax);
+        atomicMin(&st->tmin, tmin); atomicMax(&st->tmax, tmax);
+        atomicMin(&st->amin, amin); atomicMax(&st->amax, amax);
+        if (bad) atomicOr(&st->bad_type, 1u);
+        if (uns) atomicOr(&st->unsorted, 1u);
+        if (c0) atomicAdd(&st->n_type[0], (unsigned long long)c0);
+        if (c1) atomicAdd(&st->n_type[1], (unsigned long long)c1);
+        if (c2) atomicAdd(&st->n_type[2], (unsigned long long)c2);
+    }
+}
+
+// skey[i] and the identity permutation
+__global__ void __launch_bounds__(256) ev_make_keys_kernel(const int32_t* __restrict__ session,
+                                                           const int32_t* __restrict__ ts, int64_t n,
+                                                           int smin, int tmin, u64* __restrict__ skey,
+                                                           u32* __restrict__ idx) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u64 s = (u64)((int64_t)session[i] - (int64_t)smin);
+    const u64 t = (u64)((int64_t)ts[i] - (int64_t)tmin);
+    skey[i] = (s << 32) | t;
+    if (idx) idx[i] = (u32)i;
+}
+
+// bring aid/type into sorted order
+__global__ void __launch_bounds__(256) ev_gather_kernel(const u32* __restrict__ idx,
+                                                        const int32_t* __restrict__ aid,
+                                                        const int8_t* __restrict__ type, int64_t n,
+                                                        u32* __restrict__ aid_s, int8_t* __restrict__ type_s) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u32 j = idx[i];
+    aid_s[i] = (u32)aid[j];
+    type_s[i] = type[j];
+}
+
+// Scan functor: drop exact duplicates, split by type, record cross-type ranks.
+struct SplitByType {
+    static constexpr int NC = 3;
+    const u64* skey;        // sorted
+    const u32* aid;         // in sorted order
+    const int8_t* type;     // in sorted order
+    TypeArray out[3];
+    // An event is a duplicate iff an EARLIER row of its equal-(session, ts) run has the same aid and
+    // type; runs are short (mostly 1), so the backward walk is O(1) amortised.
+    __device__ bool keep(int64_t i) const {
+        const u64 k = skey[i];
+        const u32 a = aid[i];
+        const int8_t y = type[i];
+        for (int64_t j = i - 1; j >= 0 && skey[j] == k; --j)
+            if (aid[j] == a && type[j] == y) return false;
+        return true;
+    }
+    __device__ u64 value(int64_t i) const { return keep(i) ? (1ull << (21 * (int)type[i])) : 0ull; }
+    __device__ void apply(int64_t i, u64 v, const u64* pre) const {
+        if (!v) return;
+        const int t = type[i];
+        const u64 pos = pre[t];
+        out[t].skey[pos] = skey[i];
+        out[t].aid[pos] = aid[i];
+        out[t].xrank[0][pos] = (u32)pre[(t + 1) % 3];
+        out[t].xrank[1][pos] = (u32)pre[(t + 2) % 3];
+    }
+};
+
+static int bit_width_u64(u64 v) {
+    int b = 0;
+    while (v) { ++b; v >>= 1; }
+    return b;
+}
+
+void free_events(ottocov_ctx* ctx) {
+    for (int t = 0; t < 3; ++t) {
+        dev_free(ctx, ctx->ta[t].skey);
+        dev_free(ctx, ctx->ta[t].aid);
+        dev_free(ctx, ctx->ta[t].xrank[0]);
+        dev_free(ctx, ctx->ta[t].xrank[1]);
+        ctx->ta[t] = TypeArray();
+    }
+    ctx->loaded = false;
+}
+
+void load_events_impl(ottocov_ctx* ctx, const int32_t* session, const int32_t* aid,
+                      const int32_t* ts, const int8_t* type, int64_t n, int where) {
+    free_events(ctx);
+    ottocov_events_info& info = ctx->info;
+    memset(&info, 0, sizeof(info));
+    info.n_rows_in = n;
+    if (n == 0) {
+        info.was_sorted = 1;
+        ctx->loaded = true;
+        return;
+    }
+    if (n >= (int64_t)0xFFFFFFFFll) COV_THROW(OTTOCOV_ERR_ARG, "at most 2^32-2 rows per load (got %lld)", (long long)n);
+
+    // -- columns onto the device -----------------------------------------------------------------
+    DevBuf<int32_t> d_session, d_aid, d_ts;
+    DevBuf<int8_t> d_type;
+    if (where == OTTOCOV_HOST) {
+        d_session.alloc(ctx, n); d_aid.alloc(ctx, n); d_ts.alloc(ctx, n); d_type.alloc(ctx, n);
+        ctx->begin(OTTOCOV_K_LOAD);
+        CUDA_CHECK(cudaMemcpyAsync(d_session.p, session, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_CHECK(cudaMemcpyAsync(d_aid.p, aid, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_CHECK(cudaMemcpyAsync(d_ts.p, ts, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_CHECK(cudaMemcpyAsync(d_type.p, type, n, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->end(OTTOCOV_K_LOAD, 13.0 * n);
+        ctx->stats[OTTOCOV_K_LOAD].launches -= 1;   // copies, not kernels
+        session = d_session.p; aid = d_aid.p; ts = d_ts.p; type = d_type.p;
+    }
+
+    // -- validate + ranges + sortedness ------------------------------------------------------------
+    DevBuf<EvStats> d_st(ctx, 1);
+    COV_LAUNCH(ctx, OTTOCOV_K_MISC, 0, ev_stats_init_kernel, 1, 1, 0, d_st.p);
+    {
+        int grid = (int)imin64(ceil_div64(n, 256), (int64_t)ctx->num_sms * 16);
+        COV_LAUNCH(ctx, OTTOCOV_K_LOAD, 13.0 * n, ev_stats_kernel, grid, 256, 0, session, aid, ts, type, n, d_st.p);
+    }
+    EvStats st;
+    CUDA_CHECK(cudaMemcpyAsync(&st, d_st.p, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (st.bad_type) COV_THROW(OTTOCOV_ERR_DATA, "event type outside {0,1,2}");
+    if (st.amin < 0) COV_THROW(OTTOCOV_ERR_DATA, "negative aid %d", st.amin);
+    info.session_min = st.smin; info.session_max = st.smax;
+    info.ts_min = st.tmin; info.ts_max = st.tmax;
+    info.aid_max = st.amax;
+    info.aid_bits = bit_width_u64((u64)st.amax);
+    if (info.aid_bits == 0) info.aid_bits = 1;
+    info.was_sorted = st.unsorted ? 0 : 1;
+
+    // -- (session, ts) keys; sort if the rows are not already in that order ------------------------
+    DevBuf<u64> skey(ctx, n), skey_alt;
+    DevBuf<u32> idx, idx_alt, aid_sorted;
+    DevBuf<int8_t> type_sorted;
+    const unsigned g1 = (unsigned)ceil_div64(n, 256);
+    const u32* aid_s;
+    const int8_t* type_s;
+    u64* skey_p = skey.p;
+    if (st.unsorted) {
+        idx.alloc(ctx, n); idx_alt.alloc(ctx, n); skey_alt.alloc(ctx, n);
+        COV_LAUNCH(ctx, OTTOCOV_K_LOAD, 20.0 * n, ev_make_keys_kernel, g1, 256, 0, session, ts, n, st.smin, st.tmin, skey.p, idx.p);
+        BitField f[2];
+        f[0].lo = 0;  f[0].hi = bit_width_u64((u64)((int64_t)st.tmax - (int64_t)st.tmin));
+        f[1].lo = 32; f[1].hi = 32 + bit_width_u64((u64)((int64_t)st.smax - (int64_t)st.smin));
+        u64* k = skey.p; u64* ka = skey_alt.p; u32* v = idx.p; u32* va = idx_alt.p;
+        radix_sort_pairs(ctx, k, ka, v, va, n, f, 2);
+        skey_p = k;
+        aid_sorted.alloc(ctx, n); type_sorted.alloc(ctx, n);
+        COV_LAUNCH(ctx, OTTOCOV_K_LOAD, 14.0 * n, ev_gather_kernel, g1, 256, 0, v, aid, type, n, aid_sorted.p, type_sorted.p);
+        aid_s = aid_sorted.p; type_s = type_sorted.p;
+    } else {
+        COV_LAUNCH(ctx, OTTOCOV_K_LOAD, 16.0 * n, ev_make_keys_kernel, g1, 256, 0, session, ts, n, st.smin, st.tmin, skey.p, (u32*)nullptr);
+        aid_s = reinterpret_cast<const u32*>(aid); type_s = type;
+    }
+
+    // -- dedup + split by type (capacity = per-type row counts before dedup) -----------------------
+    SplitByType f;
+    f.skey = skey_p; f.aid = aid_s; f.type = type_s;
+    DevBuf<u64> o_skey[3];
+    DevBuf<u32> o_aid[3], o_x0[3], o_x1[3];
+    for (int t = 0; t < 3; ++t) {
+        const size_t cap = (size_t)st.n_type[t];
+        o_skey[t].alloc(ctx, cap); o_aid[t].alloc(ctx, cap); o_x0[t].alloc(ctx, cap); o_x1[t].alloc(ctx, cap);
+        f.out[t].skey = o_skey[t].p; f.out[t].aid = o_aid[t].p;
+        f.out[t].xrank[0] = o_x0[t].p; f.out[t].xrank[1] = o_x1[t].p;
+        f.out[t].n = 0;
+    }
+    u64 totals[3];
+    scan_apply(ctx, OTTOCOV_K_LOAD, f, n, totals, 2.0 * 13.0 * n + 20.0 * n);
+    for (int t = 0; t < 3; ++t) {
+        ctx->ta[t].skey = o_skey[t].take();
+        ctx->ta[t].aid = o_aid[t].take();
+        ctx->ta[t].xrank[0] = o_x0[t].take();
+        ctx->ta[t].xrank[1] = o_x1[t].take();
+        ctx->ta[t].n = (int64_t)totals[t];
+        info.n_by_type[t] = (int64_t)totals[t];
+    }
+    info.n_events = (int64_t)(totals[0] + totals[1] + totals[2]);
+    ctx->loaded = true;
+}

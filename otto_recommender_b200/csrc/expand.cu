@@ -1,0 +1,315 @@
+// expand.cu -- pair expansion + reduce-by-key for ONE co-event kind.
+//
+// Replaces self_merge (model/count_co_events.py:17-38: join on session, drop the event joined with
+// itself, |ts_next - ts| <= 24 h) and one iteration of count_co_events' loop (:64-72: type filter,
+// |dt| <= W, groupby(aid, aid_next).count()).  The reference materialises all n^2 joined rows per
+// session and filters them; here nothing is rejected:
+//
+//   window kernel   one thread per source event (type == type_this).  Target events of one type are
+//                   sorted by (session, ts), so the in-window targets are ONE index range [lo, hi);
+//                   found by galloping + binary search outwards from the source's own insertion rank
+//                   (xrank).  Emits lo and cnt = hi - lo (minus 1 when source and target type agree:
+//                   the event itself lies in its own window and is the only excluded row, :23-27).
+//   scan            exclusive scan of cnt -> exact output offsets; zero-count sources are compacted
+//                   away so every record owns >= 1 output.
+//   tile search     one thread per 2048-output tile finds the first record of the tile.
+//   expand kernel   output-balanced: each CTA writes exactly one tile of packed u64 keys
+//                   (aid << 32 | aid_next), whatever the session lengths are (a 498-event session and
+//                   a 2-event session cost the same per emitted pair).  Threads write 2 adjacent keys
+//                   with one 128-bit store; a warp store covers 512 contiguous bytes.
+//   sort + RLE      radix_sort.cu, reduce.cu.
+// If the pair count exceeds the budget, the output space is cut into chunks (any cut point works,
+// tiles are addressed by output offset) and the partial tables are merged at the end.
+#include "internal.cuh"
+#include "scan.cuh"
+
+constexpr int EX_THREADS = 256;
+constexpr int EX_TILE = 2048;
+constexpr int EX_ITERS = EX_TILE / (2 * EX_THREADS);
+
+// first index in [0, start] with keys[idx] >= bound, given keys[i] >= bound for all i >= start
+__device__ __forceinline__ u32 lower_bound_back(const u64* __restrict__ keys, u32 start, u64 bound) {
+    u32 hi = start, lo, step = 1;
+    while (true) {
+        if (hi == 0) return 0;
+        const u32 probe = (hi >= step) ? hi - step : 0;
+        if (keys[probe] >= bound) { hi = probe; step <<= 1; }
+        else { lo = probe; break; }
+    }
+    while (hi - lo > 1) {               // keys[lo] < bound <= keys[hi]
+        const u32 mid = lo + ((hi - lo) >> 1);
+        if (keys[mid] >= bound) hi = mid; else lo = mid;
+    }
+    return hi;
+}
+
+// first index in [start, n] with keys[idx] > bound, given keys[i] <= bound for all i < start
+__device__ __forceinline__ u32 upper_bound_fwd(const u64* __restrict__ keys, u32 n, u32 start, u64 bound) {
+    u32 lo = start, hi, step = 1;
+    while (true) {
+        if (lo >= n) return n;
+        const u32 probe = (n - lo > step) ? lo + step - 1 : n - 1;
+        if (keys[probe] <= bound) { lo = probe + 1; step <<= 1; }
+        else { hi = probe; break; }
+    }
+    while (lo < hi) {                   // everything < lo is <= bound; keys[hi] > bound
+        const u32 mid = lo + ((hi - lo) >> 1);
+        if (keys[mid] <= bound) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// per source event: target range start and count
+__global__ void __launch_bounds__(256) window_kernel(const u64* __restrict__ src_key,
+                                                     const u32* __restrict__ src_xrank,   // nullptr => same array
+                                                     int64_t n_src, const u64* __restrict__ tgt_key,
+                                                     u32 n_tgt, u32 window, u32* __restrict__ lo_out,
+                                                     u32* __restrict__ cnt_out) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_src) return;
+    const u64 k = src_key[j];
+    const u32 t = (u32)k;
+    const u64 s = k & 0xFFFFFFFF00000000ull;
+    const u64 lower = s | (u64)(t > window ? t - window : 0u);
+    const u64 upper = s | (u64)(t > 0xFFFFFFFFu - window ? 0xFFFFFFFFu : t + window);
+    const bool self = (src_xrank == nullptr);
+    const u32 start = self ? (u32)j : src_xrank[j];
+    const u32 lo = lower_bound_back(tgt_key, start, lower);
+    const u32 hi = upper_bound_fwd(tgt_key, n_tgt, start, upper);
+    lo_out[j] = lo;
+    cnt_out[j] = hi - lo - (self ? 1u : 0u);
+}
+
+// compaction of the non-empty sources into records (src, lo, output offset)
+struct WindowRecords {
+    static constexpr int NC = 2;
+    const u32* lo;
+    const u32* cnt;
+    u32* rec_src;
+    u32* rec_lo;
+    u64* rec_off;
+    __device__ u64 value(int64_t j) const {
+        const u64 c = cnt[j];
+        return c | ((u64)(c != 0) << 52);
+    }
+    __device__ void apply(int64_t j, u64 v, const u64* pre) const {
+        if (!v) return;
+        const u64 r = pre[1];
+        rec_src[r] = (u32)j;
+        rec_lo[r] = lo[j];
+        rec_off[r] = pre[0];
+    }
+};
+
+// tile t of a launch starts at output offset out_begin + t * EX_TILE: last record with off <= that
+__global__ void __launch_bounds__(256) tile_search_kernel(const u64* __restrict__ rec_off, int64_t n_rec,
+                                                          u64 out_begin, u64 out_end, int64_t n_tiles,
+                                                          u32* __restrict__ tile_rec) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > n_tiles) return;
+    u64 o = out_begin + (u64)t * EX_TILE;
+    if (o > out_end - 1) o = out_end - 1;        // entry n_tiles = record of the last output
+    int64_t lo = 0, hi = n_rec;                  // first record with off > o
+    while (lo < hi) {
+        const int64_t mid = lo + ((hi - lo) >> 1);
+        if (rec_off[mid] <= o) lo = mid + 1; else hi = mid;
+    }
+    tile_rec[t] = (u32)(lo - 1);
+}
+
+template <bool SELF>
+__global__ void __launch_bounds__(EX_THREADS)
+expand_kernel(const u32* __restrict__ rec_src, const u32* __restrict__ rec_lo,
+              const u64* __restrict__ rec_off, const u32* __restrict__ tile_rec,
+              const u32* __restrict__ aid_src, const u32* __restrict__ aid_tgt, u64 out_begin,
+              u64 out_end, u64* __restrict__ dst) {
+    __shared__ u32 s_off[EX_TILE + 1];
+    __shared__ u32 s_lo[EX_TILE + 1];
+    __shared__ u32 s_aid[EX_TILE + 1];
+    __shared__ u32 s_src[SELF ? EX_TILE + 1 : 1];
+
+    const u64 o0 = out_begin + (u64)blockIdx.x * EX_TILE;
+    const u32 n_out = (u32)min((u64)EX_TILE, out_end - o0);
+    const u32 r0 = tile_rec[blockIdx.x];
+    const u32 r1 = tile_rec[blockIdx.x + 1];          // record of the tile's last output (clamped)
+    // records that own outputs of this tile: r0 .. r_last, r_last = record of output o0 + n_out - 1
+    u32 r_last = r1;
+    if ((u64)blockIdx.x * EX_TILE + EX_TILE + out_begin < out_end) {
+        // tile_rec[b+1] is the record of the NEXT tile's first output; it owns outputs of this
+        // tile only if it starts before that output
+        if (rec_off[r1] >= o0 + n_out) r_last = r1 - 1;
+    }
+    const u32 n_rec = r_last - r0 + 1;                // <= EX_TILE (offsets strictly increase)
+
+    for (u32 j = threadIdx.x; j < n_rec; j += EX_THREADS) {
+        const u32 r = r0 + j;
+        const u64 off = rec_off[r];
+        const u32 src = rec_src[r];
+        u32 lo = rec_lo[r];
+        u32 rel;
+        if (off <= o0) { rel = 0; lo += (u32)(o0 - off); }   // only j == 0: skip outputs of earlier tiles
+        else rel = (u32)(off - o0);
+        s_off[j] = rel;
+        s_lo[j] = lo;
+        s_aid[j] = aid_src[src];
+        if (SELF) s_src[j] = src;
+    }
+    __syncthreads();
+
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+    u64* tile_dst = dst + (size_t)blockIdx.x * EX_TILE;
+#pragma unroll
+    for (int it = 0; it < EX_ITERS; ++it) {
+        const u32 k = (u32)it * (2 * EX_THREADS) + 2 * threadIdx.x;
+        if (k >= n_out) continue;
+        // last record with s_off <= k
+        u32 lo = 0, hi = n_rec;
+        while (hi - lo > 1) {
+            const u32 mid = (lo + hi) >> 1;
+            if (s_off[mid] <= k) lo = mid; else hi = mid;
+        }
+        u32 j = lo;
+        u32 tgt = s_lo[j] + (k - s_off[j]);
+        if (SELF) tgt += (tgt >= s_src[j]);
+        const u64 key0 = ((u64)s_aid[j] << 32) | (u64)aid_tgt[tgt];
+        if (k + 1 < n_out) {
+            if (j + 1 < n_rec && s_off[j + 1] <= k + 1) ++j;
+            u32 tgt1 = s_lo[j] + (k + 1 - s_off[j]);
+            if (SELF) tgt1 += (tgt1 >= s_src[j]);
+            const u64 key1 = ((u64)s_aid[j] << 32) | (u64)aid_tgt[tgt1];
+            if (vec_ok) {
+                ulonglong2 v; v.x = key0; v.y = key1;
+                __stcs(reinterpret_cast<ulonglong2*>(tile_dst + k), v);
+            } else {
+                __stcs(tile_dst + k, key0);
+                __stcs(tile_dst + k + 1, key1);
+            }
+        } else {
+            __stcs(tile_dst + k, key0);
+        }
+    }
+}
+
+struct Segment {
+    int tgt_type;
+    bool self;
+    u64 n_pairs = 0;
+    u64 n_rec = 0;
+    DevBuf<u32> rec_src, rec_lo;
+    DevBuf<u64> rec_off;
+};
+
+static ottocov_table* make_empty_table(int aid_bits) {
+    ottocov_table* t = new ottocov_table();
+    t->aid_bits = aid_bits;
+    return t;
+}
+
+ottocov_table* count_impl(ottocov_ctx* ctx, const ottocov_spec* spec) {
+    if (!ctx->loaded) COV_THROW(OTTOCOV_ERR_STATE, "ottocov_count before ottocov_load_events");
+    if (spec->type_this < 0 || spec->type_this > 2) COV_THROW(OTTOCOV_ERR_ARG, "type_this must be 0..2");
+    if (spec->next_mask == 0 || spec->next_mask > 7) COV_THROW(OTTOCOV_ERR_ARG, "next_mask must be 1..7");
+    if (spec->window < 0) COV_THROW(OTTOCOV_ERR_ARG, "window must be >= 0");
+    const int A = spec->type_this;
+    const u32 W = (u32)(spec->window > 86400 ? 86400 : spec->window);   // count_co_events.py:33-36
+    const TypeArray& src = ctx->ta[A];
+    const int aid_bits = ctx->info.aid_bits > 0 ? ctx->info.aid_bits : 1;
+    ottocov_count_info& ci = ctx->last_count;
+    memset(&ci, 0, sizeof(ci));
+
+    // ---- window + records per target type ---------------------------------------------------------
+    std::vector<Segment*> segs;
+    struct SegGuard { std::vector<Segment*>& v; ~SegGuard() { for (auto* s : v) delete s; } } guard{segs};
+    u64 P = 0;
+    for (int B = 0; B < 3; ++B) {
+        if (!((spec->next_mask >> B) & 1)) continue;
+        const TypeArray& tgt = ctx->ta[B];
+        if (src.n == 0 || tgt.n == 0) continue;
+        Segment* sg = new Segment();
+        segs.push_back(sg);
+        sg->tgt_type = B;
+        sg->self = (A == B);
+        const u32* xr = nullptr;
+        if (!sg->self) xr = (B == (A + 1) % 3) ? src.xrank[0] : src.xrank[1];
+        DevBuf<u32> lo(ctx, src.n), cnt(ctx, src.n);
+        COV_LAUNCH(ctx, OTTOCOV_K_WINDOW, 20.0 * src.n, window_kernel, (unsigned)ceil_div64(src.n, 256), 256, 0,
+                   src.skey, xr, src.n, tgt.skey, (u32)tgt.n, W, lo.p, cnt.p);
+        sg->rec_src.alloc(ctx, src.n); sg->rec_lo.alloc(ctx, src.n); sg->rec_off.alloc(ctx, src.n);
+        WindowRecords f;
+        f.lo = lo.p; f.cnt = cnt.p;
+        f.rec_src = sg->rec_src.p; f.rec_lo = sg->rec_lo.p; f.rec_off = sg->rec_off.p;
+        u64 tot[2];
+        scan_apply(ctx, OTTOCOV_K_WINDOW, f, src.n, tot, 2.0 * 4.0 * src.n + 8.0 * src.n + 16.0 * src.n);
+        sg->n_pairs = tot[0];
+        sg->n_rec = tot[1];
+        P += tot[0];
+    }
+    ci.n_pairs = (int64_t)P;
+    if (P == 0) { ci.n_chunks = 0; return make_empty_table(aid_bits); }
+
+    // ---- chunking by pair budget ----------------------------------------------------------------------
+    u64 budget = spec->pair_budget > 0 ? (u64)spec->pair_budget : 0;
+    if (budget == 0) {
+        size_t free_b = 0, total_b = 0;
+        CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+        // pool memory we already hold counts as free for our purposes; be conservative: 16 B per
+        // pair for the double buffer plus <= 12 B per pair for the reduced table
+        budget = (u64)((double)free_b * 0.6 / 28.0);
+        if (budget < (1u << 20)) budget = 1u << 20;
+    }
+    budget = (budget / EX_TILE) * EX_TILE;
+    if (budget == 0) budget = EX_TILE;
+
+    std::vector<ottocov_table*> partials;
+    struct PartGuard {
+        ottocov_ctx* c; std::vector<ottocov_table*>& v;
+        ~PartGuard() { for (auto* t : v) { dev_free(c, t->keys); dev_free(c, t->count); delete t; } }
+    } pguard{ctx, partials};
+
+    BitField fields[2] = {{0, aid_bits}, {32, 32 + aid_bits}};
+    for (u64 c0 = 0; c0 < P; c0 += budget) {
+        const u64 c1 = (c0 + budget < P) ? c0 + budget : P;
+        const u64 cn = c1 - c0;
+        DevBuf<u64> keys(ctx, cn), alt(ctx, cn);
+        u64 seg_start = 0;
+        for (Segment* sg : segs) {
+            const u64 seg_end = seg_start + sg->n_pairs;
+            const u64 a = c0 > seg_start ? c0 : seg_start;
+            const u64 b = c1 < seg_end ? c1 : seg_end;
+            if (a < b) {
+                const u64 ob = a - seg_start, oe = b - seg_start;       // segment-local output range
+                const int64_t n_tiles = ceil_div64((int64_t)(oe - ob), EX_TILE);
+                DevBuf<u32> tile_rec(ctx, n_tiles + 1);
+                COV_LAUNCH(ctx, OTTOCOV_K_EXPAND, 0, tile_search_kernel, (unsigned)ceil_div64(n_tiles + 1, 256), 256, 0,
+                           sg->rec_off.p, (int64_t)sg->n_rec, ob, oe, n_tiles, tile_rec.p);
+                const TypeArray& tgt = ctx->ta[sg->tgt_type];
+                u64* dst = keys.p + (a - c0);
+                const double bytes = 8.0 * (double)(oe - ob);
+                if (sg->self)
+                    COV_LAUNCH(ctx, OTTOCOV_K_EXPAND, bytes, expand_kernel<true>, (unsigned)n_tiles, EX_THREADS, 0,
+                               sg->rec_src.p, sg->rec_lo.p, sg->rec_off.p, tile_rec.p, src.aid, tgt.aid, ob, oe, dst);
+                else
+                    COV_LAUNCH(ctx, OTTOCOV_K_EXPAND, bytes, expand_kernel<false>, (unsigned)n_tiles, EX_THREADS, 0,
+                               sg->rec_src.p, sg->rec_lo.p, sg->rec_off.p, tile_rec.p, src.aid, tgt.aid, ob, oe, dst);
+            }
+            seg_start = seg_end;
+        }
+        u64* k = keys.p; u64* ka = alt.p; u32* v = nullptr; u32* va = nullptr;
+        ci.sort_passes = radix_sort_pairs(ctx, k, ka, v, va, (int64_t)cn, fields, 2);
+        ottocov_table* part = new ottocov_table();
+        part->aid_bits = aid_bits;
+        partials.push_back(part);
+        reduce_sorted(ctx, k, nullptr, (int64_t)cn, &part->keys, &part->count, &part->n);
+        ci.n_chunks += 1;
+    }
+
+    ottocov_table* result;
+    if (partials.size() == 1) {
+        result = partials[0];
+        partials.clear();
+    } else {
+        result = merge_tables_impl(ctx, partials.data(), (int)partials.size());
+    }
+    ci.n_unique = result->n;
+    return result;
+}

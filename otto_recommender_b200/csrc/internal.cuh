@@ -1,0 +1,236 @@
+// internal.cuh -- shared declarations of libottocov.so (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include <stdexcept>
+#include "../../include/ottocov.h"
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+// ---- errors: C++ exceptions inside, status codes at the ABI ------------------------------------
+struct CovError {
+    int code;
+    std::string msg;
+};
+
+#define COV_THROW(code_, ...)                                           \
+    do {                                                                \
+        char _b[512];                                                   \
+        snprintf(_b, sizeof(_b), __VA_ARGS__);                          \
+        throw CovError{(code_), std::string(_b)};                       \
+    } while (0)
+
+#define CUDA_CHECK(expr)                                                                   \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            int _c = (_e == cudaErrorMemoryAllocation) ? OTTOCOV_ERR_NOMEM : OTTOCOV_ERR_CUDA; \
+            COV_THROW(_c, "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,             \
+                      cudaGetErrorString(_e));                                             \
+        }                                                                                  \
+    } while (0)
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int64_t imin64(int64_t a, int64_t b) { return a < b ? a : b; }
+
+// ---- per-type sorted event arrays (the CSR-by-session layout, SoA) -------------------------------
+// Events of one type, ordered by skey = (session - session_min) << 32 | (ts - ts_min).
+struct TypeArray {
+    u64* skey = nullptr;     // [n] search key
+    u32* aid = nullptr;      // [n]
+    u32* xrank[2] = {nullptr, nullptr};  // [n] insertion rank of this event in type (t+1)%3 / (t+2)%3
+    int64_t n = 0;
+};
+
+struct ProfEvent { int family; cudaEvent_t a, b; };
+
+struct ottocov_table {
+    u64* keys = nullptr;     // [n] sorted, distinct
+    u32* count = nullptr;    // [n]
+    int64_t n = 0;
+    int aid_bits = 32;       // significant bits of both key halves (bounds the radix passes)
+};
+
+struct ottocov_ctx {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = 0;
+    std::string err;
+    // profiling / accounting
+    bool profiling = false;
+    ottocov_kernel_stat stats[OTTOCOV_K_FAMILIES];
+    std::vector<ProfEvent> prof_pending;
+    std::vector<cudaEvent_t> event_pool;
+    // events
+    bool loaded = false;
+    ottocov_events_info info;
+    TypeArray ta[3];
+    ottocov_count_info last_count;
+    // onesweep look-back state (grow-only, epoch-tagged so it is never re-zeroed per pass)
+    u64* sweep_status = nullptr;
+    size_t sweep_status_words = 0;
+    u32 sweep_epoch = 0;
+    u32* sweep_ticket = nullptr;       // [64] tickets, one per pass slot
+    // generic look-back scan state
+    u64* scan_status = nullptr;
+    size_t scan_status_words = 0;
+    u32* scan_ticket = nullptr;
+    // top-k result
+    int topk_k = 0;
+    int64_t topk_n = 0;
+    int32_t* topk_aid_x = nullptr;
+    int32_t* topk_nvalid = nullptr;
+    int32_t* topk_aid_y = nullptr;
+    int32_t* topk_cnt = nullptr;
+
+    void begin(int family);
+    void end(int family, double algo_bytes);
+};
+
+// RAII device buffer on the context's stream-ordered pool.
+template <class T>
+struct DevBuf {
+    ottocov_ctx* ctx = nullptr;
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    DevBuf(ottocov_ctx* c, size_t n_) { alloc(c, n_); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    void alloc(ottocov_ctx* c, size_t n_) {
+        release();
+        ctx = c; n = n_;
+        size_t bytes = (n_ ? n_ : 1) * sizeof(T);
+        cudaError_t e = cudaMallocAsync((void**)&p, bytes, c->stream);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            (void)cudaGetLastError();
+            COV_THROW(e == cudaErrorMemoryAllocation ? OTTOCOV_ERR_NOMEM : OTTOCOV_ERR_CUDA,
+                      "device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        }
+    }
+    T* take() { T* q = p; p = nullptr; n = 0; return q; }   // give ownership away
+    void release() {
+        if (p) { cudaFreeAsync(p, ctx->stream); p = nullptr; }
+        n = 0;
+    }
+    ~DevBuf() { release(); }
+};
+
+static inline void dev_free(ottocov_ctx* ctx, void* p) { if (p) cudaFreeAsync(p, ctx->stream); }
+
+// Launch helper: counts the launch, brackets it with CUDA events when profiling is on.
+#define COV_LAUNCH(ctx_, fam_, bytes_, kern_, grid_, block_, smem_, ...)                      \
+    do {                                                                                      \
+        (ctx_)->begin(fam_);                                                                  \
+        kern_<<<(grid_), (block_), (smem_), (ctx_)->stream>>>(__VA_ARGS__);                  \
+        (ctx_)->end(fam_, (double)(bytes_));                                                  \
+        CUDA_CHECK(cudaGetLastError());                                                       \
+    } while (0)
+
+// ---- device building blocks (implemented in the .cu files) -------------------------------------
+// radix_sort.cu
+struct BitField { int lo, hi; };   // sort on key bits [lo, hi)
+// Sorts n keys (+ optional payload) on the given fields, least significant field first.
+// keys/alt (and vals/valt) are a double buffer; on return `keys`/`vals` point at the sorted data.
+// Returns the number of radix passes it ran.
+int radix_sort_pairs(ottocov_ctx* ctx, u64*& keys, u64*& alt, u32*& vals, u32*& valt, int64_t n,
+                     const BitField* fields, int n_fields);
+
+// scan.cu
+// exclusive scan of n u64 values in place-safe manner (out may alias in); returns nothing; total
+// written to *total_dev (device, may be nullptr)
+void exclusive_scan_u64(ottocov_ctx* ctx, const u64* in, u64* out, int64_t n, u64* total_dev);
+void exclusive_scan_u32(ottocov_ctx* ctx, const u32* in, u32* out, int64_t n, u32* total_dev);
+
+// events.cu
+void load_events_impl(ottocov_ctx* ctx, const int32_t* session, const int32_t* aid,
+                      const int32_t* ts, const int8_t* type, int64_t n, int where);
+void free_events(ottocov_ctx* ctx);
+
+// expand.cu
+ottocov_table* count_impl(ottocov_ctx* ctx, const ottocov_spec* spec);
+
+// reduce.cu
+// sorted keys -> distinct keys + run lengths (vals == nullptr) or summed payload (vals != nullptr)
+void reduce_sorted(ottocov_ctx* ctx, const u64* keys, const u32* vals, int64_t n,
+                   u64** out_keys, u32** out_count, int64_t* n_out);
+ottocov_table* merge_tables_impl(ottocov_ctx* ctx, ottocov_table* const* tabs, int n_tabs);
+ottocov_table* filter_table_impl(ottocov_ctx* ctx, const ottocov_table* t, u32 min_count);
+void fetch_table_impl(ottocov_ctx* ctx, const ottocov_table* t, int order, int64_t head,
+                      int32_t* aid, int32_t* aid_next, int32_t* count, int64_t cap, int where,
+                      int64_t* n_out);
+int64_t table_total_impl(ottocov_ctx* ctx, const ottocov_table* t);
+ottocov_table* table_from_arrays_impl(ottocov_ctx* ctx, const int32_t* aid, const int32_t* aid_next,
+                                      const u32* count, int64_t n, int where);
+ottocov_table* table_from_packed_impl(ottocov_ctx* ctx, const u64* keys, const u32* count,
+                                      int64_t n, int where);
+void partition_table_impl(ottocov_ctx* ctx, const ottocov_table* t, int n_ranks, u64* keys_out,
+                          u32* count_out, int64_t* rows_per_dest);
+
+// topk.cu
+void topk_impl(ottocov_ctx* ctx, const ottocov_table* t, int k);
+void free_topk(ottocov_ctx* ctx);
+
+// ---- small device helpers -------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ u32 lanemask_lt() {
+    u32 m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+__device__ __forceinline__ u64 ld_volatile_u64(const u64* p) {
+    u64 v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u64(u64* p, u64 v) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// streaming (evict-first) accessors for data touched once per pass
+__device__ __forceinline__ u64 ld_stream_u64(const u64* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream_u64(u64* p, u64 v) { __stcs(p, v); }
+
+__device__ __forceinline__ u32 hash_dest(u32 aid, u32 n_ranks) {
+    u32 h = aid * 0x9E3779B1u;
+    h ^= h >> 15;
+    return h % n_ranks;
+}
+
+// Block-wide exclusive scan of one value per thread (blockDim.x == THREADS, multiple of 32).
+// `s_warp` must hold THREADS/32 + 1 elements of T.  Returns the exclusive prefix; *total gets the
+// block sum (same value in every thread).  Contains three __syncthreads().
+template <class T, int THREADS>
+__device__ __forceinline__ T block_exclusive_scan(T v, T* s_warp, T* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        T t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    __syncthreads();                                // s_warp may still be read from a previous call
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        constexpr int NW = THREADS / 32;
+        T w = (lane < NW) ? s_warp[lane] : T(0);
+        T winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            T t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        if (lane < NW) s_warp[lane] = winc - w;     // exclusive warp offsets
+        if (lane == NW - 1) s_warp[NW] = winc;      // block total
+    }
+    __syncthreads();
+    T res = s_warp[warp] + inc - v;
+    *total = s_warp[THREADS / 32];
+    return res;
+}
+#endif

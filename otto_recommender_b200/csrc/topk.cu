@@ -1,0 +1,128 @@
+// topk.cu -- segmented top-K per aid over a key-sorted (aid, aid_next, count) table.
+//
+// Replaces sort(['aid']) + rank('ordinal', reverse=True).over('aid') <= first_n of the consumer
+// (model/retrieve.py:41-47; first_n = 10/10/20/20/20, config.py:90-96).  The reference's order among
+// equal counts is whatever its upstream hash group-by left; the canonical rule here
+// is count descending, then aid_next ascending, which makes the result a pure function of the table.
+//
+// Rows of one aid are contiguous (the table is sorted by key).  One warp owns one aid segment and
+// streams it 32 rows at a time, keeping the running top-32 sorted across its lanes: a batch is
+// looked at only if some row beats the current K-th best (one ballot); then the batch is bitonic-
+// sorted across lanes and bitonic-merged into the running list.  The composite compare key
+// (count << 32 | ~aid_next) is unique inside a segment, so there are no ties to break.
+#include "internal.cuh"
+#include "scan.cuh"
+
+struct SegmentHeads {
+    static constexpr int NC = 1;
+    const u64* keys;
+    u64* seg_start;
+    __device__ u64 value(int64_t i) const {
+        return (i == 0 || (keys[i] >> 32) != (keys[i - 1] >> 32)) ? 1ull : 0ull;
+    }
+    __device__ void apply(int64_t i, u64 v, const u64* pre) const {
+        if (v && seg_start) seg_start[pre[0]] = (u64)i;
+    }
+};
+
+__device__ __forceinline__ u64 umax64(u64 a, u64 b) { return a > b ? a : b; }
+__device__ __forceinline__ u64 umin64(u64 a, u64 b) { return a < b ? a : b; }
+
+// full bitonic sort of one value per lane, descending by lane
+__device__ __forceinline__ u64 warp_sort_desc(u64 v, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const u64 p = __shfl_xor_sync(0xffffffffu, v, j);
+            const bool desc_block = ((lane & k) == 0);     // k == 32: always true -> final order descending
+            const bool lower = ((lane & j) == 0);
+            v = (lower == desc_block) ? umax64(v, p) : umin64(v, p);
+        }
+    }
+    return v;
+}
+
+// lanes hold a bitonic sequence -> descending by lane
+__device__ __forceinline__ u64 warp_bitonic_merge_desc(u64 v, int lane) {
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) {
+        const u64 p = __shfl_xor_sync(0xffffffffu, v, j);
+        v = ((lane & j) == 0) ? umax64(v, p) : umin64(v, p);
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(256) topk_kernel(const u64* __restrict__ keys, const u32* __restrict__ count,
+                                                   const u64* __restrict__ seg_start, int64_t n_seg, int64_t n_rows,
+                                                   int k, int32_t* __restrict__ out_aid_x,
+                                                   int32_t* __restrict__ out_nvalid, int32_t* __restrict__ out_aid_y,
+                                                   int32_t* __restrict__ out_cnt) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t s = warp0; s < n_seg; s += n_warps) {
+        const int64_t a = (int64_t)seg_start[s];
+        const int64_t b = (s + 1 < n_seg) ? (int64_t)seg_start[s + 1] : n_rows;
+        u64 best = 0;                                   // lane l: l-th largest so far (0 = empty)
+        for (int64_t i = a; i < b; i += 32) {
+            const int64_t r = i + lane;
+            u64 c = 0;
+            if (r < b) c = ((u64)count[r] << 32) | (u64)(0xFFFFFFFFu - (u32)(keys[r] & 0xFFFFFFFFu));
+            const u64 kth = __shfl_sync(0xffffffffu, best, k - 1);
+            if (__ballot_sync(0xffffffffu, c > kth) == 0) continue;
+            c = warp_sort_desc(c, lane);
+            const u64 rev = __shfl_sync(0xffffffffu, c, 31 - lane);
+            best = warp_bitonic_merge_desc(umax64(best, rev), lane);
+        }
+        const int64_t len = b - a;
+        const int nv = (int)(len < k ? len : k);
+        if (lane == 0) {
+            out_aid_x[s] = (int32_t)(keys[a] >> 32);
+            out_nvalid[s] = nv;
+        }
+        if (lane < k) {
+            const bool ok = lane < nv;
+            out_aid_y[s * k + lane] = ok ? (int32_t)(0xFFFFFFFFu - (u32)(best & 0xFFFFFFFFu)) : -1;
+            out_cnt[s * k + lane] = ok ? (int32_t)min((u64)0x7FFFFFFFull, best >> 32) : 0;
+        }
+    }
+}
+
+void free_topk(ottocov_ctx* ctx) {
+    dev_free(ctx, ctx->topk_aid_x); dev_free(ctx, ctx->topk_nvalid);
+    dev_free(ctx, ctx->topk_aid_y); dev_free(ctx, ctx->topk_cnt);
+    ctx->topk_aid_x = ctx->topk_nvalid = ctx->topk_aid_y = ctx->topk_cnt = nullptr;
+    ctx->topk_n = 0; ctx->topk_k = 0;
+}
+
+void topk_impl(ottocov_ctx* ctx, const ottocov_table* t, int k) {
+    if (k < 1 || k > 32) COV_THROW(OTTOCOV_ERR_ARG, "top-k supports 1 <= k <= 32 (got %d)", k);
+    free_topk(ctx);
+    ctx->topk_k = k;
+    if (t->n == 0) return;
+    SegmentHeads f;
+    f.keys = t->keys; f.seg_start = nullptr;
+    const int64_t n_tiles = ceil_div64(t->n, SCAN_TILE);
+    // count segments first (exact allocation), then materialise their starts
+    u64 n_seg;
+    {
+        DevBuf<u64> sums(ctx, (size_t)n_tiles + 1);
+        COV_LAUNCH(ctx, OTTOCOV_K_TOPK, 8.0 * t->n, (scan_reduce_kernel<SegmentHeads>), (unsigned)n_tiles, SCAN_THREADS, 0,
+                   f, t->n, n_tiles, sums.p);
+        COV_LAUNCH(ctx, OTTOCOV_K_MISC, 16.0 * n_tiles, scan_block_sums_kernel, 1, 1024, 0, sums.p, n_tiles, sums.p + n_tiles);
+        CUDA_CHECK(cudaMemcpyAsync(&n_seg, sums.p + n_tiles, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
+    DevBuf<u64> seg_start(ctx, n_seg);
+    f.seg_start = seg_start.p;
+    scan_apply(ctx, OTTOCOV_K_TOPK, f, t->n, nullptr, 16.0 * t->n + 8.0 * n_seg);
+    DevBuf<int32_t> ax(ctx, n_seg), nv(ctx, n_seg), ay(ctx, n_seg * k), ac(ctx, n_seg * k);
+    const int64_t warps_needed = (int64_t)n_seg;
+    int grid = (int)imin64(ceil_div64(warps_needed, 8), (int64_t)ctx->num_sms * 32);
+    COV_LAUNCH(ctx, OTTOCOV_K_TOPK, 12.0 * t->n + 8.0 * n_seg + 8.0 * k * n_seg, topk_kernel, grid, 256, 0,
+               t->keys, t->count, seg_start.p, (int64_t)n_seg, t->n, k, ax.p, nv.p, ay.p, ac.p);
+    ctx->topk_aid_x = ax.take(); ctx->topk_nvalid = nv.take();
+    ctx->topk_aid_y = ay.take(); ctx->topk_cnt = ac.take();
+    ctx->topk_n = (int64_t)n_seg;
+}

@@ -28,6 +28,9 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
+#endif
 
 #define OTTOCOV_VERSION 100
 
@@ -156,6 +159,9 @@ uint32_t ottocov_hash_dest(uint32_t aid, uint32_t n_ranks);
 int ottocov_sort_u64(ottocov_ctx* ctx, uint64_t* keys_dev, uint32_t* vals_dev, int64_t n,
                      int lo_bit, int hi_bit);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,108 @@
+"""Multi-GPU co-event counting: sessions sharded across ranks, counts re-sharded by hash(aid).
+
+The reference is single-process; this is the one place the path gains a
+collective.  Sessions are independent (pairs never cross a session; parts never split one,
+etl/jsonl_to_parquet.py:35-40) and counts are an associative integer sum keyed by (aid, aid_next),
+so:
+
+    rank r:  load its session shard -> expand -> local reduce-by-key        (no communication)
+             stable partition of the local table by dest = hash(aid) % R    (ottocov_table_partition)
+             all-to-all of (key u64, count u32) records                      (NCCL over NVLink)
+             sort + segmented sum of what it received                        (ottocov_table_from_packed)
+    => rank r owns every row whose aid hashes to r; threshold and top-K are then rank-local, and
+       the union over ranks equals the single-GPU table bit for bit (integer sums commute).
+
+One process per GPU (torch.distributed, backend nccl).  The exchange itself is backend-agnostic
+(`exchange_records`), which is what the world_size-2 gloo tests on CPU exercise.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+def hash_dest(aid: np.ndarray, n_ranks: int) -> np.ndarray:
+    """numpy twin of ottocov_hash_dest (csrc/internal.cuh): dest rank of an aid."""
+    h = (aid.astype(np.uint64) * np.uint64(0x9E3779B1)) & np.uint64(0xFFFFFFFF)
+    h ^= h >> np.uint64(15)
+    return (h % np.uint64(n_ranks)).astype(np.int64)
+
+
+def shard_bounds(session_lengths: np.ndarray, n_ranks: int) -> np.ndarray:
+    """Contiguous session ranges per rank balanced by a pair-work proxy.
+
+    Work per session grows between n (short, window-limited) and n^2 (all events inside the
+    window); n * min(n, 32) tracks the emitted pairs of OTTO-shaped sessions closely enough to
+    balance ranks within a few percent.  Returns R+1 session indices.
+    """
+    n = np.asarray(session_lengths, dtype=np.int64)
+    w = n * np.minimum(n, 32)
+    c = np.concatenate([[0], np.cumsum(w)])
+    targets = c[-1] * np.arange(1, n_ranks) / n_ranks
+    cuts = np.searchsorted(c, targets, side="left")
+    return np.concatenate([[0], cuts, [len(n)]]).astype(np.int64)
+
+
+def exchange_records(send_keys: torch.Tensor, send_cnt: torch.Tensor, rows_per_dest: Sequence[int],
+                     group=None) -> Tuple[torch.Tensor, torch.Tensor, List[int]]:
+    """All-to-all of records already grouped by destination rank.
+
+    send_keys int64 [n], send_cnt int32 [n] (rows of dest 0 first, then dest 1, ...).
+    Returns (recv_keys, recv_cnt, rows_per_source).  Works on CUDA tensors with nccl and on CPU
+    tensors with gloo.
+    """
+    world = dist.get_world_size(group)
+    assert len(rows_per_dest) == world
+    dev = send_keys.device
+    send_sizes = torch.tensor(list(rows_per_dest), dtype=torch.int64, device=dev)
+    recv_sizes = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_to_all_single(recv_sizes, send_sizes, group=group)
+    recv_list = [int(x) for x in recv_sizes.tolist()]
+    send_list = [int(x) for x in rows_per_dest]
+    n_recv = sum(recv_list)
+    recv_keys = torch.empty(n_recv, dtype=send_keys.dtype, device=dev)
+    recv_cnt = torch.empty(n_recv, dtype=send_cnt.dtype, device=dev)
+    dist.all_to_all_single(recv_keys, send_keys, recv_list, send_list, group=group)
+    dist.all_to_all_single(recv_cnt, send_cnt, recv_list, send_list, group=group)
+    return recv_keys, recv_cnt, recv_list
+
+
+def reshard_table(engine, table, group=None):
+    """Local (aid, aid_next, count) table -> this rank's shard of the global table."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return table
+    n = table.rows
+    dev = torch.device("cuda", engine.device)
+    send_keys = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    send_cnt = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    rows = engine.partition(table, world, send_keys.data_ptr(), send_cnt.data_ptr())
+    recv_keys, recv_cnt, _ = exchange_records(send_keys[:n], send_cnt[:n], rows, group)
+    return engine.table_from_packed(recv_keys, recv_cnt)
+
+
+def count_distributed(engine, name: str, group=None, free_local: bool = True):
+    """ottocov_count on this rank's events, then the hash(aid) exchange.  Returns this rank's shard."""
+    local = engine.count(name)
+    shard = reshard_table(engine, local, group)
+    if shard is not local and free_local:
+        local.free()
+    return shard
+
+
+def gather_table(table, group=None, dst: int = 0):
+    """Collect every rank's shard on `dst` as numpy (aid, aid_next, count); None elsewhere."""
+    a, b, c = table.fetch(order="key")
+    world = dist.get_world_size(group)
+    if world == 1:
+        return a, b, c
+    objs = [None] * world if dist.get_rank(group) == dst else None
+    dist.gather_object((a, b, c), objs, dst=dst, group=group)
+    if objs is None:
+        return None
+    return tuple(np.concatenate([o[i] for o in objs]) for i in range(3))

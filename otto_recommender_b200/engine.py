@@ -1,0 +1,308 @@
+"""Host-side mirror of the C ABI: one Engine per GPU, Tables of (aid, aid_next, count).
+
+The reference keeps these frames in polars (model/count_co_events.py); here they live in HBM and
+only leave it through ``Table.fetch`` / ``Engine.topk``.  numpy arrays are passed as host
+pointers, torch CUDA tensors as device pointers (no copies, no torch types cross the ABI).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import OttocovError
+from .config import DEFAULT_CONFIG, CoEventConfig
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+def _as_col(x, np_dtype, torch_dtype_name):
+    """-> (pointer, where, keepalive)"""
+    if _is_torch(x):
+        import torch
+        t = x.to(getattr(torch, torch_dtype_name)).contiguous()
+        return t.data_ptr(), (_lib.DEVICE if t.is_cuda else _lib.HOST), t
+    a = np.ascontiguousarray(x, dtype=np_dtype)
+    return a.ctypes.data, _lib.HOST, a
+
+
+class Table:
+    """A device-resident (aid, aid_next, count) table: rows sorted by (aid, aid_next), distinct."""
+
+    def __init__(self, engine: "Engine", handle: int):
+        self._e = engine
+        self._h = ctypes.c_void_p(handle)
+
+    @property
+    def rows(self) -> int:
+        n = ctypes.c_int64()
+        self._e._check(self._e._lib.ottocov_table_rows(self._h, ctypes.byref(n)))
+        return int(n.value)
+
+    def total(self) -> int:
+        s = ctypes.c_int64()
+        self._e._check(self._e._lib.ottocov_table_total(self._e._ctx, self._h, ctypes.byref(s)))
+        return int(s.value)
+
+    def fetch(self, order: str = "key", head: int = -1, device: bool = False, pinned: bool = False):
+        """-> (aid, aid_next, count) as int32 numpy arrays (or torch CUDA tensors if device=True).
+        order='count_desc' is the file order of model/count_co_events.py:173-175.  pinned=True
+        lands the rows in reusable page-locked buffers (views valid until the next pinned fetch)."""
+        n = self.rows if head < 0 else min(head, self.rows)
+        o = _lib.ORDER_COUNT_DESC if order == "count_desc" else _lib.ORDER_KEY
+        n_out = ctypes.c_int64()
+        if device:
+            import torch
+            dev = torch.device("cuda", self._e.device)
+            a, b, c = (torch.empty(n, dtype=torch.int32, device=dev) for _ in range(3))
+            pa, pb, pc, where = a.data_ptr(), b.data_ptr(), c.data_ptr(), _lib.DEVICE
+        else:
+            if pinned:
+                a, b, c = (self._e._pinned(f"fetch{i}", n) for i in range(3))
+            else:
+                a, b, c = (np.empty(n, np.int32) for _ in range(3))
+            pa, pb, pc, where = a.ctypes.data, b.ctypes.data, c.ctypes.data, _lib.HOST
+        self._e._sync_stream()
+        self._e._check(self._e._lib.ottocov_table_fetch(self._e._ctx, self._h, o, head, pa, pb, pc, n, where,
+                                                        ctypes.byref(n_out)))
+        return a, b, c
+
+    def to_dict(self) -> Dict[Tuple[int, int], int]:
+        a, b, c = self.fetch()
+        return {(int(x), int(y)): int(z) for x, y, z in zip(a, b, c)}
+
+    def device_ptrs(self) -> Tuple[int, int]:
+        k, c = ctypes.c_void_p(), ctypes.c_void_p()
+        self._e._check(self._e._lib.ottocov_table_device_ptrs(self._h, ctypes.byref(k), ctypes.byref(c)))
+        return int(k.value or 0), int(c.value or 0)
+
+    def free(self):
+        if self._h is not None and self._e._ctx is not None:
+            self._e._lib.ottocov_table_free(self._e._ctx, self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Engine:
+    """One co-visitation counting context on one GPU (``ottocov_ctx``)."""
+
+    def __init__(self, device: int = 0, config: CoEventConfig = DEFAULT_CONFIG, profiling: bool = False):
+        self._lib = _lib.load_library()          # raises if the CUDA library is not built
+        self.config = config
+        self.device = int(device)
+        ctx = ctypes.c_void_p()
+        rc = self._lib.ottocov_create(self.device, ctypes.byref(ctx))
+        if rc != 0:
+            msg = self._lib.ottocov_last_error(None)
+            raise OttocovError(rc, msg.decode() if msg else "ottocov_create failed")
+        self._ctx = ctx
+        self._stream = None
+        if profiling:
+            self.set_profiling(True)
+
+    # ---- plumbing ----------------------------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc != 0:
+            msg = self._lib.ottocov_last_error(self._ctx)
+            raise OttocovError(rc, msg.decode() if msg else "")
+
+    def _sync_stream(self):
+        """Run on torch's current stream when torch has CUDA initialised (so torch CUDA events and
+        tensors produced by torch ops order correctly with our kernels)."""
+        try:
+            import sys
+            torch = sys.modules.get("torch")
+            if torch is None or not torch.cuda.is_initialized():
+                return
+            s = torch.cuda.current_stream(self.device).cuda_stream
+        except Exception:
+            return
+        if s != self._stream:
+            self._check(self._lib.ottocov_set_stream(self._ctx, ctypes.c_void_p(s)))
+            self._stream = s
+
+    def _pinned(self, tag: str, n: int):
+        """Reusable page-locked int32 staging buffer (numpy view); valid until the next call with `tag`."""
+        import torch
+        cache = self.__dict__.setdefault("_pin_cache", {})
+        buf = cache.get(tag)
+        if buf is None or buf.numel() < n:
+            buf = torch.empty(max(n, 1), dtype=torch.int32).pin_memory()
+            cache[tag] = buf
+        return buf[:n].numpy()
+
+    def close(self):
+        if self._ctx is not None:
+            self._lib.ottocov_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        self._check(self._lib.ottocov_synchronize(self._ctx))
+
+    def set_profiling(self, on: bool):
+        self._check(self._lib.ottocov_set_profiling(self._ctx, int(on)))
+
+    def kernel_stats(self, reset: bool = False) -> Dict[str, Dict[str, float]]:
+        arr = (_lib.KernelStat * _lib.K_FAMILIES)()
+        self._check(self._lib.ottocov_kernel_stats(self._ctx, arr, int(reset)))
+        out = {}
+        for i in range(_lib.K_FAMILIES):
+            name = self._lib.ottocov_kernel_family_name(i).decode()
+            out[name] = {"launches": int(arr[i].launches), "ms": float(arr[i].ms),
+                         "algo_bytes": float(arr[i].algo_bytes)}
+        return out
+
+    # ---- (1) loader ----------------------------------------------------------------------------------
+    def load_events(self, session, aid, ts, type_) -> Dict[str, int]:
+        """pl.read_parquet(file).unique() + grouping by session (count_co_events.py:91-92, :19)."""
+        self._sync_stream()
+        ps, ws, ks = _as_col(session, np.int32, "int32")
+        pa, wa, ka = _as_col(aid, np.int32, "int32")
+        pt, wt, kt = _as_col(ts, np.int32, "int32")
+        py, wy, ky = _as_col(type_, np.int8, "int8")
+        if len({ws, wa, wt, wy}) != 1:
+            raise ValueError("all four columns must live on the same side (host or device)")
+        n = len(ks)
+        if not (len(ka) == len(kt) == len(ky) == n):
+            raise ValueError("columns differ in length")
+        self._check(self._lib.ottocov_load_events(self._ctx, ps, pa, pt, py, n, ws))
+        return self.events_info()
+
+    def events_info(self) -> Dict[str, int]:
+        info = _lib.EventsInfo()
+        self._check(self._lib.ottocov_get_events_info(self._ctx, ctypes.byref(info)))
+        d = {k: getattr(info, k) for k, _ in _lib.EventsInfo._fields_ if k != "n_by_type"}
+        d["n_by_type"] = [int(x) for x in info.n_by_type]
+        return d
+
+    # ---- (2)+(3) expansion + reduce-by-key ------------------------------------------------------------
+    def count(self, name: Optional[str] = None, *, type_this: Optional[int] = None,
+              next_types: Optional[Sequence[int]] = None, window: Optional[int] = None,
+              pair_budget: Optional[int] = None) -> Table:
+        """One iteration of count_co_events' loop (count_co_events.py:64-72) on the loaded events."""
+        if name is not None:
+            th, mask, w = self.config.spec(name)
+        else:
+            th, mask, w = int(type_this), 0, int(window)
+            for t in next_types:
+                mask |= 1 << int(t)
+        if window is not None:
+            w = int(window)
+        budget = self.config.PAIR_BUDGET if pair_budget is None else int(pair_budget)
+        spec = _lib.Spec(th, mask, w, budget)
+        h = ctypes.c_void_p()
+        self._sync_stream()
+        self._check(self._lib.ottocov_count(self._ctx, ctypes.byref(spec), ctypes.byref(h)))
+        return Table(self, h.value)
+
+    def count_info(self) -> Dict[str, int]:
+        ci = _lib.CountInfo()
+        self._check(self._lib.ottocov_get_count_info(self._ctx, ctypes.byref(ci)))
+        return {k: int(getattr(ci, k)) for k, _ in _lib.CountInfo._fields_}
+
+    # ---- tables ------------------------------------------------------------------------------------------
+    def table_from_arrays(self, aid, aid_next, count) -> Table:
+        self._sync_stream()
+        pa, wa, ka = _as_col(aid, np.int32, "int32")
+        pb, wb, kb = _as_col(aid_next, np.int32, "int32")
+        if _is_torch(count):
+            import torch
+            kc = count.to(torch.int32).contiguous()
+            pc, wc = kc.data_ptr(), (_lib.DEVICE if kc.is_cuda else _lib.HOST)
+        else:
+            kc = np.ascontiguousarray(count).astype(np.uint32, copy=False)
+            kc = np.ascontiguousarray(kc)
+            pc, wc = kc.ctypes.data, _lib.HOST
+        if len({wa, wb, wc}) != 1:
+            raise ValueError("all three columns must live on the same side")
+        h = ctypes.c_void_p()
+        self._check(self._lib.ottocov_table_from_arrays(self._ctx, pa, pb, pc, len(ka), wa, ctypes.byref(h)))
+        return Table(self, h.value)
+
+    def table_from_packed(self, keys, count, n: Optional[int] = None) -> Table:
+        """keys: u64 (aid << 32 | aid_next) as int64 tensor/array; count: u32 as int32 tensor/array."""
+        self._sync_stream()
+        pk, wk, kk = _as_col(keys, np.uint64, "int64")
+        pc, wc, kc = _as_col(count, np.uint32, "int32")
+        if wk != wc:
+            raise ValueError("keys and count must live on the same side")
+        n = len(kk) if n is None else int(n)
+        h = ctypes.c_void_p()
+        self._check(self._lib.ottocov_table_from_packed(self._ctx, pk, pc, n, wk, ctypes.byref(h)))
+        return Table(self, h.value)
+
+    def merge(self, tables: Iterable[Table]) -> Table:
+        """groupby(['aid','aid_next']).sum() over the concatenation (count_co_events.py:168)."""
+        tabs = list(tables)
+        arr = (ctypes.c_void_p * max(len(tabs), 1))(*[t._h for t in tabs])
+        h = ctypes.c_void_p()
+        self._sync_stream()
+        self._check(self._lib.ottocov_table_merge(self._ctx, arr, len(tabs), ctypes.byref(h)))
+        return Table(self, h.value)
+
+    def filter(self, table: Table, min_count: int) -> Table:
+        h = ctypes.c_void_p()
+        self._sync_stream()
+        self._check(self._lib.ottocov_table_filter(self._ctx, table._h, int(min_count), ctypes.byref(h)))
+        return Table(self, h.value)
+
+    # ---- (4) segmented top-K --------------------------------------------------------------------------------
+    def topk(self, table: Table, k: Optional[int] = None, device: bool = False, pinned: bool = False):
+        """-> aid_x [A], n_valid [A], aid_y [A, k], cnt [A, k]  (retrieve.py:41-47; canonical ties)."""
+        k = self.config.TOP_K if k is None else int(k)
+        n = ctypes.c_int64()
+        self._sync_stream()
+        self._check(self._lib.ottocov_table_topk(self._ctx, table._h, k, ctypes.byref(n)))
+        A = int(n.value)
+        if device:
+            import torch
+            dev = torch.device("cuda", self.device)
+            ax = torch.empty(A, dtype=torch.int32, device=dev); nv = torch.empty(A, dtype=torch.int32, device=dev)
+            ay = torch.empty((A, k), dtype=torch.int32, device=dev); ac = torch.empty((A, k), dtype=torch.int32, device=dev)
+            ptrs, where = (ax.data_ptr(), nv.data_ptr(), ay.data_ptr(), ac.data_ptr()), _lib.DEVICE
+        else:
+            if pinned:
+                ax = self._pinned("tk_ax", A); nv = self._pinned("tk_nv", A)
+                ay = self._pinned("tk_ay", A * k).reshape(A, k); ac = self._pinned("tk_ac", A * k).reshape(A, k)
+            else:
+                ax = np.empty(A, np.int32); nv = np.empty(A, np.int32)
+                ay = np.empty((A, k), np.int32); ac = np.empty((A, k), np.int32)
+            ptrs, where = (ax.ctypes.data, nv.ctypes.data, ay.ctypes.data, ac.ctypes.data), _lib.HOST
+        self._check(self._lib.ottocov_topk_fetch(self._ctx, *ptrs, A, where))
+        return ax, nv, ay, ac
+
+    # ---- multi-GPU support ----------------------------------------------------------------------------------
+    def partition(self, table: Table, n_ranks: int, keys_out_ptr: int, count_out_ptr: int) -> List[int]:
+        rows = (ctypes.c_int64 * n_ranks)()
+        self._sync_stream()
+        self._check(self._lib.ottocov_table_partition(self._ctx, table._h, n_ranks, keys_out_ptr, count_out_ptr, rows))
+        return [int(x) for x in rows]
+
+    def sort_u64(self, keys_ptr: int, vals_ptr: Optional[int], n: int, lo_bit: int = 0, hi_bit: int = 64):
+        self._sync_stream()
+        self._check(self._lib.ottocov_sort_u64(self._ctx, keys_ptr, vals_ptr, n, lo_bit, hi_bit))
+
+    # ---- convenience: whole hot path for one co-event kind ------------------------------------------------------
+    def count_topk(self, name: str, min_count: Optional[int] = None, k: Optional[int] = None):
+        """expand -> reduce -> threshold -> top-K for one name; returns (filtered Table, topk tuple)."""
+        t = self.count(name)
+        thr = self.config.MIN_COUNT_TO_SAVE.get(name, 1) if min_count is None else min_count
+        f = self.filter(t, thr) if thr > 1 else t
+        if f is not t:
+            t.free()
+        return f, self.topk(f, k)

@@ -1,0 +1,321 @@
+"""GPU parity suite (-m gpu): the CUDA path, called through the C ABI, against the CPU oracles on
+identical inputs.  Integer work throughout => every comparison is bit-exact equality."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import small_events
+from oracle import c_oracle, ref_restatement as rr
+from otto_recommender_b200 import OttocovError
+from otto_recommender_b200.dist import hash_dest
+from otto_recommender_b200.retrieve import topn_long
+from otto_recommender_b200.synth import SynthSpec, generate_numpy
+
+pytestmark = pytest.mark.gpu
+NAMES = list(c_oracle.NAMES)
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "b1_events.json")
+
+
+def _dict(a, b, c):
+    return {(int(x), int(y)): int(z) for x, y, z in zip(a, b, c)}
+
+
+def _check_all_names(engine, s, a, t, y, names=NAMES, **kw):
+    info = engine.load_events(s, a, t, y)
+    for name in names:
+        oa, ob, oc, emitted, nded = c_oracle.count_name(s, a, t, y, name)
+        tab = engine.count(name, **kw)
+        ga, gb, gc = tab.fetch()
+        ci = engine.count_info()
+        assert info["n_events"] == nded
+        assert ci["n_pairs"] == emitted, name
+        assert np.array_equal(ga, oa) and np.array_equal(gb, ob), name          # sorted by (aid, aid_next)
+        assert np.array_equal(gc.astype(np.uint32), oc), name
+        assert tab.total() == emitted
+        tab.free()
+
+
+# ---- radix sort ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 2, 33, 4095, 4096, 4097, 100_003, 3_000_001])
+def test_sort_keys_only(engine, n):
+    g = torch.Generator(device="cuda"); g.manual_seed(n)
+    keys = torch.randint(0, 2**62, (n,), generator=g, device="cuda", dtype=torch.int64)
+    want = torch.sort(keys).values
+    engine.sort_u64(keys.data_ptr(), None, n, 0, 62)
+    torch.cuda.synchronize()
+    assert torch.equal(keys, want)
+
+
+@pytest.mark.parametrize("lo,hi", [(0, 7), (3, 24), (32, 53), (10, 42)])
+def test_sort_pairs_partial_bits_is_stable(engine, lo, hi):
+    n = 700_001
+    g = torch.Generator(device="cuda"); g.manual_seed(lo * 100 + hi)
+    keys = torch.randint(0, 2**62, (n,), generator=g, device="cuda", dtype=torch.int64)
+    vals = torch.arange(n, device="cuda", dtype=torch.int32)
+    field = (keys >> lo) & ((1 << (hi - lo)) - 1)
+    order = torch.sort(field, stable=True).indices
+    want_k, want_v = keys[order], vals[order]
+    engine.sort_u64(keys.data_ptr(), vals.data_ptr(), n, lo, hi)
+    torch.cuda.synchronize()
+    assert torch.equal(keys, want_k)
+    assert torch.equal(vals, want_v)
+
+
+def test_sort_skewed_digits(engine):
+    # all keys share most digits (one bin takes everything in several passes)
+    n = 1_000_000
+    keys = (torch.arange(n, device="cuda", dtype=torch.int64) % 3) << 40
+    keys = keys[torch.randperm(n, device="cuda")].contiguous()
+    want = torch.sort(keys).values
+    engine.sort_u64(keys.data_ptr(), None, n, 0, 48)
+    torch.cuda.synchronize()
+    assert torch.equal(keys, want)
+
+
+# ---- golden vector + randomized differential tests -------------------------------------------------------
+def test_golden_b1(engine):
+    g = json.load(open(GOLD))
+    rows = np.array(g["rows"])
+    engine.load_events(rows[:, 0], rows[:, 1], rows[:, 2], rows[:, 3])
+    for name, exp in g["expected"].items():
+        tab = engine.count(name)
+        assert tab.to_dict() == {(r[0], r[1]): r[2] for r in exp}, name
+        tab.free()
+    assert engine.events_info()["n_events"] == 14
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+@pytest.mark.parametrize("shuffle", [False, True])
+def test_random_vs_oracle(engine, seed, shuffle):
+    s, a, t, y = small_events(seed, n_sessions=400, shuffle=shuffle)
+    _check_all_names(engine, s, a, t, y)
+    assert engine.events_info()["was_sorted"] == (0 if shuffle else 1)
+
+
+def test_long_sessions_and_chunking(engine):
+    # a few sessions of ~2000 events inside one window: quadratic tail, tiles span many records
+    s, a, t, y = small_events(7, n_sessions=6, n_aids=400, max_len=2000, span=40_000)
+    _check_all_names(engine, s, a, t, y, names=["click_to_click", "click_to_cart_or_buy", "cart_to_buy"])
+    # same result when the output space is cut into many pair-budget chunks
+    _check_all_names(engine, s, a, t, y, names=["click_to_click", "click_to_cart_or_buy"], pair_budget=3 * 2048)
+    assert engine.count_info()["n_chunks"] > 1
+
+
+def test_edge_cases(engine):
+    z = np.zeros(0, np.int32)
+    info = engine.load_events(z, z, z, z.astype(np.int8))
+    assert info["n_events"] == 0
+    for name in NAMES:
+        tab = engine.count(name)
+        assert tab.rows == 0
+        ax, nv, ay, ac = engine.topk(tab, 20)
+        assert len(ax) == 0
+        tab.free()
+    # singletons only
+    s = np.arange(10); a = np.arange(10); t = np.full(10, 1_660_000_000); y = np.zeros(10, np.int8)
+    engine.load_events(s, a, t, y)
+    assert engine.count("click_to_click").rows == 0
+    # a single event
+    engine.load_events(s[:1], a[:1], t[:1], y[:1])
+    assert engine.count("click_to_click").rows == 0
+    # same (session, ts), same aid, three types; plus exact duplicates of each
+    s = np.zeros(6); a = np.full(6, 7); t = np.full(6, 100); y = np.array([0, 1, 2, 0, 1, 2])
+    _check_all_names(engine, s, a, t, y)
+    # extreme timestamps / ids (int32 edges): windows must saturate, not wrap
+    s = np.array([-2**31, -2**31, 2**31 - 1, 2**31 - 1, 5, 5])
+    t = np.array([-2**31, -2**31 + 86400, 2**31 - 1, 2**31 - 1 - 43200, 0, 43201])
+    a = np.array([1, 2, 3, 4, 2**31 - 1, 0]); y = np.zeros(6)
+    _check_all_names(engine, s, a, t, y, names=["click_to_click"])
+    # only carts / only orders
+    s, a, t, y = small_events(21, n_sessions=50)
+    _check_all_names(engine, s, a, t, np.ones_like(y))
+    _check_all_names(engine, s, a, t, np.full_like(y, 2))
+
+
+def test_invariants_on_gpu(engine):
+    s, a, t, y = small_events(13, n_sessions=500, n_aids=80)
+    engine.load_events(s, a, t, y)
+    for name in ("click_to_click", "cart_to_cart", "buy_to_buy"):
+        d = engine.count(name).to_dict()
+        for (x, z), c in d.items():
+            assert d[(z, x)] == c
+    cb = engine.count("click_to_cart_or_buy")
+    c1 = engine.count(type_this=0, next_types=[1], window=86400)
+    c2 = engine.count(type_this=0, next_types=[2], window=86400)
+    m = engine.merge([c1, c2])
+    assert m.to_dict() == cb.to_dict()
+    # window larger than 24 h is clamped by the +-24 h pre-filter (count_co_events.py:33-36)
+    w1 = engine.count(type_this=0, next_types=[0], window=86400).to_dict()
+    w2 = engine.count(type_this=0, next_types=[0], window=10 * 86400).to_dict()
+    assert w1 == w2
+
+
+def test_device_resident_inputs(engine):
+    s, a, t, y = small_events(17, n_sessions=300, shuffle=True)
+    ts_ = [torch.from_numpy(x).cuda() for x in (s, a, t, y)]
+    engine.load_events(*ts_)
+    oa, ob, oc, _, _ = c_oracle.count_name(s, a, t, y, "click_to_click")
+    tab = engine.count("click_to_click")
+    ga, gb, gc = tab.fetch(device=True)
+    assert np.array_equal(ga.cpu().numpy(), oa) and np.array_equal(gb.cpu().numpy(), ob)
+    assert np.array_equal(gc.cpu().numpy().astype(np.uint32), oc)
+
+
+# ---- tables: merge / filter / order / top-K / partition --------------------------------------------------------
+def test_merge_filter_order(engine):
+    s, a, t, y = small_events(9, n_sessions=600, n_aids=40)
+    half = s < np.median(s)
+    tabs = []
+    for m in (half, ~half):
+        engine.load_events(s[m], a[m], t[m], y[m])
+        tabs.append(engine.count("click_to_click"))
+    merged = engine.merge(tabs)
+    whole = c_oracle.count_name(s, a, t, y, "click_to_click")
+    assert merged.to_dict() == _dict(*whole[:3])
+    for thr in (1, 2, 5, 50, 10**6):
+        f = engine.filter(merged, thr)
+        ka, kb, kc = c_oracle.merge_tables([whole[:3]], min_count=thr)
+        ga, gb, gc = f.fetch()
+        assert np.array_equal(ga, ka) and np.array_equal(gb, kb) and np.array_equal(gc, kc)
+        sa, sb, sc = c_oracle.sort_count_desc(ka, kb, kc)
+        ga, gb, gc = f.fetch(order="count_desc")
+        assert np.array_equal(ga, sa) and np.array_equal(gb, sb) and np.array_equal(gc, sc)
+        ga, gb, gc = f.fetch(order="count_desc", head=7)
+        assert np.array_equal(ga, sa[:7]) and np.array_equal(gc, sc[:7])
+    # round trip through arrays (unsorted, with duplicate keys that must be summed)
+    ka, kb, kc = whole[:3]
+    p = np.random.default_rng(1).permutation(len(ka))
+    t2 = engine.table_from_arrays(np.concatenate([ka[p], ka[:100]]), np.concatenate([kb[p], kb[:100]]),
+                                  np.concatenate([kc[p], kc[:100]]))
+    want = _dict(ka, kb, kc)
+    for i in range(100):
+        want[(int(ka[i]), int(kb[i]))] += int(kc[i])
+    assert t2.to_dict() == want
+
+
+@pytest.mark.parametrize("k", [1, 10, 20, 32])
+def test_topk_vs_oracle(engine, k):
+    # head-heavy aids: segments from 1 row to several thousand rows, lots of equal counts (ties)
+    rng = np.random.default_rng(k)
+    n = 400_000
+    ax = np.minimum(rng.zipf(1.3, n), 5000) - 1
+    ay = rng.integers(0, 3000, n)
+    cnt = rng.integers(1, 6, n)
+    tab = engine.table_from_arrays(ax, ay, cnt)
+    ka, kb, kc = c_oracle.merge_tables([(ax, ay, cnt)])
+    assert tab.rows == len(ka)
+    ta, tb, tc, tr = c_oracle.top_n(ka, kb, kc, k)
+    gx, nv, gy, gc = engine.topk(tab, k)
+    la, lb, lc, lr = topn_long(gx, nv, gy, gc)
+    assert np.array_equal(la, ta) and np.array_equal(lb, tb) and np.array_equal(lc, tc) and np.array_equal(lr, tr)
+    assert np.all(gy[np.arange(k)[None, :] >= nv[:, None]] == -1)
+
+
+def test_partition_by_hash(engine):
+    s, a, t, y = small_events(3, n_sessions=500, n_aids=500)
+    engine.load_events(s, a, t, y)
+    tab = engine.count("click_to_click")
+    ka, kb, kc = tab.fetch()
+    for R in (1, 2, 3, 8):
+        keys = torch.empty(tab.rows, dtype=torch.int64, device="cuda")
+        cnts = torch.empty(tab.rows, dtype=torch.int32, device="cuda")
+        rows = engine.partition(tab, R, keys.data_ptr(), cnts.data_ptr())
+        torch.cuda.synchronize()
+        dest = hash_dest(ka, R)
+        assert rows == np.bincount(dest, minlength=R).tolist()
+        order = np.argsort(dest, kind="stable")
+        want = (ka.astype(np.int64) << 32 | kb.astype(np.int64))[order]
+        assert np.array_equal(keys.cpu().numpy(), want)
+        assert np.array_equal(cnts.cpu().numpy(), kc[order])
+        # emulate the exchange on one GPU: every "rank" re-reduces what it would receive
+        off = np.concatenate([[0], np.cumsum(rows)])
+        got = {}
+        for r in range(R):
+            sh = engine.table_from_packed(keys[off[r]:off[r + 1]].clone(), cnts[off[r]:off[r + 1]].clone())
+            got.update(sh.to_dict())
+        assert got == _dict(ka, kb, kc)
+
+
+def test_errors_are_loud(engine):
+    s, a, t, y = small_events(1, n_sessions=20)
+    bad = y.copy(); bad[3] = 5
+    with pytest.raises(OttocovError) as e:
+        engine.load_events(s, a, t, bad)
+    assert e.value.code == -3
+    neg = a.copy(); neg[0] = -4
+    with pytest.raises(OttocovError) as e:
+        engine.load_events(s, neg, t, y)
+    assert e.value.code == -3
+    with pytest.raises(OttocovError) as e:      # failed load leaves no events behind
+        engine.count("click_to_click")
+    assert e.value.code == -4
+    engine.load_events(s, a, t, y)
+    tab = engine.count("click_to_click")
+    with pytest.raises(OttocovError) as e:
+        engine.topk(tab, 33)
+    assert e.value.code == -2
+
+
+# ---- BASELINE config 1: 100k-session synthetic slice, full pair table + top-20 ----------------------------------
+def test_config1_100k_sessions(engine):
+    d = generate_numpy(SynthSpec(n_sessions=100_000, seed=42))
+    s, a, t, y = d["session"], d["aid"], d["ts"], d["type"]
+    info = engine.load_events(s, a, t, y)
+    assert info["was_sorted"] == 1
+    for name in NAMES:
+        oa, ob, oc, emitted, nded = c_oracle.count_name(s, a, t, y, name)
+        tab = engine.count(name)
+        ga, gb, gc = tab.fetch()
+        assert engine.count_info()["n_pairs"] == emitted and info["n_events"] == nded
+        assert np.array_equal(ga, oa) and np.array_equal(gb, ob) and np.array_equal(gc.astype(np.uint32), oc), name
+        # threshold 2 + top-20 (the full-size thresholds 10/5 leave almost nothing on one part)
+        f = engine.filter(tab, 2)
+        ka, kb, kc = c_oracle.merge_tables([(oa, ob, oc)], min_count=2)
+        ta, tb, tc, tr = c_oracle.top_n(ka, kb, kc, 20)
+        la, lb, lc, lr = topn_long(*engine.topk(f, 20))
+        assert np.array_equal(la, ta) and np.array_equal(lb, tb) and np.array_equal(lc, tc), name
+    # shuffled rows give the same tables (row order of the input is irrelevant)
+    p = np.random.default_rng(0).permutation(len(s))
+    engine.load_events(s[p], a[p], t[p], y[p])
+    assert engine.events_info()["was_sorted"] == 0
+    oa, ob, oc, _, _ = c_oracle.count_name(s, a, t, y, "click_to_cart_or_buy")
+    ga, gb, gc = engine.count("click_to_cart_or_buy").fetch()
+    assert np.array_equal(ga, oa) and np.array_equal(gb, ob) and np.array_equal(gc.astype(np.uint32), oc)
+
+
+# ---- size-independent properties at a larger scale (oracle too slow there) -----------------------------------------
+def test_properties_at_scale(engine):
+    from otto_recommender_b200.synth import generate
+    d = generate(SynthSpec(n_sessions=1_500_000, seed=7), "cuda")
+    info = engine.load_events(d["session"], d["aid"], d["ts"], d["type"])
+    assert sum(info["n_by_type"]) == info["n_events"] <= info["n_rows_in"]
+    cc = engine.count("click_to_click")
+    ci = engine.count_info()
+    assert cc.total() == ci["n_pairs"] and cc.rows == ci["n_unique"]
+    # symmetric kind: the transposed table is the same table
+    ka, kb, kc = cc.fetch(device=True)
+    tr = engine.table_from_arrays(kb, ka, kc)
+    a2, b2, c2 = tr.fetch(device=True)
+    assert torch.equal(a2, ka) and torch.equal(b2, kb) and torch.equal(c2, kc)
+    # chunked == unchunked
+    cc2 = engine.count("click_to_click", pair_budget=ci["n_pairs"] // 5 + 1)
+    assert engine.count_info()["n_chunks"] >= 5
+    a3, b3, c3 = cc2.fetch(device=True)
+    assert torch.equal(a3, ka) and torch.equal(b3, kb) and torch.equal(c3, kc)
+    # click_to_cart_or_buy == click_to_cart + click_to_buy
+    cb = engine.count("click_to_cart_or_buy")
+    m = engine.merge([engine.count(type_this=0, next_types=[1], window=86400),
+                      engine.count(type_this=0, next_types=[2], window=86400)])
+    for x, z in zip(cb.fetch(device=True), m.fetch(device=True)):
+        assert torch.equal(x, z)
+    # top-20: per aid non-increasing counts, n_valid = min(20, segment size), ids inside the segment
+    f = engine.filter(cc, 2)
+    ax, nv, ay, ac = engine.topk(f, 20, device=True)
+    assert bool((ac[:, :-1] >= ac[:, 1:]).all())
+    fa, fb, fc = f.fetch(device=True)
+    seg = torch.unique_consecutive(fa, return_counts=True)
+    assert torch.equal(seg[0], ax) and torch.equal(torch.clamp(seg[1], max=20).to(torch.int32), nv)
+    assert int(ac[:, 0].max()) == int(fc.max())

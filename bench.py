@@ -208,15 +208,19 @@ def run_ours(args):
 
     def step_device():
         eng.load_events(*cols)
-        local = eng.count(NAME)
-        ci = eng.count_info()
-        tab = reshard_table(eng, local) if world > 1 else local
-        if tab is not local:
+        if world > 1:                                     # thresholds apply to the global sums only
+            local = eng.count(NAME)
+            ci = eng.count_info()
+            tab = reshard_table(eng, local)
             local.free()
-        f = eng.filter(tab, MIN_COUNT)
+            f = eng.filter(tab, MIN_COUNT)
+            tab.free()
+        else:                                             # threshold fused into the run-length reduce
+            f = eng.count(NAME, min_count=MIN_COUNT)
+            ci = eng.count_info()
         eng.topk(f, TOP_K, device=True)
         rows_f = f.rows
-        tab.free(); f.free()
+        f.free()
         return ci, rows_f
 
     def barrier():
@@ -227,6 +231,17 @@ def run_ours(args):
     for _ in range(args.warmup):
         ci, rows_f = step_device()
     barrier()
+    if args.breakdown and rank == 0:
+        def timed(label, fn):
+            torch.cuda.synchronize(); t0 = time.perf_counter(); r = fn(); torch.cuda.synchronize()
+            print(f"[breakdown] {label:14s} {(time.perf_counter() - t0) * 1e3:9.3f} ms", file=sys.stderr)
+            return r
+        for _ in range(2):
+            timed("load_events", lambda: eng.load_events(*cols))
+            fl = timed("count+filter", lambda: eng.count(NAME, min_count=MIN_COUNT))
+            timed("topk", lambda: eng.topk(fl, TOP_K, device=True))
+            timed("free", lambda: fl.free())
+            print(f"[breakdown] memory {eng.memory_info()}", file=sys.stderr)
     eng.kernel_stats(reset=True)
     eng.set_profiling(True)
     sampler = ClockSampler(local_rank)
@@ -260,15 +275,18 @@ def run_ours(args):
 
     def step_e2e():
         eng.load_events(*host_cols)                       # H2D inside
-        local = eng.count(NAME)
-        tab = reshard_table(eng, local) if world > 1 else local
-        if tab is not local:
+        if world > 1:
+            local = eng.count(NAME)
+            tab = reshard_table(eng, local)
             local.free()
-        f = eng.filter(tab, MIN_COUNT)
+            f = eng.filter(tab, MIN_COUNT)
+            tab.free()
+        else:
+            f = eng.count(NAME, min_count=MIN_COUNT)
         ax, nv, ay, ac = eng.topk(f, TOP_K, pinned=True)   # D2H inside
         fa, fb, fc = f.fetch(order="count_desc", pinned=True)
         d2h = (ax.size + nv.size + ay.size + ac.size + 3 * fa.size) * 4
-        tab.free(); f.free()
+        f.free()
         return d2h
 
     for _ in range(max(1, args.warmup)):
@@ -325,7 +343,7 @@ def run_ours(args):
         "config": {
             "workload": f"click_to_click 12h co-visitation top-{TOP_K}, min_count {MIN_COUNT}: {args.sessions:,} sessions / "
                         f"{rows_global:,} event rows / {N_AIDS:,} aids (BASELINE configs[1])",
-            "pairs_per_step": pairs_global, "unique_pairs_sum_over_ranks": uniq_sum,
+            "pairs_per_step": pairs_global, "table_rows_sum_over_ranks": uniq_sum,
             "thresholded_rows_rank0": rows_f, "sort_passes": ci["sort_passes"], "chunks": ci["n_chunks"],
             "parallelism": f"session-sharded x{world}, hash(aid) all-to-all" if world > 1 else "single GPU",
             "l2": "inputs (event columns, pair keys) are far larger than the 126 MB L2; no flush needed",
@@ -357,6 +375,7 @@ def main():
     ap.add_argument("--sessions", type=int, default=FULL_SESSIONS, help="sessions of the synthetic workload")
     ap.add_argument("--cpu-sample-sessions", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="per-API-call wall times on stderr")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

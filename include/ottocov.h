@@ -59,6 +59,9 @@ typedef struct {
     int64_t window;          /* |ts_next - ts| <= window, seconds, inclusive; clamped to 86400     */
                              /* (the +-24 h pre-filter of count_co_events.py:33-36)                */
     int64_t pair_budget;     /* max co-event pairs expanded at once (HBM footprint); 0 = auto     */
+    uint32_t min_count;      /* keep only pairs with count >= min_count (0 or 1 = keep all); fused */
+                             /* into the run-length reduce: filter(count >= ...) of :131-132, :172  */
+    uint32_t reserved;       /* must be 0                                                           */
 } ottocov_spec;
 
 typedef struct {
@@ -94,6 +97,10 @@ int ottocov_destroy(ottocov_ctx* ctx);
 const char* ottocov_last_error(const ottocov_ctx* ctx);      /* ctx may be NULL (create failures) */
 int ottocov_set_stream(ottocov_ctx* ctx, void* cuda_stream); /* cudaStream_t; NULL = default       */
 int ottocov_synchronize(ottocov_ctx* ctx);
+/* The context keeps freed device blocks for re-use (no driver allocation in steady state).
+ * ottocov_trim hands them back to the driver; ottocov_memory_info reports the footprint. */
+int ottocov_trim(ottocov_ctx* ctx);
+int ottocov_memory_info(ottocov_ctx* ctx, int64_t* live_bytes, int64_t* cached_bytes, int64_t* peak_bytes);
 int ottocov_set_profiling(ottocov_ctx* ctx, int on);         /* CUDA-event timing per family       */
 int ottocov_kernel_stats(ottocov_ctx* ctx, ottocov_kernel_stat* out /*[OTTOCOV_K_FAMILIES]*/, int reset);
 const char* ottocov_kernel_family_name(int family);

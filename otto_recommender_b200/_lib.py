@@ -22,7 +22,8 @@ class OttocovError(RuntimeError):
 
 
 class Spec(Structure):
-    _fields_ = [("type_this", c_int32), ("next_mask", c_uint32), ("window", c_int64), ("pair_budget", c_int64)]
+    _fields_ = [("type_this", c_int32), ("next_mask", c_uint32), ("window", c_int64), ("pair_budget", c_int64),
+                ("min_count", c_uint32), ("reserved", c_uint32)]
 
 
 class EventsInfo(Structure):
@@ -47,6 +48,8 @@ SYMBOLS = {
     "ottocov_last_error": (c_char_p, [c_void_p]),
     "ottocov_set_stream": (c_int, [c_void_p, c_void_p]),
     "ottocov_synchronize": (c_int, [c_void_p]),
+    "ottocov_trim": (c_int, [c_void_p]),
+    "ottocov_memory_info": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]),
     "ottocov_set_profiling": (c_int, [c_void_p, c_int]),
     "ottocov_kernel_stats": (c_int, [c_void_p, POINTER(KernelStat), c_int]),
     "ottocov_kernel_family_name": (c_char_p, [c_int]),

@@ -31,6 +31,63 @@ void ottocov_ctx::end(int family, double algo_bytes) {
     if (pe.family == family && pe.b) cudaEventRecord(pe.b, stream);
 }
 
+// ---- caching allocator --------------------------------------------------------------------------------
+void* cov_alloc(ottocov_ctx* ctx, size_t bytes) {
+    bytes = (bytes + 511) & ~(size_t)511;
+    // best fit among cached blocks, at most 25 % (+1 MiB) larger than asked
+    int best = -1;
+    const size_t limit = bytes + bytes / 4 + (1u << 20);
+    for (int i = 0; i < (int)ctx->cache.size(); ++i) {
+        const size_t b = ctx->cache[i].bytes;
+        if (b >= bytes && b <= limit && (best < 0 || b < ctx->cache[best].bytes)) best = i;
+    }
+    void* p = nullptr;
+    size_t got = bytes;
+    if (best >= 0) {
+        p = ctx->cache[best].p; got = ctx->cache[best].bytes;
+        ctx->cached_bytes -= got;
+        ctx->cache[best] = ctx->cache.back();
+        ctx->cache.pop_back();
+    } else {
+        cudaError_t e = cudaMallocAsync(&p, bytes, ctx->stream);
+        if (e != cudaSuccess) {           // give the cache back to the driver and retry once
+            (void)cudaGetLastError();
+            cov_trim(ctx);
+            e = cudaMallocAsync(&p, bytes, ctx->stream);
+        }
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            COV_THROW(e == cudaErrorMemoryAllocation ? OTTOCOV_ERR_NOMEM : OTTOCOV_ERR_CUDA,
+                      "device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        }
+    }
+    ctx->live[p] = got;
+    ctx->live_bytes += got;
+    if (ctx->live_bytes + ctx->cached_bytes > ctx->peak_bytes) ctx->peak_bytes = ctx->live_bytes + ctx->cached_bytes;
+    return p;
+}
+
+void cov_free(ottocov_ctx* ctx, void* p) {
+    if (!p) return;
+    auto it = ctx->live.find(p);
+    if (it == ctx->live.end()) { cudaFreeAsync(p, ctx->stream); return; }   // not ours: plain free
+    const size_t b = it->second;
+    ctx->live.erase(it);
+    ctx->live_bytes -= b;
+    ctx->cache.push_back(CacheBlock{p, b});
+    ctx->cached_bytes += b;
+}
+
+void cov_trim(ottocov_ctx* ctx) {
+    for (CacheBlock& c : ctx->cache) cudaFreeAsync(c.p, ctx->stream);
+    ctx->cache.clear();
+    ctx->cached_bytes = 0;
+    cudaStreamSynchronize(ctx->stream);
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    (void)cudaGetLastError();
+}
+
 static void resolve_profile(ottocov_ctx* ctx) {
     if (ctx->prof_pending.empty()) return;
     cudaStreamSynchronize(ctx->stream);
@@ -123,6 +180,9 @@ int ottocov_destroy(ottocov_ctx* ctx) {
     free_events(ctx);
     free_topk(ctx);
     if (ctx->sweep_status) cudaFreeAsync(ctx->sweep_status, ctx->stream);
+    for (auto& kv : ctx->live) cudaFreeAsync(kv.first, ctx->stream);    // tables the caller never freed
+    ctx->live.clear();
+    cov_trim(ctx);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->sweep_ticket) cudaFree(ctx->sweep_ticket);
     for (ProfEvent& pe : ctx->prof_pending) { if (pe.a) cudaEventDestroy(pe.a); if (pe.b) cudaEventDestroy(pe.b); }
@@ -142,6 +202,20 @@ int ottocov_set_stream(ottocov_ctx* ctx, void* cuda_stream) {
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));   // pool frees are ordered on the old stream
         ctx->stream = (cudaStream_t)cuda_stream;
     }
+    API_END(ctx)
+}
+
+int ottocov_trim(ottocov_ctx* ctx) {
+    API_BEGIN(ctx)
+    cov_trim(ctx);
+    API_END(ctx)
+}
+
+int ottocov_memory_info(ottocov_ctx* ctx, int64_t* live_bytes, int64_t* cached_bytes, int64_t* peak_bytes) {
+    API_BEGIN(ctx)
+    if (live_bytes) *live_bytes = (int64_t)ctx->live_bytes;
+    if (cached_bytes) *cached_bytes = (int64_t)ctx->cached_bytes;
+    if (peak_bytes) *peak_bytes = (int64_t)ctx->peak_bytes;
     API_END(ctx)
 }
 

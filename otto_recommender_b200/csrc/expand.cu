@@ -254,12 +254,14 @@ ottocov_table* count_impl(ottocov_ctx* ctx, const ottocov_spec* spec) {
         CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
         // pool memory we already hold counts as free for our purposes; be conservative: 16 B per
         // pair for the double buffer plus <= 12 B per pair for the reduced table
-        budget = (u64)((double)free_b * 0.6 / 28.0);
+        budget = (u64)((double)(free_b + ctx->cached_bytes) * 0.6 / 28.0);
         if (budget < (1u << 20)) budget = 1u << 20;
     }
     budget = (budget / EX_TILE) * EX_TILE;
     if (budget == 0) budget = EX_TILE;
 
+    const u32 user_min = spec->min_count > 1 ? spec->min_count : 1;
+    const u32 fused_min = (P <= budget) ? user_min : 1;     // thresholds apply to complete sums only
     std::vector<ottocov_table*> partials;
     struct PartGuard {
         ottocov_ctx* c; std::vector<ottocov_table*>& v;
@@ -299,7 +301,7 @@ ottocov_table* count_impl(ottocov_ctx* ctx, const ottocov_spec* spec) {
         ottocov_table* part = new ottocov_table();
         part->aid_bits = aid_bits;
         partials.push_back(part);
-        reduce_sorted(ctx, k, nullptr, (int64_t)cn, &part->keys, &part->count, &part->n);
+        reduce_sorted(ctx, k, nullptr, (int64_t)cn, fused_min, &part->keys, &part->count, &part->n);
         ci.n_chunks += 1;
     }
 
@@ -309,6 +311,11 @@ ottocov_table* count_impl(ottocov_ctx* ctx, const ottocov_spec* spec) {
         partials.clear();
     } else {
         result = merge_tables_impl(ctx, partials.data(), (int)partials.size());
+        if (user_min > 1) {
+            ottocov_table* f = filter_table_impl(ctx, result, user_min);
+            dev_free(ctx, result->keys); dev_free(ctx, result->count); delete result;
+            result = f;
+        }
     }
     ci.n_unique = result->n;
     return result;

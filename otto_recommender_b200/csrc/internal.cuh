@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <string>
 #include <vector>
+#include <unordered_map>
 #include <stdexcept>
 #include "../../include/ottocov.h"
 
@@ -46,9 +47,10 @@ struct TypeArray {
 };
 
 struct ProfEvent { int family; cudaEvent_t a, b; };
+struct CacheBlock { void* p; size_t bytes; };
 
 struct ottocov_table {
-    u64* keys = nullptr;     // [n] sorted, distinct
+    u64* keys = nullptr;     // [n] sorted, distinct (buffers may be larger than n)
     u32* count = nullptr;    // [n]
     int64_t n = 0;
     int aid_bits = 32;       // significant bits of both key halves (bounds the radix passes)
@@ -64,6 +66,11 @@ struct ottocov_ctx {
     ottocov_kernel_stat stats[OTTOCOV_K_FAMILIES];
     std::vector<ProfEvent> prof_pending;
     std::vector<cudaEvent_t> event_pool;
+    // caching allocator: freed blocks are kept and re-used (all work is ordered on one stream), so
+    // the steady-state pipeline performs no driver allocations at all
+    std::vector<CacheBlock> cache;
+    std::unordered_map<void*, size_t> live;
+    size_t cached_bytes = 0, live_bytes = 0, peak_bytes = 0;
     // events
     bool loaded = false;
     ottocov_events_info info;
@@ -77,7 +84,9 @@ struct ottocov_ctx {
     // generic look-back scan state
     u64* scan_status = nullptr;
     size_t scan_status_words = 0;
+    u32 scan_epoch = 0;
     u32* scan_ticket = nullptr;
+    u64* scan_totals = nullptr;        // [8] grand totals of the last scan launch
     // top-k result
     int topk_k = 0;
     int64_t topk_n = 0;
@@ -90,7 +99,11 @@ struct ottocov_ctx {
     void end(int family, double algo_bytes);
 };
 
-// RAII device buffer on the context's stream-ordered pool.
+void* cov_alloc(ottocov_ctx* ctx, size_t bytes);      // api.cu; throws CovError
+void cov_free(ottocov_ctx* ctx, void* p);             // returns the block to the context cache
+void cov_trim(ottocov_ctx* ctx);                      // releases every cached block to the driver
+
+// RAII device buffer on the context's caching allocator.
 template <class T>
 struct DevBuf {
     ottocov_ctx* ctx = nullptr;
@@ -104,23 +117,17 @@ struct DevBuf {
         release();
         ctx = c; n = n_;
         size_t bytes = (n_ ? n_ : 1) * sizeof(T);
-        cudaError_t e = cudaMallocAsync((void**)&p, bytes, c->stream);
-        if (e != cudaSuccess) {
-            p = nullptr;
-            (void)cudaGetLastError();
-            COV_THROW(e == cudaErrorMemoryAllocation ? OTTOCOV_ERR_NOMEM : OTTOCOV_ERR_CUDA,
-                      "device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
-        }
+        p = (T*)cov_alloc(c, bytes);
     }
     T* take() { T* q = p; p = nullptr; n = 0; return q; }   // give ownership away
     void release() {
-        if (p) { cudaFreeAsync(p, ctx->stream); p = nullptr; }
+        if (p) { cov_free(ctx, p); p = nullptr; }
         n = 0;
     }
     ~DevBuf() { release(); }
 };
 
-static inline void dev_free(ottocov_ctx* ctx, void* p) { if (p) cudaFreeAsync(p, ctx->stream); }
+static inline void dev_free(ottocov_ctx* ctx, void* p) { if (p) cov_free(ctx, p); }
 
 // Launch helper: counts the launch, brackets it with CUDA events when profiling is on.
 #define COV_LAUNCH(ctx_, fam_, bytes_, kern_, grid_, block_, smem_, ...)                      \
@@ -140,12 +147,6 @@ struct BitField { int lo, hi; };   // sort on key bits [lo, hi)
 int radix_sort_pairs(ottocov_ctx* ctx, u64*& keys, u64*& alt, u32*& vals, u32*& valt, int64_t n,
                      const BitField* fields, int n_fields);
 
-// scan.cu
-// exclusive scan of n u64 values in place-safe manner (out may alias in); returns nothing; total
-// written to *total_dev (device, may be nullptr)
-void exclusive_scan_u64(ottocov_ctx* ctx, const u64* in, u64* out, int64_t n, u64* total_dev);
-void exclusive_scan_u32(ottocov_ctx* ctx, const u32* in, u32* out, int64_t n, u32* total_dev);
-
 // events.cu
 void load_events_impl(ottocov_ctx* ctx, const int32_t* session, const int32_t* aid,
                       const int32_t* ts, const int8_t* type, int64_t n, int where);
@@ -155,8 +156,9 @@ void free_events(ottocov_ctx* ctx);
 ottocov_table* count_impl(ottocov_ctx* ctx, const ottocov_spec* spec);
 
 // reduce.cu
-// sorted keys -> distinct keys + run lengths (vals == nullptr) or summed payload (vals != nullptr)
-void reduce_sorted(ottocov_ctx* ctx, const u64* keys, const u32* vals, int64_t n,
+// sorted keys -> distinct keys + run lengths (vals == nullptr) or summed payload (vals != nullptr),
+// keeping only rows whose count is >= min_count
+void reduce_sorted(ottocov_ctx* ctx, const u64* keys, const u32* vals, int64_t n, u32 min_count,
                    u64** out_keys, u32** out_count, int64_t* n_out);
 ottocov_table* merge_tables_impl(ottocov_ctx* ctx, ottocov_table* const* tabs, int n_tabs);
 ottocov_table* filter_table_impl(ottocov_ctx* ctx, const ottocov_table* t, u32 min_count);

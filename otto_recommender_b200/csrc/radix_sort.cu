@@ -7,10 +7,11 @@
 // distribution pass):
 //   * one up-front kernel builds the digit histograms of ALL passes in a single read;
 //   * each pass is one kernel.  A CTA takes the next tile (atomic ticket, so a CTA only ever waits
-//     for tiles that already started), ranks its 4096 keys by digit with warp match-any, publishes
-//     its per-digit tile counts, resolves the per-digit exclusive prefix over earlier tiles by
-//     decoupled look-back on epoch-tagged 64-bit status words, stages the keys in shared memory in
-//     digit order and writes them out as coalesced per-digit runs.
+//     for tiles that already started), histograms its 4096 keys by digit, publishes the per-digit
+//     tile counts at once, ranks the keys with warp match-any into a digit-ordered staging buffer in
+//     shared memory, resolves the per-digit exclusive prefix over earlier tiles by decoupled
+//     look-back on epoch-tagged 64-bit status words and writes the keys out as coalesced per-digit
+//     runs.
 //   * status word = flag(2) | epoch(6) | value(56).  The epoch changes every pass, so the status
 //     array is never re-zeroed between passes.
 // Only the significant bit fields are sorted: for co-event keys that is 2 x aid_bits (42 bits for
@@ -67,11 +68,28 @@ __global__ void __launch_bounds__(RS_RADIX) rs_scan_hist_kernel(u64* __restrict_
 }
 
 // ---- one distribution pass ---------------------------------------------------------------------------
-template <bool HAS_VALS>
-__global__ void __launch_bounds__(RS_THREADS)
+// Order of work inside a CTA (one tile of 4096 keys):
+//   A  load keys into registers (16 independent 8-byte loads per thread in flight)
+//   B  stable rank of each key inside its warp's segment (ballot matching + running per-warp digit
+//      counters); the per-warp digit histograms fall out of the same pass
+//   C  per digit: offsets over warps, tile total, position of the digit inside the tile; the tile
+//      total is published at once (flag AGG)
+//   E  look-back RIGHT AWAY (before the long ranking phase, so the gap between a tile's AGG and its
+//      PREFIX is one short walk and later tiles almost always find a PREFIX next door): thread d
+//      walks status[tile-1][d], status[tile-2][d], ... RS_WINDOW entries per round trip, sums AGGs
+//      until the first PREFIX, publishes its own PREFIX
+//   D  keys go to their slot of the digit-ordered staging buffer (the warps without look-back duty do
+//      this while the first `radix` threads are still walking)
+//   F  staged keys leave as coalesced per-digit runs
+constexpr int RS_WINDOW = 4;
+
+// ALGO selects how lanes holding the same digit find each other (tuning knob):
+//   0  match.any            1  NB ballots (one per digit bit)            2  atomicOr on a per-warp mask table
+template <bool HAS_VALS, int ALGO, int NB>
+__global__ void __launch_bounds__(RS_THREADS, 4)
 rs_onesweep_kernel(const u64* __restrict__ keys_in, u64* __restrict__ keys_out,
                    const u32* __restrict__ vals_in, u32* __restrict__ vals_out, int64_t n, int shift,
-                   int bits, const u64* __restrict__ digit_base, u64* status, u32* ticket, u32 epoch) {
+                   int bits, const u64* __restrict__ digit_base, u64* status, u32* ticket, u32 epoch, int dbg) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     u64* s_keys = reinterpret_cast<u64*>(s_raw);                              // [RS_TILE]
     u32* s_whist = reinterpret_cast<u32*>(s_keys + RS_TILE);                  // [RS_WARPS][RS_RADIX]
@@ -79,38 +97,67 @@ rs_onesweep_kernel(const u64* __restrict__ keys_in, u64* __restrict__ keys_out,
     u64* s_gbase = reinterpret_cast<u64*>(s_dstart + RS_RADIX);               // [RS_RADIX]
     u32* s_scan = reinterpret_cast<u32*>(s_gbase + RS_RADIX);                 // [RS_WARPS + 1] (+pad)
     u32* s_tile = s_scan + 16;                                                // [1] (+pad to 16)
-    u32* s_vals = s_tile + 16;                                                // [RS_TILE] if HAS_VALS
+    u32* s_match = s_tile + 16;                                               // [RS_WARPS][RS_RADIX] if ALGO == 2
+    u32* s_vals = s_match + (ALGO == 2 ? RS_WARPS * RS_RADIX : 0);            // [RS_TILE] if HAS_VALS
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 radix = 1u << bits, mask = radix - 1u;
 
     if (tid == 0) *s_tile = atomicAdd(ticket, 1u);
-    for (int j = tid; j < RS_WARPS * RS_RADIX; j += RS_THREADS) s_whist[j] = 0;
+    for (int j = tid; j < RS_WARPS * RS_RADIX; j += RS_THREADS) {
+        s_whist[j] = 0;
+        if (ALGO == 2) s_match[j] = 0;
+    }
     __syncthreads();
     const int64_t tile = *s_tile;
     const int64_t tile_base = tile * RS_TILE;
     const int tile_n = (int)min((int64_t)RS_TILE, n - tile_base);
 
-    // -- load (warp-striped: every access is a coalesced 256 B row) --------------------------------
+    // -- A: load (warp-striped: every access is a coalesced 256 B row) ------------------------------
     u64 key[RS_IPT];
     u32 val[RS_IPT];
     const int64_t lbase = tile_base + (int64_t)warp * 32 * RS_IPT + lane;
+    const int my_n = (int)min((int64_t)RS_IPT, (n - lbase + 31) / 32);        // valid items of this lane (may be <= 0)
 #pragma unroll
     for (int i = 0; i < RS_IPT; ++i) {
         const int64_t idx = lbase + i * 32;
-        key[i] = (idx < n) ? ld_stream_u64(keys_in + idx) : ~0ull;
-        if (HAS_VALS) val[i] = (idx < n) ? __ldcs(vals_in + idx) : 0u;
+        key[i] = (i < my_n) ? ld_stream_u64(keys_in + idx) : ~0ull;
+        if (HAS_VALS) val[i] = (i < my_n) ? __ldcs(vals_in + idx) : 0u;
     }
 
-    // -- rank inside the warp's 512-key segment by digit (stable) ----------------------------------
-    u32 rnk[RS_IPT];
+    // -- B: stable rank of every key inside its warp's 512-key segment; the per-warp digit counts fall
+    //       out of the same pass.  Lanes holding the same digit are found with one ballot per digit
+    //       bit (match.any is far slower than `bits` ballots on this part); the lowest such lane
+    //       bumps the warp's running counter for the digit, no atomics needed.
     u32* my_whist = s_whist + warp * RS_RADIX;
     const u32 lt = lanemask_lt();
+    u32 rnk2[RS_IPT / 2];                       // two 16-bit ranks per register
 #pragma unroll
     for (int i = 0; i < RS_IPT; ++i) {
-        const bool valid = (lbase + i * 32) < n;
-        const u32 d = valid ? ((u32)(key[i] >> shift) & mask) : radix;   // `radix` never matches a digit
-        const u32 peers = __match_any_sync(0xffffffffu, d);
+        const bool valid = i < my_n;
+        const u32 d = (u32)(key[i] >> shift) & mask;
+        u32 peers;
+        if (dbg & 2) {
+            peers = 1u << lane;
+        } else if (ALGO == 0) {
+            peers = __match_any_sync(0xffffffffu, valid ? d : radix);      // `radix` never matches a digit
+        } else if (ALGO == 1) {
+            const u32 vm = __ballot_sync(0xffffffffu, valid);
+            peers = valid ? vm : ~vm;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {                                 // bits above `bits` are zero everywhere
+                const bool bit = (d >> b) & 1u;
+                const u32 m = __ballot_sync(0xffffffffu, bit);
+                peers &= bit ? m : ~m;
+            }
+        } else {
+            u32* mm = s_match + warp * RS_RADIX;
+            if (valid) atomicOr(&mm[d], 1u << lane);
+            __syncwarp();
+            peers = valid ? mm[d] : (1u << lane);
+            __syncwarp();
+            if (valid && lane == __ffs(peers) - 1) mm[d] = 0;              // ready for the next row
+        }
         const int leader = __ffs(peers) - 1;
         u32 old = 0;
         if (lane == leader && valid) {
@@ -118,12 +165,13 @@ rs_onesweep_kernel(const u64* __restrict__ keys_in, u64* __restrict__ keys_out,
             my_whist[d] = old + __popc(peers);
         }
         old = __shfl_sync(0xffffffffu, old, leader);
-        rnk[i] = old + __popc(peers & lt);
+        const u32 r = old + __popc(peers & lt);
+        if (i & 1) rnk2[i >> 1] |= r << 16; else rnk2[i >> 1] = r;
         __syncwarp();
     }
     __syncthreads();
 
-    // -- per digit: exclusive offsets over warps, tile total ------------------------------------------
+    // -- C: offsets over warps, tile totals, digit starts; publish the aggregate ----------------------
     u32 total = 0;
     if (tid < (int)radix) {
         u32 run = 0;
@@ -137,63 +185,78 @@ rs_onesweep_kernel(const u64* __restrict__ keys_in, u64* __restrict__ keys_out,
     }
     u32 blk_total;
     const u32 dstart = block_exclusive_scan<u32, RS_THREADS>(total, s_scan, &blk_total);
-
-    // -- decoupled look-back: exclusive count of this digit over all earlier tiles --------------------
+    const u64 tag = (u64)epoch << 56;
+    u64* mine = status + (size_t)tile * radix + tid;          // [tile][digit]: a tile's words are contiguous
     if (tid < (int)radix) {
+        st_volatile_u64(mine, (tile == 0 ? ST_FLAG_PREFIX : ST_FLAG_AGG) | tag | (u64)total);
         s_dstart[tid] = dstart;
-        const u64 tag = (u64)epoch << 56;
-        u64* mine = status + (size_t)tile * radix + tid;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) s_whist[w * RS_RADIX + tid] += dstart;   // absolute slots
+    }
+    __syncthreads();
+
+    // -- E: decoupled look-back, RS_WINDOW predecessors per round trip -----------------------------------
+    if (tid < (int)radix) {
         u64 excl = 0;
-        if (tile == 0) {
-            st_volatile_u64(mine, ST_FLAG_PREFIX | tag | (u64)total);
-        } else {
-            st_volatile_u64(mine, ST_FLAG_AGG | tag | (u64)total);
+        if (tile > 0 && !(dbg & 1)) {
             int64_t t = tile - 1;
             while (true) {
-                const u64 v = ld_volatile_u64(status + (size_t)t * radix + tid);
-                if ((u32)((v >> 56) & 0x3F) != epoch || (v >> 62) == 0) {
-                    __nanosleep(20);
-                    continue;
+                u64 v[RS_WINDOW];
+#pragma unroll
+                for (int j = 0; j < RS_WINDOW; ++j)
+                    v[j] = (t - j >= 0) ? ld_volatile_u64(status + (size_t)(t - j) * radix + tid)
+                                        : (ST_FLAG_PREFIX | tag);
+                bool done = false;
+                int consumed = 0;
+#pragma unroll
+                for (int j = 0; j < RS_WINDOW; ++j) {
+                    if (done || consumed != j) continue;
+                    const u64 x = v[j];
+                    if ((u32)((x >> 56) & 0x3F) != epoch || (x >> 62) == 0) continue;   // not published yet
+                    excl += x & ST_VALUE_MASK;
+                    ++consumed;
+                    if ((x >> 62) == 2) done = true;
                 }
-                excl += v & ST_VALUE_MASK;
-                if ((v >> 62) == 2) break;
-                --t;
+                if (done) break;
+                t -= consumed;
+                if (consumed == 0) __nanosleep(20);
             }
             st_volatile_u64(mine, ST_FLAG_PREFIX | tag | (excl + (u64)total));
         }
         s_gbase[tid] = digit_base[tid] + excl - (u64)dstart;
     }
-    __syncthreads();
 
-    // -- stage keys in shared memory in digit order ------------------------------------------------------
+    // -- D: scatter into the digit-ordered staging buffer ---------------------------------------------------
 #pragma unroll
     for (int i = 0; i < RS_IPT; ++i) {
-        if ((lbase + i * 32) < n) {
+        if (i < my_n) {
             const u32 d = (u32)(key[i] >> shift) & mask;
-            const u32 pos = s_dstart[d] + my_whist[d] + rnk[i];
+            const u32 r = (i & 1) ? (rnk2[i >> 1] >> 16) : (rnk2[i >> 1] & 0xFFFFu);
+            const u32 pos = my_whist[d] + r;
             s_keys[pos] = key[i];
             if (HAS_VALS) s_vals[pos] = val[i];
         }
     }
     __syncthreads();
 
-    // -- coalesced per-digit runs out --------------------------------------------------------------------
+    // -- F: coalesced per-digit runs out --------------------------------------------------------------------
 #pragma unroll
     for (int i = 0; i < RS_IPT; ++i) {
         const int j = tid + i * RS_THREADS;
-        if (j < tile_n) {
+        if (j < tile_n && !(dbg & 4)) {
             const u64 k = s_keys[j];
             const u32 d = (u32)(k >> shift) & mask;
-            const u64 g = s_gbase[d] + (u64)j;
+            const u64 g = (dbg & 8) ? (u64)(tile_base + j) : s_gbase[d] + (u64)j;
             keys_out[g] = k;
             if (HAS_VALS) vals_out[g] = s_vals[j];
         }
     }
 }
 
-static size_t rs_smem_bytes(bool has_vals) {
+static size_t rs_smem_bytes(bool has_vals, int algo) {
     size_t b = (size_t)RS_TILE * 8 + (size_t)RS_WARPS * RS_RADIX * 4 + RS_RADIX * 4 + RS_RADIX * 8 +
                16 * 4 + 16 * 4;
+    if (algo == 2) b += (size_t)RS_WARPS * RS_RADIX * 4;
     if (has_vals) b += (size_t)RS_TILE * 4;
     return b;
 }
@@ -258,28 +321,42 @@ int radix_sort_pairs(ottocov_ctx* ctx, u64*& keys, u64*& alt, u32*& vals, u32*& 
     ensure_sweep_state(ctx, (size_t)n_tiles * RS_RADIX);
     CUDA_CHECK(cudaMemsetAsync(ctx->sweep_ticket, 0, RS_MAX_PASSES * sizeof(u32), ctx->stream));
 
-    const size_t smem = rs_smem_bytes(has_vals);
-    static bool attr_set = false;
-    if (!attr_set) {
-        CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<true>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(true)));
-        CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<false>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(false)));
-        attr_set = true;
+    static int algo = -1, dbg = 0;
+    if (algo < 0) {
+        const char* g = getenv("OTTOCOV_RS_DEBUG");           // timing experiments only (results are wrong)
+        dbg = g ? atoi(g) : 0;
+        const char* e = getenv("OTTOCOV_RS_ALGO");            // tuning knob, default = ballots
+        algo = e ? atoi(e) : 1;
+        if (algo < 0 || algo > 2) algo = 1;
     }
+    const size_t smem = rs_smem_bytes(has_vals, algo);
     const double pass_bytes = (has_vals ? 24.0 : 16.0) * (double)n;
     for (int p = 0; p < pl.n; ++p) {
         const u32 epoch = next_epoch(ctx);
-        if (has_vals) {
-            COV_LAUNCH(ctx, OTTOCOV_K_SORT_PASS, pass_bytes, rs_onesweep_kernel<true>, (unsigned)n_tiles,
-                       RS_THREADS, smem, keys, alt, vals, valt, n, pl.shift[p], pl.bits[p],
-                       ghist.p + (size_t)p * RS_RADIX, ctx->sweep_status, ctx->sweep_ticket + p, epoch);
-        } else {
-            COV_LAUNCH(ctx, OTTOCOV_K_SORT_PASS, pass_bytes, rs_onesweep_kernel<false>, (unsigned)n_tiles,
-                       RS_THREADS, smem, keys, alt, (const u32*)nullptr, (u32*)nullptr, n, pl.shift[p],
-                       pl.bits[p], ghist.p + (size_t)p * RS_RADIX, ctx->sweep_status,
-                       ctx->sweep_ticket + p, epoch);
-        }
+        const int bits = pl.bits[p];
+#define RS_LAUNCH(HV, AL, NBITS)                                                                            \
+        do {                                                                                                \
+            auto kern = rs_onesweep_kernel<HV, AL, NBITS>;                                                  \
+            static bool attr_done = false;                                                                  \
+            if (!attr_done) {                                                                               \
+                CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(true, 2))); \
+                CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); \
+                attr_done = true;                                                                           \
+            }                                                                                               \
+            COV_LAUNCH(ctx, OTTOCOV_K_SORT_PASS, pass_bytes, kern, (unsigned)n_tiles, RS_THREADS, smem, keys, alt, \
+                       (const u32*)vals, valt, n, pl.shift[p], bits, ghist.p + (size_t)p * RS_RADIX,        \
+                       ctx->sweep_status, ctx->sweep_ticket + p, epoch, dbg);                               \
+        } while (0)
+#define RS_DISPATCH(HV)                                                                                     \
+        if (algo == 0) RS_LAUNCH(HV, 0, 8);                                                                 \
+        else if (algo == 2) RS_LAUNCH(HV, 2, 8);                                                            \
+        else if (bits <= 4) RS_LAUNCH(HV, 1, 4);                                                            \
+        else if (bits <= 6) RS_LAUNCH(HV, 1, 6);                                                            \
+        else if (bits == 7) RS_LAUNCH(HV, 1, 7);                                                            \
+        else RS_LAUNCH(HV, 1, 8)
+        if (has_vals) { RS_DISPATCH(true); } else { RS_DISPATCH(false); }
+#undef RS_DISPATCH
+#undef RS_LAUNCH
         u64* tk = keys; keys = alt; alt = tk;
         if (has_vals) { u32* tv = vals; vals = valt; valt = tv; }
     }

@@ -9,95 +9,221 @@
 #include "internal.cuh"
 #include "scan.cuh"
 
-// ---- run heads ------------------------------------------------------------------------------------------
-template <class IdxT>
-struct RunHeads {
-    static constexpr int NC = 1;
-    const u64* keys;
-    u64* ukeys;
-    IdxT* ustart;
-    __device__ u64 value(int64_t i) const { return (i == 0 || keys[i] != keys[i - 1]) ? 1ull : 0ull; }
-    __device__ void apply(int64_t i, u64 v, const u64* pre) const {
-        if (!v) return;
-        ukeys[pre[0]] = keys[i];
-        ustart[pre[0]] = (IdxT)i;
+// ---- scan / look-back state ---------------------------------------------------------------------------
+void scan_state_prepare(ottocov_ctx* ctx, size_t status_words, u32* epoch_out) {
+    if (!ctx->scan_ticket) {
+        CUDA_CHECK(cudaMalloc((void**)&ctx->scan_ticket, 64));
+        CUDA_CHECK(cudaMalloc((void**)&ctx->scan_totals, 8 * sizeof(u64)));
     }
-};
-
-// count only: value() without outputs, used to size the result exactly
-struct RunHeadsCount {
-    static constexpr int NC = 1;
-    const u64* keys;
-    __device__ u64 value(int64_t i) const { return (i == 0 || keys[i] != keys[i - 1]) ? 1ull : 0ull; }
-    __device__ void apply(int64_t, u64, const u64*) const {}
-};
-
-template <class IdxT>
-__global__ void __launch_bounds__(256) run_length_kernel(const IdxT* __restrict__ ustart, int64_t n_runs,
-                                                         int64_t n, u32* __restrict__ count) {
-    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= n_runs) return;
-    const u64 a = (u64)ustart[u];
-    const u64 b = (u + 1 < n_runs) ? (u64)ustart[u + 1] : (u64)n;
-    count[u] = (u32)(b - a);
+    if (status_words > ctx->scan_status_words) {
+        if (ctx->scan_status) CUDA_CHECK(cudaFreeAsync(ctx->scan_status, ctx->stream));
+        ctx->scan_status = nullptr;
+        ctx->scan_status_words = 0;
+        const size_t cap = status_words + status_words / 4 + 1024;
+        CUDA_CHECK(cudaMallocAsync((void**)&ctx->scan_status, cap * sizeof(u64), ctx->stream));
+        CUDA_CHECK(cudaMemsetAsync(ctx->scan_status, 0, cap * sizeof(u64), ctx->stream));
+        ctx->scan_status_words = cap;
+        ctx->scan_epoch = 0;
+    }
+    if (ctx->scan_epoch >= 63) {
+        CUDA_CHECK(cudaMemsetAsync(ctx->scan_status, 0, ctx->scan_status_words * sizeof(u64), ctx->stream));
+        ctx->scan_epoch = 0;
+    }
+    *epoch_out = ++ctx->scan_epoch;
+    CUDA_CHECK(cudaMemsetAsync(ctx->scan_ticket, 0, 64, ctx->stream));
 }
 
-template <class IdxT>
-__global__ void __launch_bounds__(256) run_sum_kernel(const IdxT* __restrict__ ustart, int64_t n_runs,
-                                                      int64_t n, const u32* __restrict__ vals,
-                                                      u32* __restrict__ count) {
-    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= n_runs) return;
-    const u64 a = (u64)ustart[u];
-    const u64 b = (u + 1 < n_runs) ? (u64)ustart[u + 1] : (u64)n;
-    u64 s = 0;
-    for (u64 i = a; i < b; ++i) s += vals[i];
-    count[u] = (u32)(s > 0xFFFFFFFFull ? 0xFFFFFFFFull : s);
+// ---- run-length / segmented-sum reduce of sorted keys, fused with the count threshold ---------------------
+// One pass over the sorted keys (read 8 B/key, + 4 B/key payload when summing); writes 12 B per KEPT
+// run only.  Per tile of 2048 keys:
+//   1. heads (key != previous key) and ends (key != next key) per 32-key row by ballot; the running
+//      sum since the last head needs no shuffles when counting (lane - head lane + 1);
+//   2. the tile publishes (has_head, sum after its last head).  A run that began in an earlier tile
+//      gets its carry-in by walking back to the nearest tile that has a head -- a pure function of the
+//      data, so there is no prefix chain to wait on (almost always one step);
+//   3. every run END now knows the run's total; keep = total >= min_count;
+//   4. kept ends are compacted with the usual chained scan (aggregate / inclusive-prefix look-back).
+constexpr int RLE_THREADS = 256;
+constexpr int RLE_ITEMS = 8;
+constexpr int RLE_WARPS = RLE_THREADS / 32;
+constexpr int RLE_TILE = RLE_THREADS * RLE_ITEMS;
+constexpr u64 RLE_HAS_HEAD = 1ull << 55;
+constexpr u64 RLE_VALUE_MASK = (1ull << 55) - 1;
+
+template <bool HAS_VALS>
+__global__ void __launch_bounds__(RLE_THREADS)
+rle_kernel(const u64* __restrict__ keys, const u32* __restrict__ vals, int64_t n, int64_t n_tiles, u32 min_count,
+           u64* __restrict__ out_keys, u32* __restrict__ out_count, u64* status_tail, u64* status_keep,
+           u32* ticket, u32 epoch, u64* __restrict__ totals) {
+    __shared__ u64 s_wsum[RLE_WARPS];      // sum since the warp chunk's last head (whole chunk if none)
+    __shared__ u32 s_whead[RLE_WARPS];     // chunk contains a head
+    __shared__ u64 s_wcarry[RLE_WARPS];    // carry-in for runs that began before the chunk
+    __shared__ u32 s_wkeep[RLE_WARPS];
+    __shared__ u64 s_outbase;
+    __shared__ u32 s_tile;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const int64_t tile = s_tile;
+    const int64_t cb = tile * RLE_TILE + (int64_t)warp * 32 * RLE_ITEMS;    // chunk base
+    const u32 le = lanemask_lt() | (1u << lane);
+
+    u64 key[RLE_ITEMS];
+    u32 val[RLE_ITEMS];
+#pragma unroll
+    for (int r = 0; r < RLE_ITEMS; ++r) {
+        const int64_t idx = cb + r * 32 + lane;
+        key[r] = (idx < n) ? __ldcs(keys + idx) : 0ull;
+        val[r] = HAS_VALS ? ((idx < n) ? __ldcs(vals + idx) : 0u) : 1u;
+    }
+    // neighbours across the chunk edges
+    u64 edge_prev = 0, edge_next = 0;
+    if (lane == 0 && cb > 0 && cb <= n) edge_prev = keys[cb - 1];
+    if (lane == 31 && cb + 32 * RLE_ITEMS < n) edge_next = keys[cb + 32 * RLE_ITEMS];
+
+    u64 s[RLE_ITEMS];                      // inclusive sum since the last head at or before this element
+    u32 end_bits = 0, open_bits = 0;       // bit r: element is a run end / its run began before the chunk
+    u64 carry = 0;                         // sum since the last head, at the end of the previous row
+    bool seen_head = false;
+#pragma unroll
+    for (int r = 0; r < RLE_ITEMS; ++r) {
+        const int64_t idx = cb + r * 32 + lane;
+        const bool valid = idx < n;
+        u64 kprev = __shfl_up_sync(0xffffffffu, key[r], 1);
+        u64 knext = __shfl_down_sync(0xffffffffu, key[r], 1);
+        const u64 prow_last = __shfl_sync(0xffffffffu, key[r > 0 ? r - 1 : 0], 31);
+        const u64 nrow_first = __shfl_sync(0xffffffffu, key[r < RLE_ITEMS - 1 ? r + 1 : r], 0);
+        if (lane == 0) kprev = (r == 0) ? edge_prev : prow_last;
+        if (lane == 31) knext = (r == RLE_ITEMS - 1) ? edge_next : nrow_first;
+        const bool head = valid && (idx == 0 || key[r] != kprev);
+        const bool end = valid && (idx == n - 1 || key[r] != knext);
+        const u32 hm = __ballot_sync(0xffffffffu, head);
+        const u32 m = hm & le;
+        const bool has = m != 0;
+        const int pl = 31 - __clz(m);                      // lane of the last head at or before this lane
+        u64 si;
+        if (!HAS_VALS) {
+            si = has ? (u64)(lane - pl + 1) : carry + (u64)(lane + 1);
+        } else {
+            u64 inc = val[r];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const u64 t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            const u64 before_head = __shfl_sync(0xffffffffu, inc - val[r], has ? pl : 0);
+            si = has ? inc - before_head : carry + inc;
+        }
+        s[r] = si;
+        if (end) end_bits |= 1u << r;
+        if (!has && !seen_head) open_bits |= 1u << r;
+        carry = __shfl_sync(0xffffffffu, si, 31);
+        seen_head = seen_head || (hm != 0);
+    }
+    if (lane == 0) { s_wsum[warp] = carry; s_whead[warp] = seen_head ? 1u : 0u; }
+    __syncthreads();
+
+    if (threadIdx.x == 0) {
+        // tile aggregate: sum after the tile's last head (whole tile if it has none)
+        u64 tail = 0; bool hh = false;
+        for (int w = RLE_WARPS - 1; w >= 0; --w) {
+            tail += s_wsum[w];
+            if (s_whead[w]) { hh = true; break; }
+        }
+        const u64 tag = (u64)epoch << 56;
+        st_volatile_u64(status_tail + tile, SC_FLAG_AGG | tag | (hh ? RLE_HAS_HEAD : 0ull) | (tail & RLE_VALUE_MASK));
+        // carry-in of the tile: walk back to the nearest tile that contains a head (tile 0 always does)
+        u64 c_in = 0;
+        for (int64_t t = tile - 1; t >= 0; --t) {
+            u64 x;
+            while (true) {
+                x = ld_volatile_u64(status_tail + t);
+                if ((u32)((x >> 56) & 0x3F) == epoch && (x >> 62) != 0) break;
+                __nanosleep(40);
+            }
+            c_in += x & RLE_VALUE_MASK;
+            if (x & RLE_HAS_HEAD) break;
+        }
+        u64 cur = c_in;
+        for (int w = 0; w < RLE_WARPS; ++w) {
+            s_wcarry[w] = cur;
+            cur = s_whead[w] ? s_wsum[w] : cur + s_wsum[w];
+        }
+    }
+    __syncthreads();
+
+    // totals at the run ends, threshold, positions
+    const u64 wc = s_wcarry[warp];
+    const u32 lt = lanemask_lt();
+    u32 keep_bits = 0, wkeep = 0;
+    u32 pos[RLE_ITEMS];
+#pragma unroll
+    for (int r = 0; r < RLE_ITEMS; ++r) {
+        const u64 total = s[r] + (((open_bits >> r) & 1u) ? wc : 0ull);
+        s[r] = total;
+        const bool keep = ((end_bits >> r) & 1u) && total >= (u64)min_count;
+        const u32 km = __ballot_sync(0xffffffffu, keep);
+        pos[r] = wkeep + __popc(km & lt);
+        wkeep += __popc(km);
+        if (keep) keep_bits |= 1u << r;
+    }
+    if (lane == 0) s_wkeep[warp] = wkeep;
+    __syncthreads();
+    if (warp == 0) {
+        u64 k = (lane < RLE_WARPS) ? (u64)s_wkeep[lane] : 0ull;
+        k = warp_sum_u64(k);
+        const u64 pre = warp_lookback_sum(status_keep + tile, 1, tile, k, epoch);
+        if (lane == 0) {
+            s_outbase = pre;
+            if (tile == n_tiles - 1) totals[0] = pre + k;
+        }
+    }
+    __syncthreads();
+    u64 ob = s_outbase;
+    for (int w = 0; w < warp; ++w) ob += s_wkeep[w];
+#pragma unroll
+    for (int r = 0; r < RLE_ITEMS; ++r) {
+        if ((keep_bits >> r) & 1u) {
+            out_keys[ob + pos[r]] = key[r];
+            out_count[ob + pos[r]] = (u32)(s[r] > 0xFFFFFFFFull ? 0xFFFFFFFFull : s[r]);
+        }
+    }
 }
 
-// sums of tile totals only (pass 1 + 2 of the scan framework), to size outputs exactly
-template <class F>
-static u64 scan_count(ottocov_ctx* ctx, int family, const F& f, int64_t n, double bytes) {
-    if (n <= 0) return 0;
-    const int64_t n_tiles = ceil_div64(n, SCAN_TILE);
-    DevBuf<u64> sums(ctx, (size_t)n_tiles + 1);
-    COV_LAUNCH(ctx, family, bytes, (scan_reduce_kernel<F>), (unsigned)n_tiles, SCAN_THREADS, 0, f, n, n_tiles, sums.p);
-    COV_LAUNCH(ctx, OTTOCOV_K_MISC, n_tiles * 16.0, scan_block_sums_kernel, 1, 1024, 0, sums.p, n_tiles, sums.p + n_tiles);
-    u64 tot = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&tot, sums.p + n_tiles, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    return tot;
+// shrink an over-allocated result when most of it is unused (keeps long-lived tables small)
+template <class T>
+static T* shrink_to_fit(ottocov_ctx* ctx, DevBuf<T>& buf, int64_t used) {
+    if ((int64_t)buf.n <= 2 * used + 1024) return buf.take();
+    DevBuf<T> small(ctx, used);
+    if (used > 0)
+        CUDA_CHECK(cudaMemcpyAsync(small.p, buf.p, used * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
+    return small.take();
 }
 
-template <class IdxT>
-static void reduce_sorted_t(ottocov_ctx* ctx, const u64* keys, const u32* vals, int64_t n, int64_t n_runs,
-                            u64* ukeys, u32* ucount) {
-    DevBuf<IdxT> ustart(ctx, n_runs);
-    RunHeads<IdxT> f;
-    f.keys = keys; f.ukeys = ukeys; f.ustart = ustart.p;
-    scan_apply(ctx, OTTOCOV_K_RLE, f, n, nullptr, 16.0 * n + (8.0 + sizeof(IdxT)) * n_runs);
-    const unsigned grid = (unsigned)ceil_div64(n_runs, 256);
-    if (vals)
-        COV_LAUNCH(ctx, OTTOCOV_K_RLE, sizeof(IdxT) * n_runs + 4.0 * n + 4.0 * n_runs, run_sum_kernel<IdxT>, grid, 256, 0,
-                   ustart.p, n_runs, n, vals, ucount);
-    else
-        COV_LAUNCH(ctx, OTTOCOV_K_RLE, sizeof(IdxT) * n_runs + 4.0 * n_runs, run_length_kernel<IdxT>, grid, 256, 0,
-                   ustart.p, n_runs, n, ucount);
-}
-
-void reduce_sorted(ottocov_ctx* ctx, const u64* keys, const u32* vals, int64_t n, u64** out_keys,
+void reduce_sorted(ottocov_ctx* ctx, const u64* keys, const u32* vals, int64_t n, u32 min_count, u64** out_keys,
                    u32** out_count, int64_t* n_out) {
     *out_keys = nullptr; *out_count = nullptr; *n_out = 0;
     if (n <= 0) return;
-    RunHeadsCount fc; fc.keys = keys;
-    const int64_t n_runs = (int64_t)scan_count(ctx, OTTOCOV_K_RLE, fc, n, 8.0 * n);
-    DevBuf<u64> ukeys(ctx, n_runs);
-    DevBuf<u32> ucount(ctx, n_runs);
-    if (n < (int64_t)0xFFFFFFFFll) reduce_sorted_t<u32>(ctx, keys, vals, n, n_runs, ukeys.p, ucount.p);
-    else reduce_sorted_t<u64>(ctx, keys, vals, n, n_runs, ukeys.p, ucount.p);
-    *out_keys = ukeys.take();
-    *out_count = ucount.take();
-    *n_out = n_runs;
+    const int64_t n_tiles = ceil_div64(n, RLE_TILE);
+    DevBuf<u64> ukeys(ctx, n);             // upper bound: every key distinct (blocks come from the cache)
+    DevBuf<u32> ucount(ctx, n);
+    u32 epoch;
+    scan_state_prepare(ctx, 2 * (size_t)n_tiles, &epoch);
+    u64* st_tail = ctx->scan_status;
+    u64* st_keep = ctx->scan_status + n_tiles;
+    if (vals)
+        COV_LAUNCH(ctx, OTTOCOV_K_RLE, 12.0 * n, rle_kernel<true>, (unsigned)n_tiles, RLE_THREADS, 0, keys, vals, n,
+                   n_tiles, min_count, ukeys.p, ucount.p, st_tail, st_keep, ctx->scan_ticket, epoch, ctx->scan_totals);
+    else
+        COV_LAUNCH(ctx, OTTOCOV_K_RLE, 8.0 * n, rle_kernel<false>, (unsigned)n_tiles, RLE_THREADS, 0, keys, vals, n,
+                   n_tiles, min_count, ukeys.p, ucount.p, st_tail, st_keep, ctx->scan_ticket, epoch, ctx->scan_totals);
+    u64 rows = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&rows, ctx->scan_totals, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->stats[OTTOCOV_K_RLE].algo_bytes += 12.0 * (double)rows;
+    *out_keys = shrink_to_fit(ctx, ukeys, (int64_t)rows);
+    *out_count = shrink_to_fit(ctx, ucount, (int64_t)rows);
+    *n_out = (int64_t)rows;
 }
 
 // ---- small reductions -------------------------------------------------------------------------------------
@@ -162,7 +288,7 @@ static ottocov_table* sort_reduce_pairs(ottocov_ctx* ctx, DevBuf<u64>& keys, Dev
         u64* k = keys.p; u64* ka = kalt.p; u32* v = count.p; u32* va = valt.p;
         BitField fields[2] = {{0, aid_bits}, {32, 32 + aid_bits}};
         radix_sort_pairs(ctx, k, ka, v, va, n, fields, 2);
-        reduce_sorted(ctx, k, v, n, &out->keys, &out->count, &out->n);
+        reduce_sorted(ctx, k, v, n, 1, &out->keys, &out->count, &out->n);
     } catch (...) {
         delete out;
         throw;
@@ -261,16 +387,17 @@ ottocov_table* filter_table_impl(ottocov_ctx* ctx, const ottocov_table* t, u32 m
     out->aid_bits = t->aid_bits;
     if (t->n == 0) return out;
     try {
+        DevBuf<u64> ok(ctx, t->n);
+        DevBuf<u32> oc(ctx, t->n);
         KeepAtLeast f;
-        f.keys = t->keys; f.count = t->count; f.min_count = min_count; f.okeys = nullptr; f.ocount = nullptr;
-        const int64_t m = (int64_t)scan_count(ctx, OTTOCOV_K_FILTER, f, t->n, 4.0 * t->n);
-        if (m > 0) {
-            DevBuf<u64> ok(ctx, m);
-            DevBuf<u32> oc(ctx, m);
-            f.okeys = ok.p; f.ocount = oc.p;
-            scan_apply(ctx, OTTOCOV_K_FILTER, f, t->n, nullptr, 8.0 * t->n + 12.0 * t->n + 12.0 * m);
-            out->keys = ok.take(); out->count = oc.take(); out->n = m;
-        }
+        f.keys = t->keys; f.count = t->count; f.min_count = min_count; f.okeys = ok.p; f.ocount = oc.p;
+        u64 tot[1];
+        scan_apply(ctx, OTTOCOV_K_FILTER, f, t->n, tot, 4.0 * t->n);
+        const int64_t m = (int64_t)tot[0];
+        ctx->stats[OTTOCOV_K_FILTER].algo_bytes += 20.0 * (double)m;
+        out->keys = shrink_to_fit(ctx, ok, m);
+        out->count = shrink_to_fit(ctx, oc, m);
+        out->n = m;
     } catch (...) {
         delete out;
         throw;

@@ -1,19 +1,24 @@
-// scan.cuh -- generic "reduce / scan block sums / apply" exclusive-scan framework.
+// scan.cuh -- single-pass ("chained scan", decoupled look-back) exclusive-scan framework.
 //
-// Every compaction in the engine (duplicate removal, split by type, window records, run heads,
-// threshold filter, segment heads, destination partition) is the same shape: each element i has
-// up to NC small counters; element i needs the exclusive prefix of every counter.  A functor F
-// supplies
+// Every compaction in the engine (duplicate removal + split by type, window records, threshold
+// filter, segment heads, destination partition) has the same shape: element i carries up to NC small
+// counters and needs the exclusive prefix of each.  A functor F supplies
 //     static constexpr int NC;                    number of counters (1..3)
 //     __device__ u64  value(int64_t i) const;      the counters of element i, packed
 //     __device__ void apply(int64_t i, u64 packed_value, const u64* prefix /*[NC]*/) const;
-// Packing inside one tile: NC==1 -> the full 64 bits; NC==2 -> counter 0 in bits [0,52),
-// counter 1 in [52,64) (must stay < 4096 per tile: it is a 0/1 flag everywhere it is used);
-// NC==3 -> 21 bits each (0/1 flags).  Across tiles the counters are carried unpacked as u64.
+// Packing inside one tile: NC==1 -> the full 64 bits; NC==2 -> counter 0 in bits [0,52), counter 1
+// in [52,64) (a 0/1 flag everywhere it is used); NC==3 -> 21 bits each (0/1 flags).  Across tiles the
+// counters travel unpacked, one 64-bit status word per (tile, counter):
+//     flag(2) | epoch(6) | value(56)        flag 1 = tile aggregate, 2 = inclusive prefix
+// The epoch changes with every launch, so the status array is never cleared between launches.
 //
-// Element order inside a tile: warp w owns elements [w*32*ITEMS, (w+1)*32*ITEMS); in round r its
-// lane l handles element w*32*ITEMS + r*32 + l, so every warp access is a coalesced 32-wide row.
-// No inter-CTA waiting anywhere (three plain launches), so it cannot hang.
+// One kernel, one read of the input: a CTA takes the next tile (atomic ticket => it only ever waits
+// for tiles that have already started), scans it, publishes its aggregate, warp 0 resolves the
+// exclusive prefix over earlier tiles by a 32-wide look-back, then every element is handed to
+// F::apply with its global prefix.
+//
+// Element order inside a tile: warp w owns elements [w*32*ITEMS, (w+1)*32*ITEMS); in round r its lane
+// l handles element w*32*ITEMS + r*32 + l, so every warp access is a coalesced 32-wide row.
 #pragma once
 #include "internal.cuh"
 
@@ -21,6 +26,10 @@ constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 constexpr int SCAN_MAX_NC = 3;
+
+constexpr u64 SC_VALUE_MASK = (1ull << 56) - 1;
+constexpr u64 SC_FLAG_AGG = 1ull << 62;
+constexpr u64 SC_FLAG_PREFIX = 2ull << 62;
 
 template <int NC>
 __device__ __forceinline__ void scan_unpack(u64 p, u64* c) {
@@ -36,67 +45,71 @@ __device__ __forceinline__ void scan_unpack(u64 p, u64* c) {
     }
 }
 
-// pass 1: per-tile totals, unpacked: block_sums[c * n_tiles + tile]
-template <class F>
-__global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(F f, int64_t n, int64_t n_tiles,
-                                                                    u64* __restrict__ block_sums) {
-    __shared__ u64 s_part[SCAN_THREADS / 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)warp * 32 * SCAN_ITEMS + lane;
-    u64 sum = 0;
+__device__ __forceinline__ u64 warp_sum_u64(u64 v) {
 #pragma unroll
-    for (int r = 0; r < SCAN_ITEMS; ++r) {
-        int64_t i = base + r * 32;
-        if (i < n) sum += f.value(i);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
-    if (lane == 0) s_part[warp] = sum;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        u64 t = 0;
-        for (int w = 0; w < SCAN_THREADS / 32; ++w) t += s_part[w];
-        u64 c[SCAN_MAX_NC];
-        scan_unpack<F::NC>(t, c);
-        for (int k = 0; k < F::NC; ++k) block_sums[(int64_t)k * n_tiles + blockIdx.x] = c[k];
-    }
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
 }
 
-// pass 2: one CTA per counter turns its row of tile totals into exclusive prefixes; totals[c] = sum
-static __global__ void __launch_bounds__(1024) scan_block_sums_kernel(u64* __restrict__ block_sums,
-                                                               int64_t n_tiles,
-                                                               u64* __restrict__ totals) {
-    __shared__ u64 s_warp[1024 / 32 + 1];
-    u64* row = block_sums + (int64_t)blockIdx.x * n_tiles;
-    u64 carry = 0;
-    for (int64_t b = 0; b < n_tiles; b += 1024) {
-        int64_t i = b + threadIdx.x;
-        u64 v = (i < n_tiles) ? row[i] : 0;
-        u64 tot;
-        u64 ex = block_exclusive_scan<u64, 1024>(v, s_warp, &tot);
-        if (i < n_tiles) row[i] = carry + ex;
-        carry += tot;
+// Called by all 32 lanes of ONE warp.  `word` points at status[tile] for one counter, consecutive tiles
+// are `stride` words apart.  Publishes `aggregate`, returns the exclusive prefix over tiles < tile and
+// publishes the inclusive prefix.
+__device__ __forceinline__ u64 warp_lookback_sum(u64* word, int64_t stride, int64_t tile, u64 aggregate,
+                                                 u32 epoch) {
+    const int lane = threadIdx.x & 31;
+    const u64 tag = (u64)epoch << 56;
+    if (tile == 0) {
+        if (lane == 0) st_volatile_u64(word, SC_FLAG_PREFIX | tag | aggregate);
+        return 0;
     }
-    if (threadIdx.x == 0 && totals) totals[blockIdx.x] = carry;
+    if (lane == 0) st_volatile_u64(word, SC_FLAG_AGG | tag | aggregate);
+    u64 excl = 0;
+    int64_t base = tile - 1;                       // lane l looks at tile base - l
+    while (true) {
+        const int64_t idx = base - lane;
+        const u64 v = (idx >= 0) ? ld_volatile_u64(word - (tile - idx) * stride) : (SC_FLAG_PREFIX | tag);
+        const bool ready = ((u32)((v >> 56) & 0x3F) == epoch) && ((v >> 62) != 0);
+        const u32 rmask = __ballot_sync(0xffffffffu, ready);
+        const u32 pmask = __ballot_sync(0xffffffffu, ready && (v >> 62) == 2);
+        const int first_nr = (~rmask) ? (__ffs(~rmask) - 1) : 32;    // lanes [0, first_nr) are ready
+        const int first_p = pmask ? (__ffs(pmask) - 1) : 32;
+        if (first_p < first_nr) {                  // a prefix inside the ready run: done
+            excl += warp_sum_u64(lane <= first_p ? (v & SC_VALUE_MASK) : 0ull);
+            break;
+        }
+        excl += warp_sum_u64(lane < first_nr ? (v & SC_VALUE_MASK) : 0ull);
+        base -= first_nr;
+        if (first_nr == 0) __nanosleep(40);
+    }
+    if (lane == 0) st_volatile_u64(word, SC_FLAG_PREFIX | tag | (excl + aggregate));
+    return excl;
 }
 
-// pass 3: recompute the values, scan inside the tile, add the tile prefix, hand to F::apply
 template <class F>
-__global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(F f, int64_t n, int64_t n_tiles,
-                                                                   const u64* __restrict__ block_prefix) {
+__global__ void __launch_bounds__(SCAN_THREADS) scan_onepass_kernel(F f, int64_t n, int64_t n_tiles, u64* status,
+                                                                     u32* ticket, u32 epoch,
+                                                                     u64* __restrict__ totals) {
     __shared__ u64 s_warp_tot[SCAN_THREADS / 32];
+    __shared__ u64 s_tile_pref[SCAN_MAX_NC];
+    __shared__ u32 s_tile;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)warp * 32 * SCAN_ITEMS + lane;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const int64_t tile = s_tile;
+    const int64_t base = tile * SCAN_TILE + (int64_t)warp * 32 * SCAN_ITEMS + lane;
     u64 v[SCAN_ITEMS], ex[SCAN_ITEMS];
     u64 carry = 0;      // packed running total of this warp's earlier rounds
 #pragma unroll
     for (int r = 0; r < SCAN_ITEMS; ++r) {
-        int64_t i = base + r * 32;
+        const int64_t i = base + r * 32;
         v[r] = (i < n) ? f.value(i) : 0;
+    }
+#pragma unroll
+    for (int r = 0; r < SCAN_ITEMS; ++r) {
         u64 inc = v[r];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            u64 t = __shfl_up_sync(0xffffffffu, inc, o);
+            const u64 t = __shfl_up_sync(0xffffffffu, inc, o);
             if (lane >= o) inc += t;
         }
         ex[r] = carry + inc - v[r];
@@ -104,21 +117,38 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(F f, int64_t n
     }
     if (lane == 0) s_warp_tot[warp] = carry;
     __syncthreads();
+    if (warp == 0) {
+        u64 t = (lane < SCAN_THREADS / 32) ? s_warp_tot[lane] : 0ull;
+        t = warp_sum_u64(t);
+        u64 c[SCAN_MAX_NC];
+        scan_unpack<F::NC>(t, c);
+#pragma unroll
+        for (int k = 0; k < F::NC; ++k) {
+            const u64 pre = warp_lookback_sum(status + tile * F::NC + k, F::NC, tile, c[k], epoch);
+            if (lane == 0) {
+                s_tile_pref[k] = pre;
+                if (tile == n_tiles - 1) totals[k] = pre + c[k];
+            }
+        }
+    }
+    __syncthreads();
     u64 warp_off = 0;
     for (int w = 0; w < warp; ++w) warp_off += s_warp_tot[w];
-    u64 tile_pref[SCAN_MAX_NC];
-    for (int k = 0; k < F::NC; ++k) tile_pref[k] = block_prefix[(int64_t)k * n_tiles + blockIdx.x];
 #pragma unroll
     for (int r = 0; r < SCAN_ITEMS; ++r) {
-        int64_t i = base + r * 32;
+        const int64_t i = base + r * 32;
         if (i < n) {
             u64 c[SCAN_MAX_NC], pre[SCAN_MAX_NC];
             scan_unpack<F::NC>(warp_off + ex[r], c);
-            for (int k = 0; k < F::NC; ++k) pre[k] = tile_pref[k] + c[k];
+#pragma unroll
+            for (int k = 0; k < F::NC; ++k) pre[k] = s_tile_pref[k] + c[k];
             f.apply(i, v[r], pre);
         }
     }
 }
+
+// grow-only status words + ticket + totals; returns the epoch to launch with
+void scan_state_prepare(ottocov_ctx* ctx, size_t status_words, u32* epoch_out);     // reduce.cu
 
 // Host driver.  totals_host (may be nullptr) receives the NC grand totals and forces a stream sync.
 template <class F>
@@ -128,17 +158,13 @@ static void scan_apply(ottocov_ctx* ctx, int family, const F& f, int64_t n, u64*
         for (int k = 0; k < F::NC; ++k) totals_host[k] = 0;
     if (n <= 0) return;
     const int64_t n_tiles = ceil_div64(n, SCAN_TILE);
-    DevBuf<u64> sums(ctx, (size_t)n_tiles * F::NC + SCAN_MAX_NC);
-    u64* totals_dev = sums.p + (size_t)n_tiles * F::NC;
-    COV_LAUNCH(ctx, family, algo_bytes * 0.5, (scan_reduce_kernel<F>), (unsigned)n_tiles,
-               SCAN_THREADS, 0, f, n, n_tiles, sums.p);
-    COV_LAUNCH(ctx, OTTOCOV_K_MISC, n_tiles * 16.0 * F::NC, scan_block_sums_kernel, F::NC, 1024, 0,
-               sums.p, n_tiles, totals_dev);
-    COV_LAUNCH(ctx, family, algo_bytes * 0.5, (scan_apply_kernel<F>), (unsigned)n_tiles,
-               SCAN_THREADS, 0, f, n, n_tiles, sums.p);
+    u32 epoch;
+    scan_state_prepare(ctx, (size_t)n_tiles * F::NC, &epoch);
+    COV_LAUNCH(ctx, family, algo_bytes, (scan_onepass_kernel<F>), (unsigned)n_tiles, SCAN_THREADS, 0, f, n, n_tiles,
+               ctx->scan_status, ctx->scan_ticket, epoch, ctx->scan_totals);
     if (totals_host) {
-        CUDA_CHECK(cudaMemcpyAsync(totals_host, totals_dev, sizeof(u64) * F::NC,
-                                   cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaMemcpyAsync(totals_host, ctx->scan_totals, sizeof(u64) * F::NC, cudaMemcpyDeviceToHost,
+                                   ctx->stream));
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     }
 }

@@ -101,22 +101,16 @@ void topk_impl(ottocov_ctx* ctx, const ottocov_table* t, int k) {
     free_topk(ctx);
     ctx->topk_k = k;
     if (t->n == 0) return;
+    // number of distinct aids is bounded by min(rows, 2^aid_bits)
+    int64_t cap = t->n;
+    if (t->aid_bits < 40 && ((int64_t)1 << t->aid_bits) < cap) cap = (int64_t)1 << t->aid_bits;
+    DevBuf<u64> seg_start(ctx, cap);
     SegmentHeads f;
-    f.keys = t->keys; f.seg_start = nullptr;
-    const int64_t n_tiles = ceil_div64(t->n, SCAN_TILE);
-    // count segments first (exact allocation), then materialise their starts
-    u64 n_seg;
-    {
-        DevBuf<u64> sums(ctx, (size_t)n_tiles + 1);
-        COV_LAUNCH(ctx, OTTOCOV_K_TOPK, 8.0 * t->n, (scan_reduce_kernel<SegmentHeads>), (unsigned)n_tiles, SCAN_THREADS, 0,
-                   f, t->n, n_tiles, sums.p);
-        COV_LAUNCH(ctx, OTTOCOV_K_MISC, 16.0 * n_tiles, scan_block_sums_kernel, 1, 1024, 0, sums.p, n_tiles, sums.p + n_tiles);
-        CUDA_CHECK(cudaMemcpyAsync(&n_seg, sums.p + n_tiles, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    }
-    DevBuf<u64> seg_start(ctx, n_seg);
-    f.seg_start = seg_start.p;
-    scan_apply(ctx, OTTOCOV_K_TOPK, f, t->n, nullptr, 16.0 * t->n + 8.0 * n_seg);
+    f.keys = t->keys; f.seg_start = seg_start.p;
+    u64 tot[1];
+    scan_apply(ctx, OTTOCOV_K_TOPK, f, t->n, tot, 8.0 * t->n);
+    const u64 n_seg = tot[0];
+    ctx->stats[OTTOCOV_K_TOPK].algo_bytes += 8.0 * (double)n_seg;
     DevBuf<int32_t> ax(ctx, n_seg), nv(ctx, n_seg), ay(ctx, n_seg * k), ac(ctx, n_seg * k);
     const int64_t warps_needed = (int64_t)n_seg;
     int grid = (int)imin64(ceil_div64(warps_needed, 8), (int64_t)ctx->num_sms * 32);

@@ -154,6 +154,15 @@ class Engine:
     def synchronize(self):
         self._check(self._lib.ottocov_synchronize(self._ctx))
 
+    def trim(self):
+        """Give cached device blocks back to the driver."""
+        self._check(self._lib.ottocov_trim(self._ctx))
+
+    def memory_info(self) -> Dict[str, int]:
+        a, b, c = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        self._check(self._lib.ottocov_memory_info(self._ctx, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return {"live_bytes": a.value, "cached_bytes": b.value, "peak_bytes": c.value}
+
     def set_profiling(self, on: bool):
         self._check(self._lib.ottocov_set_profiling(self._ctx, int(on)))
 
@@ -193,8 +202,9 @@ class Engine:
     # ---- (2)+(3) expansion + reduce-by-key ------------------------------------------------------------
     def count(self, name: Optional[str] = None, *, type_this: Optional[int] = None,
               next_types: Optional[Sequence[int]] = None, window: Optional[int] = None,
-              pair_budget: Optional[int] = None) -> Table:
-        """One iteration of count_co_events' loop (count_co_events.py:64-72) on the loaded events."""
+              pair_budget: Optional[int] = None, min_count: int = 1) -> Table:
+        """One iteration of count_co_events' loop (count_co_events.py:64-72) on the loaded events.
+        min_count > 1 fuses filter(count >= min_count) (count_co_events.py:172) into the reduce."""
         if name is not None:
             th, mask, w = self.config.spec(name)
         else:
@@ -204,7 +214,7 @@ class Engine:
         if window is not None:
             w = int(window)
         budget = self.config.PAIR_BUDGET if pair_budget is None else int(pair_budget)
-        spec = _lib.Spec(th, mask, w, budget)
+        spec = _lib.Spec(th, mask, w, budget, max(int(min_count), 0), 0)
         h = ctypes.c_void_p()
         self._sync_stream()
         self._check(self._lib.ottocov_count(self._ctx, ctypes.byref(spec), ctypes.byref(h)))
@@ -300,9 +310,6 @@ class Engine:
     # ---- convenience: whole hot path for one co-event kind ------------------------------------------------------
     def count_topk(self, name: str, min_count: Optional[int] = None, k: Optional[int] = None):
         """expand -> reduce -> threshold -> top-K for one name; returns (filtered Table, topk tuple)."""
-        t = self.count(name)
         thr = self.config.MIN_COUNT_TO_SAVE.get(name, 1) if min_count is None else min_count
-        f = self.filter(t, thr) if thr > 1 else t
-        if f is not t:
-            t.free()
+        f = self.count(name, min_count=thr)
         return f, self.topk(f, k)

@@ -153,6 +153,35 @@ def test_invariants_on_gpu(engine):
     assert w1 == w2
 
 
+def test_fused_threshold_equals_filter(engine):
+    s, a, t, y = small_events(23, n_sessions=800, n_aids=60)
+    engine.load_events(s, a, t, y)
+    for name in ("click_to_click", "click_to_cart_or_buy"):
+        full = engine.count(name)
+        for thr in (1, 2, 3, 7, 1000):
+            want = engine.filter(full, thr)
+            got = engine.count(name, min_count=thr)
+            assert engine.count_info()["n_pairs"] == full.total()
+            for x, z in zip(got.fetch(), want.fetch()):
+                assert np.array_equal(x, z)
+            # chunked: thresholds must still apply to complete sums
+            got2 = engine.count(name, min_count=thr, pair_budget=4096)
+            for x, z in zip(got2.fetch(), want.fetch()):
+                assert np.array_equal(x, z)
+
+
+def test_long_runs_span_tiles(engine):
+    # one pair repeated far beyond a reduce tile (2048 keys): carries must cross many tiles
+    n = 30_000
+    s = np.zeros(n); a = np.where(np.arange(n) % 2 == 0, 5, 9); t = np.full(n, 1000) + np.arange(n) % 7
+    y = np.zeros(n)
+    # events are distinct only by ts (7 values) -> after dedup 14 events; use distinct ts instead
+    t = 1_660_000_000 + np.arange(n) % 40_000
+    _check_all_names(engine, s, a, t, y, names=["click_to_click"])
+    tab = engine.table_from_arrays(np.full(50_000, 3), np.full(50_000, 4), np.ones(50_000))
+    assert tab.to_dict() == {(3, 4): 50_000}
+
+
 def test_device_resident_inputs(engine):
     s, a, t, y = small_events(17, n_sessions=300, shuffle=True)
     ts_ = [torch.from_numpy(x).cuda() for x in (s, a, t, y)]

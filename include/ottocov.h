@@ -53,6 +53,8 @@ typedef struct ottocov_table ottocov_table;
 
 /* One co-event kind = one entry of config.MAP_NAME_COUNT_TYPE + MAP_MAX_TIME_TO_NEXT
  * (reference config.py:43-49, 81-88). */
+enum { OTTOCOV_SYM_OFF = 1, OTTOCOV_SYM_ON = 2 };
+
 typedef struct {
     int32_t type_this;       /* source event type: 0 click, 1 cart, 2 order                       */
     uint32_t next_mask;      /* bit t set <=> events of type t are "next" events                  */
@@ -61,7 +63,10 @@ typedef struct {
     int64_t pair_budget;     /* max co-event pairs expanded at once (HBM footprint); 0 = auto     */
     uint32_t min_count;      /* keep only pairs with count >= min_count (0 or 1 = keep all); fused */
                              /* into the run-length reduce: filter(count >= ...) of :131-132, :172  */
-    uint32_t reserved;       /* must be 0                                                           */
+    uint32_t flags;          /* 0 = auto.  Kinds whose source and target type agree are symmetric  */
+                             /* (count(a,b) == count(b,a)): the engine may expand each unordered    */
+                             /* event pair once and mirror the reduced table.  Auto does so when    */
+                             /* min_count > 1.  OTTOCOV_SYM_OFF / OTTOCOV_SYM_ON force the choice.   */
 } ottocov_spec;
 
 typedef struct {
@@ -101,7 +106,8 @@ int ottocov_synchronize(ottocov_ctx* ctx);
  * ottocov_trim hands them back to the driver; ottocov_memory_info reports the footprint. */
 int ottocov_trim(ottocov_ctx* ctx);
 int ottocov_memory_info(ottocov_ctx* ctx, int64_t* live_bytes, int64_t* cached_bytes, int64_t* peak_bytes);
-int ottocov_set_profiling(ottocov_ctx* ctx, int on);         /* CUDA-event timing per family       */
+int ottocov_set_profiling(ottocov_ctx* ctx, int on);         /* 0 off, 1 all families, else a bit  */
+                                                             /* mask (1 << family): CUDA events    */
 int ottocov_kernel_stats(ottocov_ctx* ctx, ottocov_kernel_stat* out /*[OTTOCOV_K_FAMILIES]*/, int reset);
 const char* ottocov_kernel_family_name(int family);
 

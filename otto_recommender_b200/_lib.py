@@ -23,7 +23,7 @@ class OttocovError(RuntimeError):
 
 class Spec(Structure):
     _fields_ = [("type_this", c_int32), ("next_mask", c_uint32), ("window", c_int64), ("pair_budget", c_int64),
-                ("min_count", c_uint32), ("reserved", c_uint32)]
+                ("min_count", c_uint32), ("flags", c_uint32)]
 
 
 class EventsInfo(Structure):

@@ -10,7 +10,7 @@ static const char* k_family_names[OTTOCOV_K_FAMILIES] = {
 
 void ottocov_ctx::begin(int family) {
     stats[family].launches += 1;
-    if (!profiling) return;
+    if (!((profiling >> family) & 1u)) return;
     ProfEvent pe;
     pe.family = family;
     auto grab = [&]() {
@@ -26,7 +26,7 @@ void ottocov_ctx::begin(int family) {
 
 void ottocov_ctx::end(int family, double algo_bytes) {
     stats[family].algo_bytes += algo_bytes;
-    if (!profiling || prof_pending.empty()) return;
+    if (!((profiling >> family) & 1u) || prof_pending.empty()) return;
     ProfEvent& pe = prof_pending.back();
     if (pe.family == family && pe.b) cudaEventRecord(pe.b, stream);
 }
@@ -228,7 +228,7 @@ int ottocov_synchronize(ottocov_ctx* ctx) {
 int ottocov_set_profiling(ottocov_ctx* ctx, int on) {
     API_BEGIN(ctx)
     resolve_profile(ctx);
-    ctx->profiling = on != 0;
+    ctx->profiling = on == 1 ? 0xFFFFFFFFu : (unsigned)on;      // 1 = every family, else a bit mask << 0
     API_END(ctx)
 }
 

@@ -80,6 +80,21 @@ __global__ void __launch_bounds__(256) window_kernel(const u64* __restrict__ src
     cnt_out[j] = hi - lo - (self ? 1u : 0u);
 }
 
+// Symmetric kinds (source type == target type): every unordered event pair {i, j} is emitted ONCE, from
+// its earlier event, as the canonical key (min aid, max aid); count(a, b) == count(b, a) is restored by
+// mirroring the reduced table.  Targets are the events after j inside the window.
+__global__ void __launch_bounds__(256) window_fwd_kernel(const u64* __restrict__ key, int64_t n, u32 window,
+                                                         u32* __restrict__ lo_out, u32* __restrict__ cnt_out) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const u64 k = key[j];
+    const u32 t = (u32)k;
+    const u64 upper = (k & 0xFFFFFFFF00000000ull) | (u64)(t > 0xFFFFFFFFu - window ? 0xFFFFFFFFu : t + window);
+    const u32 hi = upper_bound_fwd(key, (u32)n, (u32)j, upper);
+    lo_out[j] = (u32)j + 1u;
+    cnt_out[j] = hi - (u32)j - 1u;
+}
+
 // compaction of the non-empty sources into records (src, lo, output offset)
 struct WindowRecords {
     static constexpr int NC = 2;
@@ -117,7 +132,13 @@ __global__ void __launch_bounds__(256) tile_search_kernel(const u64* __restrict_
     tile_rec[t] = (u32)(lo - 1);
 }
 
-template <bool SELF>
+template <bool CANON>
+__device__ __forceinline__ u64 make_pair_key(u32 a, u32 b) {
+    if (CANON) { const u32 lo = a < b ? a : b, hi = a < b ? b : a; return ((u64)lo << 32) | (u64)hi; }
+    return ((u64)a << 32) | (u64)b;
+}
+
+template <bool SELF, bool CANON>
 __global__ void __launch_bounds__(EX_THREADS)
 expand_kernel(const u32* __restrict__ rec_src, const u32* __restrict__ rec_lo,
               const u64* __restrict__ rec_off, const u32* __restrict__ tile_rec,
@@ -171,12 +192,12 @@ expand_kernel(const u32* __restrict__ rec_src, const u32* __restrict__ rec_lo,
         u32 j = lo;
         u32 tgt = s_lo[j] + (k - s_off[j]);
         if (SELF) tgt += (tgt >= s_src[j]);
-        const u64 key0 = ((u64)s_aid[j] << 32) | (u64)aid_tgt[tgt];
+        const u64 key0 = make_pair_key<CANON>(s_aid[j], aid_tgt[tgt]);
         if (k + 1 < n_out) {
             if (j + 1 < n_rec && s_off[j + 1] <= k + 1) ++j;
             u32 tgt1 = s_lo[j] + (k + 1 - s_off[j]);
             if (SELF) tgt1 += (tgt1 >= s_src[j]);
-            const u64 key1 = ((u64)s_aid[j] << 32) | (u64)aid_tgt[tgt1];
+            const u64 key1 = make_pair_key<CANON>(s_aid[j], aid_tgt[tgt1]);
             if (vec_ok) {
                 ulonglong2 v; v.x = key0; v.y = key1;
                 __stcs(reinterpret_cast<ulonglong2*>(tile_dst + k), v);
@@ -217,6 +238,12 @@ ottocov_table* count_impl(ottocov_ctx* ctx, const ottocov_spec* spec) {
     ottocov_count_info& ci = ctx->last_count;
     memset(&ci, 0, sizeof(ci));
 
+    // symmetric shortcut: one canonical key per unordered event pair, mirrored after the reduce.  Pays
+    // when the threshold leaves few rows to mirror; OTTOCOV_SYM_OFF / OTTOCOV_SYM_ON force the choice.
+    const u32 user_min = spec->min_count > 1 ? spec->min_count : 1;
+    const bool sym_kind = spec->next_mask == (1u << A);
+    const bool sym = sym_kind && !(spec->flags & 1u) && ((spec->flags & 2u) || user_min > 1);
+
     // ---- window + records per target type ---------------------------------------------------------
     std::vector<Segment*> segs;
     struct SegGuard { std::vector<Segment*>& v; ~SegGuard() { for (auto* s : v) delete s; } } guard{segs};
@@ -232,8 +259,12 @@ ottocov_table* count_impl(ottocov_ctx* ctx, const ottocov_spec* spec) {
         const u32* xr = nullptr;
         if (!sg->self) xr = (B == (A + 1) % 3) ? src.xrank[0] : src.xrank[1];
         DevBuf<u32> lo(ctx, src.n), cnt(ctx, src.n);
-        COV_LAUNCH(ctx, OTTOCOV_K_WINDOW, 20.0 * src.n, window_kernel, (unsigned)ceil_div64(src.n, 256), 256, 0,
-                   src.skey, xr, src.n, tgt.skey, (u32)tgt.n, W, lo.p, cnt.p);
+        if (sym)
+            COV_LAUNCH(ctx, OTTOCOV_K_WINDOW, 16.0 * src.n, window_fwd_kernel, (unsigned)ceil_div64(src.n, 256), 256, 0,
+                       src.skey, src.n, W, lo.p, cnt.p);
+        else
+            COV_LAUNCH(ctx, OTTOCOV_K_WINDOW, 20.0 * src.n, window_kernel, (unsigned)ceil_div64(src.n, 256), 256, 0,
+                       src.skey, xr, src.n, tgt.skey, (u32)tgt.n, W, lo.p, cnt.p);
         sg->rec_src.alloc(ctx, src.n); sg->rec_lo.alloc(ctx, src.n); sg->rec_off.alloc(ctx, src.n);
         WindowRecords f;
         f.lo = lo.p; f.cnt = cnt.p;
@@ -244,7 +275,7 @@ ottocov_table* count_impl(ottocov_ctx* ctx, const ottocov_spec* spec) {
         sg->n_rec = tot[1];
         P += tot[0];
     }
-    ci.n_pairs = (int64_t)P;
+    ci.n_pairs = (int64_t)(sym ? 2 * P : P);       // ordered co-event pairs, as the reference counts them
     if (P == 0) { ci.n_chunks = 0; return make_empty_table(aid_bits); }
 
     // ---- chunking by pair budget ----------------------------------------------------------------------
@@ -260,7 +291,6 @@ ottocov_table* count_impl(ottocov_ctx* ctx, const ottocov_spec* spec) {
     budget = (budget / EX_TILE) * EX_TILE;
     if (budget == 0) budget = EX_TILE;
 
-    const u32 user_min = spec->min_count > 1 ? spec->min_count : 1;
     const u32 fused_min = (P <= budget) ? user_min : 1;     // thresholds apply to complete sums only
     std::vector<ottocov_table*> partials;
     struct PartGuard {
@@ -287,11 +317,14 @@ ottocov_table* count_impl(ottocov_ctx* ctx, const ottocov_spec* spec) {
                 const TypeArray& tgt = ctx->ta[sg->tgt_type];
                 u64* dst = keys.p + (a - c0);
                 const double bytes = 8.0 * (double)(oe - ob);
-                if (sg->self)
-                    COV_LAUNCH(ctx, OTTOCOV_K_EXPAND, bytes, expand_kernel<true>, (unsigned)n_tiles, EX_THREADS, 0,
+                if (sym)
+                    COV_LAUNCH(ctx, OTTOCOV_K_EXPAND, bytes, (expand_kernel<false, true>), (unsigned)n_tiles, EX_THREADS, 0,
+                               sg->rec_src.p, sg->rec_lo.p, sg->rec_off.p, tile_rec.p, src.aid, tgt.aid, ob, oe, dst);
+                else if (sg->self)
+                    COV_LAUNCH(ctx, OTTOCOV_K_EXPAND, bytes, (expand_kernel<true, false>), (unsigned)n_tiles, EX_THREADS, 0,
                                sg->rec_src.p, sg->rec_lo.p, sg->rec_off.p, tile_rec.p, src.aid, tgt.aid, ob, oe, dst);
                 else
-                    COV_LAUNCH(ctx, OTTOCOV_K_EXPAND, bytes, expand_kernel<false>, (unsigned)n_tiles, EX_THREADS, 0,
+                    COV_LAUNCH(ctx, OTTOCOV_K_EXPAND, bytes, (expand_kernel<false, false>), (unsigned)n_tiles, EX_THREADS, 0,
                                sg->rec_src.p, sg->rec_lo.p, sg->rec_off.p, tile_rec.p, src.aid, tgt.aid, ob, oe, dst);
             }
             seg_start = seg_end;
@@ -301,7 +334,7 @@ ottocov_table* count_impl(ottocov_ctx* ctx, const ottocov_spec* spec) {
         ottocov_table* part = new ottocov_table();
         part->aid_bits = aid_bits;
         partials.push_back(part);
-        reduce_sorted(ctx, k, nullptr, (int64_t)cn, fused_min, &part->keys, &part->count, &part->n);
+        reduce_sorted(ctx, k, nullptr, (int64_t)cn, fused_min, sym, &part->keys, &part->count, &part->n);
         ci.n_chunks += 1;
     }
 
@@ -316,6 +349,11 @@ ottocov_table* count_impl(ottocov_ctx* ctx, const ottocov_spec* spec) {
             dev_free(ctx, result->keys); dev_free(ctx, result->count); delete result;
             result = f;
         }
+    }
+    if (sym) {                                      // (a, b, c) -> also (b, a, c)
+        ottocov_table* full = mirror_table_impl(ctx, result);
+        dev_free(ctx, result->keys); dev_free(ctx, result->count); delete result;
+        result = full;
     }
     ci.n_unique = result->n;
     return result;

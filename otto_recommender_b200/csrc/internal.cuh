@@ -62,7 +62,7 @@ struct ottocov_ctx {
     cudaStream_t stream = 0;
     std::string err;
     // profiling / accounting
-    bool profiling = false;
+    unsigned profiling = 0;            // bit f set: CUDA-event timing of kernel family f
     ottocov_kernel_stat stats[OTTOCOV_K_FAMILIES];
     std::vector<ProfEvent> prof_pending;
     std::vector<cudaEvent_t> event_pool;
@@ -158,8 +158,12 @@ ottocov_table* count_impl(ottocov_ctx* ctx, const ottocov_spec* spec);
 // reduce.cu
 // sorted keys -> distinct keys + run lengths (vals == nullptr) or summed payload (vals != nullptr),
 // keeping only rows whose count is >= min_count
-void reduce_sorted(ottocov_ctx* ctx, const u64* keys, const u32* vals, int64_t n, u32 min_count,
+// `sym`: keys are canonical (min aid, max aid) pairs counted once per unordered event pair; a
+// diagonal key (a, a) then stands for two ordered pairs, so its total is doubled before the threshold.
+void reduce_sorted(ottocov_ctx* ctx, const u64* keys, const u32* vals, int64_t n, u32 min_count, bool sym,
                    u64** out_keys, u32** out_count, int64_t* n_out);
+// half table (rows a <= b) -> full symmetric table
+ottocov_table* mirror_table_impl(ottocov_ctx* ctx, const ottocov_table* half);
 ottocov_table* merge_tables_impl(ottocov_ctx* ctx, ottocov_table* const* tabs, int n_tabs);
 ottocov_table* filter_table_impl(ottocov_ctx* ctx, const ottocov_table* t, u32 min_count);
 void fetch_table_impl(ottocov_ctx* ctx, const ottocov_table* t, int order, int64_t head,

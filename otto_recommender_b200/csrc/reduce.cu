@@ -8,6 +8,7 @@
 //   partition          stable split by hash(aid) % R for the multi-GPU exchange (no reference counterpart)
 #include "internal.cuh"
 #include "scan.cuh"
+#include <type_traits>
 
 // ---- scan / look-back state ---------------------------------------------------------------------------
 void scan_state_prepare(ottocov_ctx* ctx, size_t status_words, u32* epoch_out) {
@@ -44,17 +45,19 @@ void scan_state_prepare(ottocov_ctx* ctx, size_t status_words, u32* epoch_out) {
 //   3. every run END now knows the run's total; keep = total >= min_count;
 //   4. kept ends are compacted with the usual chained scan (aggregate / inclusive-prefix look-back).
 constexpr int RLE_THREADS = 256;
-constexpr int RLE_ITEMS = 8;
 constexpr int RLE_WARPS = RLE_THREADS / 32;
-constexpr int RLE_TILE = RLE_THREADS * RLE_ITEMS;
 constexpr u64 RLE_HAS_HEAD = 1ull << 55;
 constexpr u64 RLE_VALUE_MASK = (1ull << 55) - 1;
 
-template <bool HAS_VALS>
-__global__ void __launch_bounds__(RLE_THREADS)
+// ITEMS rows of 32 keys per warp: 16 when counting (tile = 4096 keys = 32 KB; 4 CTAs/SM keep 128 KB of
+// reads in flight per SM, which is what hides the look-back round trips), 8 when summing a payload.
+template <bool HAS_VALS, int ITEMS, int MINB>
+__global__ void __launch_bounds__(RLE_THREADS, MINB)
 rle_kernel(const u64* __restrict__ keys, const u32* __restrict__ vals, int64_t n, int64_t n_tiles, u32 min_count,
-           u64* __restrict__ out_keys, u32* __restrict__ out_count, u64* status_tail, u64* status_keep,
+           int sym, u64* __restrict__ out_keys, u32* __restrict__ out_count, u64* status_tail, u64* status_keep,
            u32* ticket, u32 epoch, u64* __restrict__ totals) {
+    typedef typename std::conditional<HAS_VALS, u64, u32>::type sum_t;      // in-tile sums: counts fit 32 bits
+    constexpr int TILE = RLE_THREADS * ITEMS;
     __shared__ u64 s_wsum[RLE_WARPS];      // sum since the warp chunk's last head (whole chunk if none)
     __shared__ u32 s_whead[RLE_WARPS];     // chunk contains a head
     __shared__ u64 s_wcarry[RLE_WARPS];    // carry-in for runs that began before the chunk
@@ -65,36 +68,35 @@ rle_kernel(const u64* __restrict__ keys, const u32* __restrict__ vals, int64_t n
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
     __syncthreads();
     const int64_t tile = s_tile;
-    const int64_t cb = tile * RLE_TILE + (int64_t)warp * 32 * RLE_ITEMS;    // chunk base
-    const u32 le = lanemask_lt() | (1u << lane);
+    const int64_t cb = tile * TILE + (int64_t)warp * 32 * ITEMS;    // chunk base
+    const u32 lt = lanemask_lt();
+    const u32 le = lt | (1u << lane);
 
-    u64 key[RLE_ITEMS];
-    u32 val[RLE_ITEMS];
+    u64 key[ITEMS];
 #pragma unroll
-    for (int r = 0; r < RLE_ITEMS; ++r) {
+    for (int r = 0; r < ITEMS; ++r) {
         const int64_t idx = cb + r * 32 + lane;
         key[r] = (idx < n) ? __ldcs(keys + idx) : 0ull;
-        val[r] = HAS_VALS ? ((idx < n) ? __ldcs(vals + idx) : 0u) : 1u;
     }
     // neighbours across the chunk edges
     u64 edge_prev = 0, edge_next = 0;
     if (lane == 0 && cb > 0 && cb <= n) edge_prev = keys[cb - 1];
-    if (lane == 31 && cb + 32 * RLE_ITEMS < n) edge_next = keys[cb + 32 * RLE_ITEMS];
+    if (lane == 31 && cb + 32 * ITEMS < n) edge_next = keys[cb + 32 * ITEMS];
 
-    u64 s[RLE_ITEMS];                      // inclusive sum since the last head at or before this element
+    sum_t s[ITEMS];                        // inclusive sum since the last head at or before this element
     u32 end_bits = 0, open_bits = 0;       // bit r: element is a run end / its run began before the chunk
     u64 carry = 0;                         // sum since the last head, at the end of the previous row
     bool seen_head = false;
 #pragma unroll
-    for (int r = 0; r < RLE_ITEMS; ++r) {
+    for (int r = 0; r < ITEMS; ++r) {
         const int64_t idx = cb + r * 32 + lane;
         const bool valid = idx < n;
         u64 kprev = __shfl_up_sync(0xffffffffu, key[r], 1);
         u64 knext = __shfl_down_sync(0xffffffffu, key[r], 1);
         const u64 prow_last = __shfl_sync(0xffffffffu, key[r > 0 ? r - 1 : 0], 31);
-        const u64 nrow_first = __shfl_sync(0xffffffffu, key[r < RLE_ITEMS - 1 ? r + 1 : r], 0);
+        const u64 nrow_first = __shfl_sync(0xffffffffu, key[r < ITEMS - 1 ? r + 1 : r], 0);
         if (lane == 0) kprev = (r == 0) ? edge_prev : prow_last;
-        if (lane == 31) knext = (r == RLE_ITEMS - 1) ? edge_next : nrow_first;
+        if (lane == 31) knext = (r == ITEMS - 1) ? edge_next : nrow_first;
         const bool head = valid && (idx == 0 || key[r] != kprev);
         const bool end = valid && (idx == n - 1 || key[r] != knext);
         const u32 hm = __ballot_sync(0xffffffffu, head);
@@ -105,16 +107,17 @@ rle_kernel(const u64* __restrict__ keys, const u32* __restrict__ vals, int64_t n
         if (!HAS_VALS) {
             si = has ? (u64)(lane - pl + 1) : carry + (u64)(lane + 1);
         } else {
-            u64 inc = val[r];
+            const u32 v = valid ? __ldcs(vals + idx) : 0u;
+            u64 inc = v;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const u64 t = __shfl_up_sync(0xffffffffu, inc, o);
                 if (lane >= o) inc += t;
             }
-            const u64 before_head = __shfl_sync(0xffffffffu, inc - val[r], has ? pl : 0);
+            const u64 before_head = __shfl_sync(0xffffffffu, inc - v, has ? pl : 0);
             si = has ? inc - before_head : carry + inc;
         }
-        s[r] = si;
+        s[r] = (sum_t)si;
         if (end) end_bits |= 1u << r;
         if (!has && !seen_head) open_bits |= 1u << r;
         carry = __shfl_sync(0xffffffffu, si, 31);
@@ -132,17 +135,21 @@ rle_kernel(const u64* __restrict__ keys, const u32* __restrict__ vals, int64_t n
         }
         const u64 tag = (u64)epoch << 56;
         st_volatile_u64(status_tail + tile, SC_FLAG_AGG | tag | (hh ? RLE_HAS_HEAD : 0ull) | (tail & RLE_VALUE_MASK));
-        // carry-in of the tile: walk back to the nearest tile that contains a head (tile 0 always does)
+        // carry-in: only needed when the tile does not open with a head; walk back to the nearest tile
+        // that contains one (tile 0 always does)
         u64 c_in = 0;
-        for (int64_t t = tile - 1; t >= 0; --t) {
-            u64 x;
-            while (true) {
-                x = ld_volatile_u64(status_tail + t);
-                if ((u32)((x >> 56) & 0x3F) == epoch && (x >> 62) != 0) break;
-                __nanosleep(40);
+        const bool first_is_head = (tile == 0) || (keys[tile * TILE] != keys[tile * TILE - 1]);
+        if (!first_is_head) {
+            for (int64_t t = tile - 1; t >= 0; --t) {
+                u64 x;
+                while (true) {
+                    x = ld_volatile_u64(status_tail + t);
+                    if ((u32)((x >> 56) & 0x3F) == epoch && (x >> 62) != 0) break;
+                    __nanosleep(40);
+                }
+                c_in += x & RLE_VALUE_MASK;
+                if (x & RLE_HAS_HEAD) break;
             }
-            c_in += x & RLE_VALUE_MASK;
-            if (x & RLE_HAS_HEAD) break;
         }
         u64 cur = c_in;
         for (int w = 0; w < RLE_WARPS; ++w) {
@@ -152,19 +159,15 @@ rle_kernel(const u64* __restrict__ keys, const u32* __restrict__ vals, int64_t n
     }
     __syncthreads();
 
-    // totals at the run ends, threshold, positions
+    // totals at the run ends, threshold
     const u64 wc = s_wcarry[warp];
-    const u32 lt = lanemask_lt();
     u32 keep_bits = 0, wkeep = 0;
-    u32 pos[RLE_ITEMS];
 #pragma unroll
-    for (int r = 0; r < RLE_ITEMS; ++r) {
-        const u64 total = s[r] + (((open_bits >> r) & 1u) ? wc : 0ull);
-        s[r] = total;
+    for (int r = 0; r < ITEMS; ++r) {
+        u64 total = (u64)s[r] + (((open_bits >> r) & 1u) ? wc : 0ull);
+        if (sym && (u32)(key[r] >> 32) == (u32)key[r]) total *= 2;      // (a, a): both orders of each event pair
         const bool keep = ((end_bits >> r) & 1u) && total >= (u64)min_count;
-        const u32 km = __ballot_sync(0xffffffffu, keep);
-        pos[r] = wkeep + __popc(km & lt);
-        wkeep += __popc(km);
+        wkeep += __popc(__ballot_sync(0xffffffffu, keep));
         if (keep) keep_bits |= 1u << r;
     }
     if (lane == 0) s_wkeep[warp] = wkeep;
@@ -182,11 +185,17 @@ rle_kernel(const u64* __restrict__ keys, const u32* __restrict__ vals, int64_t n
     u64 ob = s_outbase;
     for (int w = 0; w < warp; ++w) ob += s_wkeep[w];
 #pragma unroll
-    for (int r = 0; r < RLE_ITEMS; ++r) {
-        if ((keep_bits >> r) & 1u) {
-            out_keys[ob + pos[r]] = key[r];
-            out_count[ob + pos[r]] = (u32)(s[r] > 0xFFFFFFFFull ? 0xFFFFFFFFull : s[r]);
+    for (int r = 0; r < ITEMS; ++r) {
+        const bool keep = (keep_bits >> r) & 1u;
+        const u32 km = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            u64 total = (u64)s[r] + (((open_bits >> r) & 1u) ? wc : 0ull);
+            if (sym && (u32)(key[r] >> 32) == (u32)key[r]) total *= 2;
+            const u64 o = ob + __popc(km & lt);
+            out_keys[o] = key[r];
+            out_count[o] = (u32)(total > 0xFFFFFFFFull ? 0xFFFFFFFFull : total);
         }
+        ob += __popc(km);
     }
 }
 
@@ -200,23 +209,29 @@ static T* shrink_to_fit(ottocov_ctx* ctx, DevBuf<T>& buf, int64_t used) {
     return small.take();
 }
 
-void reduce_sorted(ottocov_ctx* ctx, const u64* keys, const u32* vals, int64_t n, u32 min_count, u64** out_keys,
-                   u32** out_count, int64_t* n_out) {
+void reduce_sorted(ottocov_ctx* ctx, const u64* keys, const u32* vals, int64_t n, u32 min_count, bool sym,
+                   u64** out_keys, u32** out_count, int64_t* n_out) {
     *out_keys = nullptr; *out_count = nullptr; *n_out = 0;
     if (n <= 0) return;
-    const int64_t n_tiles = ceil_div64(n, RLE_TILE);
+    const int items = vals ? 8 : 16;
+    const int64_t n_tiles = ceil_div64(n, (int64_t)RLE_THREADS * items);
     DevBuf<u64> ukeys(ctx, n);             // upper bound: every key distinct (blocks come from the cache)
     DevBuf<u32> ucount(ctx, n);
     u32 epoch;
     scan_state_prepare(ctx, 2 * (size_t)n_tiles, &epoch);
     u64* st_tail = ctx->scan_status;
     u64* st_keep = ctx->scan_status + n_tiles;
+    static int minb = 0;
+    if (!minb) { const char* e = getenv("OTTOCOV_RLE_MINB"); minb = (e && atoi(e) == 3) ? 3 : 4; }
     if (vals)
-        COV_LAUNCH(ctx, OTTOCOV_K_RLE, 12.0 * n, rle_kernel<true>, (unsigned)n_tiles, RLE_THREADS, 0, keys, vals, n,
-                   n_tiles, min_count, ukeys.p, ucount.p, st_tail, st_keep, ctx->scan_ticket, epoch, ctx->scan_totals);
+        COV_LAUNCH(ctx, OTTOCOV_K_RLE, 12.0 * n, (rle_kernel<true, 8, 2>), (unsigned)n_tiles, RLE_THREADS, 0, keys, vals, n,
+                   n_tiles, min_count, sym ? 1 : 0, ukeys.p, ucount.p, st_tail, st_keep, ctx->scan_ticket, epoch, ctx->scan_totals);
+    else if (minb == 3)
+        COV_LAUNCH(ctx, OTTOCOV_K_RLE, 8.0 * n, (rle_kernel<false, 16, 3>), (unsigned)n_tiles, RLE_THREADS, 0, keys, vals, n,
+                   n_tiles, min_count, sym ? 1 : 0, ukeys.p, ucount.p, st_tail, st_keep, ctx->scan_ticket, epoch, ctx->scan_totals);
     else
-        COV_LAUNCH(ctx, OTTOCOV_K_RLE, 8.0 * n, rle_kernel<false>, (unsigned)n_tiles, RLE_THREADS, 0, keys, vals, n,
-                   n_tiles, min_count, ukeys.p, ucount.p, st_tail, st_keep, ctx->scan_ticket, epoch, ctx->scan_totals);
+        COV_LAUNCH(ctx, OTTOCOV_K_RLE, 8.0 * n, (rle_kernel<false, 16, 4>), (unsigned)n_tiles, RLE_THREADS, 0, keys, vals, n,
+                   n_tiles, min_count, sym ? 1 : 0, ukeys.p, ucount.p, st_tail, st_keep, ctx->scan_ticket, epoch, ctx->scan_totals);
     u64 rows = 0;
     CUDA_CHECK(cudaMemcpyAsync(&rows, ctx->scan_totals, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -288,7 +303,7 @@ static ottocov_table* sort_reduce_pairs(ottocov_ctx* ctx, DevBuf<u64>& keys, Dev
         u64* k = keys.p; u64* ka = kalt.p; u32* v = count.p; u32* va = valt.p;
         BitField fields[2] = {{0, aid_bits}, {32, 32 + aid_bits}};
         radix_sort_pairs(ctx, k, ka, v, va, n, fields, 2);
-        reduce_sorted(ctx, k, v, n, 1, &out->keys, &out->count, &out->n);
+        reduce_sorted(ctx, k, v, n, 1, false, &out->keys, &out->count, &out->n);
     } catch (...) {
         delete out;
         throw;
@@ -364,6 +379,51 @@ ottocov_table* table_from_packed_impl(ottocov_ctx* ctx, const u64* keys_in, cons
     table_stats(ctx, keys.p, nullptr, n, st);
     if ((st[0] >> 63) || ((st[0] >> 31) & 1)) COV_THROW(OTTOCOV_ERR_DATA, "packed key with a negative aid");
     return sort_reduce_pairs(ctx, keys, dc, n, aid_bits_from_or(st[0]));
+}
+
+// ---- mirror of a half table -------------------------------------------------------------------------------
+struct MirrorRows {
+    static constexpr int NC = 1;
+    const u64* keys;
+    const u32* count;
+    int64_t n;
+    u64* okeys;
+    u32* ocount;
+    __device__ u64 value(int64_t i) const { return ((u32)(keys[i] >> 32) != (u32)keys[i]) ? 1ull : 0ull; }
+    __device__ void apply(int64_t i, u64 v, const u64* pre) const {
+        const u64 k = keys[i];
+        const u32 c = count[i];
+        okeys[i] = k; ocount[i] = c;
+        if (v) { okeys[n + pre[0]] = (k << 32) | (k >> 32); ocount[n + pre[0]] = c; }
+    }
+};
+
+ottocov_table* mirror_table_impl(ottocov_ctx* ctx, const ottocov_table* half) {
+    ottocov_table* out = new ottocov_table();
+    out->aid_bits = half->aid_bits;
+    const int64_t n = half->n;
+    if (n == 0) return out;
+    try {
+        DevBuf<u64> keys(ctx, 2 * n), kalt;
+        DevBuf<u32> count(ctx, 2 * n), calt;
+        MirrorRows f;
+        f.keys = half->keys; f.count = half->count; f.n = n; f.okeys = keys.p; f.ocount = count.p;
+        u64 tot[1];
+        scan_apply(ctx, OTTOCOV_K_ORDER, f, n, tot, 36.0 * n);
+        const int64_t m = n + (int64_t)tot[0];
+        kalt.alloc(ctx, m); calt.alloc(ctx, m);
+        u64* k = keys.p; u64* ka = kalt.p; u32* v = count.p; u32* va = calt.p;
+        BitField fields[2] = {{0, half->aid_bits}, {32, 32 + half->aid_bits}};
+        radix_sort_pairs(ctx, k, ka, v, va, m, fields, 2);
+        // the sorted rows may sit in either half of the double buffer: hand that half to the table
+        if (k == keys.p) { out->keys = keys.take(); out->count = count.take(); }
+        else { out->keys = kalt.take(); out->count = calt.take(); }
+        out->n = m;
+    } catch (...) {
+        delete out;
+        throw;
+    }
+    return out;
 }
 
 // ---- threshold filter -------------------------------------------------------------------------------------

@@ -163,8 +163,18 @@ class Engine:
         self._check(self._lib.ottocov_memory_info(self._ctx, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
         return {"live_bytes": a.value, "cached_bytes": b.value, "peak_bytes": c.value}
 
-    def set_profiling(self, on: bool):
-        self._check(self._lib.ottocov_set_profiling(self._ctx, int(on)))
+    def set_profiling(self, on, families=None):
+        """on=True: CUDA-event timing of every kernel family; families=[...] restricts it (event
+        records between back-to-back launches cost a few microseconds of GPU idle each)."""
+        mask = int(bool(on))
+        if on and families:
+            names = [self._lib.ottocov_kernel_family_name(i).decode() for i in range(_lib.K_FAMILIES)]
+            mask = 0
+            for f in families:
+                mask |= 1 << names.index(f)
+            if mask == 1:                 # family 0 alone would read as "all": add a harmless second bit
+                mask |= 1 << names.index("misc")
+        self._check(self._lib.ottocov_set_profiling(self._ctx, mask))
 
     def kernel_stats(self, reset: bool = False) -> Dict[str, Dict[str, float]]:
         arr = (_lib.KernelStat * _lib.K_FAMILIES)()
@@ -202,7 +212,8 @@ class Engine:
     # ---- (2)+(3) expansion + reduce-by-key ------------------------------------------------------------
     def count(self, name: Optional[str] = None, *, type_this: Optional[int] = None,
               next_types: Optional[Sequence[int]] = None, window: Optional[int] = None,
-              pair_budget: Optional[int] = None, min_count: int = 1) -> Table:
+              pair_budget: Optional[int] = None, min_count: int = 1,
+              symmetric: Optional[bool] = None) -> Table:
         """One iteration of count_co_events' loop (count_co_events.py:64-72) on the loaded events.
         min_count > 1 fuses filter(count >= min_count) (count_co_events.py:172) into the reduce."""
         if name is not None:
@@ -214,7 +225,8 @@ class Engine:
         if window is not None:
             w = int(window)
         budget = self.config.PAIR_BUDGET if pair_budget is None else int(pair_budget)
-        spec = _lib.Spec(th, mask, w, budget, max(int(min_count), 0), 0)
+        flags = 0 if symmetric is None else (2 if symmetric else 1)
+        spec = _lib.Spec(th, mask, w, budget, max(int(min_count), 0), flags)
         h = ctypes.c_void_p()
         self._sync_stream()
         self._check(self._lib.ottocov_count(self._ctx, ctypes.byref(spec), ctypes.byref(h)))

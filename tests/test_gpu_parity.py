@@ -170,6 +170,27 @@ def test_fused_threshold_equals_filter(engine):
                 assert np.array_equal(x, z)
 
 
+@pytest.mark.parametrize("name", ["click_to_click", "cart_to_cart", "buy_to_buy"])
+def test_symmetric_shortcut_is_exact(engine, name):
+    s, a, t, y = small_events(31, n_sessions=700, n_aids=70, max_len=60)
+    engine.load_events(s, a, t, y)
+    oa, ob, oc, emitted, _ = c_oracle.count_name(s, a, t, y, name)
+    for kw in ({}, {"pair_budget": 2048}):
+        full = engine.count(name, symmetric=False, **kw)
+        half = engine.count(name, symmetric=True, **kw)          # canonical half pairs + mirror
+        assert engine.count_info()["n_pairs"] == emitted
+        for x, z, w in zip(half.fetch(), full.fetch(), (oa, ob, oc)):
+            assert np.array_equal(x, z) and np.array_equal(x.astype(w.dtype), w)
+        for thr in (2, 4, 9):                                     # diagonal rows count both orders
+            ka, kb, kc = c_oracle.merge_tables([(oa, ob, oc)], min_count=thr)
+            for sym in (True, False, None):
+                got = engine.count(name, min_count=thr, symmetric=sym, **kw).fetch()
+                assert np.array_equal(got[0], ka) and np.array_equal(got[1], kb) and np.array_equal(got[2], kc)
+    # an asymmetric kind ignores the request
+    cb = engine.count("click_to_cart_or_buy", symmetric=True)
+    assert cb.to_dict() == _dict(*c_oracle.count_name(s, a, t, y, "click_to_cart_or_buy")[:3])
+
+
 def test_long_runs_span_tiles(engine):
     # one pair repeated far beyond a reduce tile (2048 keys): carries must cross many tiles
     n = 30_000

@@ -178,7 +178,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from otto_recommender_b200 import Engine
-    from otto_recommender_b200.dist import reshard_table, shard_bounds
+    from otto_recommender_b200.dist import count_exchange_first, shard_bounds
     from otto_recommender_b200.synth import SynthSpec, generate
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -208,13 +208,9 @@ def run_ours(args):
 
     def step_device():
         eng.load_events(*cols)
-        if world > 1:                                     # thresholds apply to the global sums only
-            local = eng.count(NAME)
+        if world > 1:                                     # raw keys cross NVLink once, reduce where they land
+            f = count_exchange_first(eng, NAME, MIN_COUNT)
             ci = eng.count_info()
-            tab = reshard_table(eng, local)
-            local.free()
-            f = eng.filter(tab, MIN_COUNT)
-            tab.free()
         else:                                             # threshold fused into the run-length reduce
             f = eng.count(NAME, min_count=MIN_COUNT)
             ci = eng.count_info()
@@ -280,11 +276,7 @@ def run_ours(args):
     def step_e2e():
         eng.load_events(*host_cols)                       # H2D inside
         if world > 1:
-            local = eng.count(NAME)
-            tab = reshard_table(eng, local)
-            local.free()
-            f = eng.filter(tab, MIN_COUNT)
-            tab.free()
+            f = count_exchange_first(eng, NAME, MIN_COUNT)
         else:
             f = eng.count(NAME, min_count=MIN_COUNT)
         ax, nv, ay, ac = eng.topk(f, TOP_K, pinned=True)   # D2H inside

@@ -166,6 +166,25 @@ int ottocov_table_partition(ottocov_ctx* ctx, const ottocov_table* t, int n_rank
                             uint64_t* keys_out_dev, uint32_t* count_out_dev, int64_t* rows_per_dest);
 uint32_t ottocov_hash_dest(uint32_t aid, uint32_t n_ranks);
 
+/* Exchange-before-reduce path (used for N > 1): raw co-event keys are expanded, grouped by destination
+ * rank (dest = ottocov_hash_dest(aid of the key, n_ranks), stamped into key bits 56..63, one stable
+ * radix pass), exchanged by the caller (NCCL all-to-all on its own tensors) and reduced where they land.
+ *   ottocov_expand_prepare  window pass for `spec` on the loaded events: how many keys will be emitted,
+ *                           and whether they are canonical half pairs of a symmetric kind
+ *   ottocov_expand_run      emits them into caller-owned DEVICE buffers (each >= n_keys); the grouped
+ *                           keys end in buf_b when *result_in_b, else in buf_a; rows_per_dest is HOST
+ *   ottocov_reduce_pairs    sort + run-length count of received keys (keys_dev is used as scratch);
+ *                           symmetric = keys are half pairs (diagonal counts are doubled), strip_dest =
+ *                           clear key bits 56..63 first
+ *   ottocov_table_mirror    half table (rows a <= b) -> full symmetric table, or only the transposed
+ *                           off-diagonal rows (transpose_only), which belong to rank hash(b) */
+int ottocov_expand_prepare(ottocov_ctx* ctx, const ottocov_spec* spec, int64_t* n_keys, int* symmetric);
+int ottocov_expand_run(ottocov_ctx* ctx, int n_ranks, uint64_t* buf_a_dev, uint64_t* buf_b_dev,
+                       int* result_in_b, int64_t* rows_per_dest);
+int ottocov_reduce_pairs(ottocov_ctx* ctx, uint64_t* keys_dev, int64_t n, int aid_bits, uint32_t min_count,
+                         int symmetric, int strip_dest, ottocov_table** out);
+int ottocov_table_mirror(ottocov_ctx* ctx, const ottocov_table* t, int transpose_only, ottocov_table** out);
+
 /* ---- building blocks exposed for tests and micro-benchmarks ---------------------------------- */
 /* LSD radix sort of device-resident 64-bit keys on bits [lo_bit, hi_bit), optional 32-bit
  * payload (vals may be NULL).  Sorted data ends in keys/vals (in place from the caller's view). */

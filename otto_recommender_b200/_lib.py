@@ -56,6 +56,10 @@ SYMBOLS = {
     "ottocov_load_events": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int]),
     "ottocov_get_events_info": (c_int, [c_void_p, POINTER(EventsInfo)]),
     "ottocov_count": (c_int, [c_void_p, POINTER(Spec), POINTER(c_void_p)]),
+    "ottocov_expand_prepare": (c_int, [c_void_p, POINTER(Spec), POINTER(c_int64), POINTER(c_int)]),
+    "ottocov_expand_run": (c_int, [c_void_p, c_int, c_void_p, c_void_p, POINTER(c_int), POINTER(c_int64)]),
+    "ottocov_reduce_pairs": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_uint32, c_int, c_int, POINTER(c_void_p)]),
+    "ottocov_table_mirror": (c_int, [c_void_p, c_void_p, c_int, POINTER(c_void_p)]),
     "ottocov_get_count_info": (c_int, [c_void_p, POINTER(CountInfo)]),
     "ottocov_table_from_arrays": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, POINTER(c_void_p)]),
     "ottocov_table_from_packed": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, POINTER(c_void_p)]),

@@ -179,6 +179,7 @@ int ottocov_destroy(ottocov_ctx* ctx) {
     cudaSetDevice(ctx->device);
     free_events(ctx);
     free_topk(ctx);
+    free_plan(ctx);
     if (ctx->sweep_status) cudaFreeAsync(ctx->sweep_status, ctx->stream);
     for (auto& kv : ctx->live) cudaFreeAsync(kv.first, ctx->stream);    // tables the caller never freed
     ctx->live.clear();
@@ -263,6 +264,38 @@ int ottocov_count(ottocov_ctx* ctx, const ottocov_spec* spec, ottocov_table** ou
     if (!spec || !out) COV_THROW(OTTOCOV_ERR_ARG, "NULL argument");
     *out = nullptr;
     *out = count_impl(ctx, spec);
+    API_END(ctx)
+}
+
+int ottocov_expand_prepare(ottocov_ctx* ctx, const ottocov_spec* spec, int64_t* n_keys, int* symmetric) {
+    API_BEGIN(ctx)
+    if (!spec || !n_keys || !symmetric) COV_THROW(OTTOCOV_ERR_ARG, "NULL argument");
+    expand_prepare_impl(ctx, spec, n_keys, symmetric);
+    API_END(ctx)
+}
+
+int ottocov_expand_run(ottocov_ctx* ctx, int n_ranks, uint64_t* buf_a_dev, uint64_t* buf_b_dev, int* result_in_b,
+                       int64_t* rows_per_dest) {
+    API_BEGIN(ctx)
+    if (!result_in_b || !rows_per_dest) COV_THROW(OTTOCOV_ERR_ARG, "NULL argument");
+    expand_run_impl(ctx, n_ranks, (u64*)buf_a_dev, (u64*)buf_b_dev, result_in_b, rows_per_dest);
+    API_END(ctx)
+}
+
+int ottocov_reduce_pairs(ottocov_ctx* ctx, uint64_t* keys_dev, int64_t n, int aid_bits, uint32_t min_count,
+                         int symmetric, int strip_dest, ottocov_table** out) {
+    API_BEGIN(ctx)
+    if (!out || n < 0 || (n > 0 && !keys_dev)) COV_THROW(OTTOCOV_ERR_ARG, "bad argument");
+    *out = nullptr;
+    *out = reduce_pairs_impl(ctx, (u64*)keys_dev, n, aid_bits, min_count, symmetric, strip_dest);
+    API_END(ctx)
+}
+
+int ottocov_table_mirror(ottocov_ctx* ctx, const ottocov_table* t, int transpose_only, ottocov_table** out) {
+    API_BEGIN(ctx)
+    if (!t || !out) COV_THROW(OTTOCOV_ERR_ARG, "NULL argument");
+    *out = nullptr;
+    *out = mirror_table_impl(ctx, t, transpose_only != 0);
     API_END(ctx)
 }
 

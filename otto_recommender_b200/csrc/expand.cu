@@ -133,9 +133,12 @@ __global__ void __launch_bounds__(256) tile_search_kernel(const u64* __restrict_
 }
 
 template <bool CANON>
-__device__ __forceinline__ u64 make_pair_key(u32 a, u32 b) {
-    if (CANON) { const u32 lo = a < b ? a : b, hi = a < b ? b : a; return ((u64)lo << 32) | (u64)hi; }
-    return ((u64)a << 32) | (u64)b;
+__device__ __forceinline__ u64 make_pair_key(u32 a, u32 b, u32 n_dest) {
+    u32 x = a, y = b;
+    if (CANON) { x = a < b ? a : b; y = a < b ? b : a; }
+    u64 k = ((u64)x << 32) | (u64)y;
+    if (n_dest > 1) k |= (u64)hash_dest(x, n_dest) << 56;      // destination rank of the row (x, .)
+    return k;
 }
 
 template <bool SELF, bool CANON>
@@ -143,7 +146,7 @@ __global__ void __launch_bounds__(EX_THREADS)
 expand_kernel(const u32* __restrict__ rec_src, const u32* __restrict__ rec_lo,
               const u64* __restrict__ rec_off, const u32* __restrict__ tile_rec,
               const u32* __restrict__ aid_src, const u32* __restrict__ aid_tgt, u64 out_begin,
-              u64 out_end, u64* __restrict__ dst) {
+              u64 out_end, u64* __restrict__ dst, u32 n_dest) {
     __shared__ u32 s_off[EX_TILE + 1];
     __shared__ u32 s_lo[EX_TILE + 1];
     __shared__ u32 s_aid[EX_TILE + 1];
@@ -192,12 +195,12 @@ expand_kernel(const u32* __restrict__ rec_src, const u32* __restrict__ rec_lo,
         u32 j = lo;
         u32 tgt = s_lo[j] + (k - s_off[j]);
         if (SELF) tgt += (tgt >= s_src[j]);
-        const u64 key0 = make_pair_key<CANON>(s_aid[j], aid_tgt[tgt]);
+        const u64 key0 = make_pair_key<CANON>(s_aid[j], aid_tgt[tgt], n_dest);
         if (k + 1 < n_out) {
             if (j + 1 < n_rec && s_off[j + 1] <= k + 1) ++j;
             u32 tgt1 = s_lo[j] + (k + 1 - s_off[j]);
             if (SELF) tgt1 += (tgt1 >= s_src[j]);
-            const u64 key1 = make_pair_key<CANON>(s_aid[j], aid_tgt[tgt1]);
+            const u64 key1 = make_pair_key<CANON>(s_aid[j], aid_tgt[tgt1], n_dest);
             if (vec_ok) {
                 ulonglong2 v; v.x = key0; v.y = key1;
                 __stcs(reinterpret_cast<ulonglong2*>(tile_dst + k), v);
@@ -220,78 +223,143 @@ struct Segment {
     DevBuf<u64> rec_off;
 };
 
+// Everything the window pass learns about one co-event kind on the loaded events: which sources emit,
+// where their targets start, and the exact output offset of every source.  ottocov_count runs plan ->
+// expand -> sort -> reduce in one go; the multi-GPU path stops after expand to exchange the raw keys.
+struct ExpandPlan {
+    ottocov_spec spec;
+    int A = 0;
+    u32 W = 0;
+    bool sym = false;
+    u32 user_min = 1;
+    int aid_bits = 1;
+    u64 P = 0;                       // keys to emit (half pairs when sym)
+    std::vector<Segment*> segs;
+    ~ExpandPlan() { for (auto* s : segs) delete s; }
+};
+
+void free_plan(ottocov_ctx* ctx) {
+    delete static_cast<ExpandPlan*>(ctx->plan);
+    ctx->plan = nullptr;
+}
+
 static ottocov_table* make_empty_table(int aid_bits) {
     ottocov_table* t = new ottocov_table();
     t->aid_bits = aid_bits;
     return t;
 }
 
-ottocov_table* count_impl(ottocov_ctx* ctx, const ottocov_spec* spec) {
-    if (!ctx->loaded) COV_THROW(OTTOCOV_ERR_STATE, "ottocov_count before ottocov_load_events");
+static ExpandPlan* make_plan(ottocov_ctx* ctx, const ottocov_spec* spec, bool distributed) {
+    if (!ctx->loaded) COV_THROW(OTTOCOV_ERR_STATE, "co-event counting before ottocov_load_events");
     if (spec->type_this < 0 || spec->type_this > 2) COV_THROW(OTTOCOV_ERR_ARG, "type_this must be 0..2");
     if (spec->next_mask == 0 || spec->next_mask > 7) COV_THROW(OTTOCOV_ERR_ARG, "next_mask must be 1..7");
     if (spec->window < 0) COV_THROW(OTTOCOV_ERR_ARG, "window must be >= 0");
-    const int A = spec->type_this;
-    const u32 W = (u32)(spec->window > 86400 ? 86400 : spec->window);   // count_co_events.py:33-36
-    const TypeArray& src = ctx->ta[A];
-    const int aid_bits = ctx->info.aid_bits > 0 ? ctx->info.aid_bits : 1;
+    ExpandPlan* pl = new ExpandPlan();
+    try {
+        pl->spec = *spec;
+        pl->A = spec->type_this;
+        pl->W = (u32)(spec->window > 86400 ? 86400 : spec->window);   // count_co_events.py:33-36
+        pl->aid_bits = ctx->info.aid_bits > 0 ? ctx->info.aid_bits : 1;
+        pl->user_min = spec->min_count > 1 ? spec->min_count : 1;
+        // symmetric shortcut: one canonical key per unordered event pair, mirrored after the reduce.  It
+        // pays when few rows are left to mirror (a threshold) or when the keys are about to cross NVLink
+        // anyway; OTTOCOV_SYM_OFF / OTTOCOV_SYM_ON force the choice.
+        const bool sym_kind = spec->next_mask == (1u << pl->A);
+        pl->sym = sym_kind && !(spec->flags & OTTOCOV_SYM_OFF) &&
+                  ((spec->flags & OTTOCOV_SYM_ON) || pl->user_min > 1 || distributed);
+        const TypeArray& src = ctx->ta[pl->A];
+        for (int B = 0; B < 3; ++B) {
+            if (!((spec->next_mask >> B) & 1)) continue;
+            const TypeArray& tgt = ctx->ta[B];
+            if (src.n == 0 || tgt.n == 0) continue;
+            Segment* sg = new Segment();
+            pl->segs.push_back(sg);
+            sg->tgt_type = B;
+            sg->self = (pl->A == B);
+            const u32* xr = nullptr;
+            if (!sg->self) xr = (B == (pl->A + 1) % 3) ? src.xrank[0] : src.xrank[1];
+            DevBuf<u32> lo(ctx, src.n), cnt(ctx, src.n);
+            if (pl->sym)
+                COV_LAUNCH(ctx, OTTOCOV_K_WINDOW, 16.0 * src.n, window_fwd_kernel, (unsigned)ceil_div64(src.n, 256), 256, 0,
+                           src.skey, src.n, pl->W, lo.p, cnt.p);
+            else
+                COV_LAUNCH(ctx, OTTOCOV_K_WINDOW, 20.0 * src.n, window_kernel, (unsigned)ceil_div64(src.n, 256), 256, 0,
+                           src.skey, xr, src.n, tgt.skey, (u32)tgt.n, pl->W, lo.p, cnt.p);
+            sg->rec_src.alloc(ctx, src.n); sg->rec_lo.alloc(ctx, src.n); sg->rec_off.alloc(ctx, src.n);
+            WindowRecords f;
+            f.lo = lo.p; f.cnt = cnt.p;
+            f.rec_src = sg->rec_src.p; f.rec_lo = sg->rec_lo.p; f.rec_off = sg->rec_off.p;
+            u64 tot[2];
+            scan_apply(ctx, OTTOCOV_K_WINDOW, f, src.n, tot, 2.0 * 4.0 * src.n + 8.0 * src.n + 16.0 * src.n);
+            sg->n_pairs = tot[0];
+            sg->n_rec = tot[1];
+            pl->P += tot[0];
+        }
+    } catch (...) {
+        delete pl;
+        throw;
+    }
+    return pl;
+}
+
+// keys of plan outputs [c0, c1) -> dst[0 .. c1-c0).  n_dest > 1 also stamps hash(aid of the key) % n_dest
+// into key bits [56, 64) so one radix pass on those bits groups the keys by destination rank.
+static void expand_range(ottocov_ctx* ctx, const ExpandPlan* pl, u64 c0, u64 c1, u64* dst_base, u32 n_dest) {
+    const TypeArray& src = ctx->ta[pl->A];
+    u64 seg_start = 0;
+    for (Segment* sg : pl->segs) {
+        const u64 seg_end = seg_start + sg->n_pairs;
+        const u64 a = c0 > seg_start ? c0 : seg_start;
+        const u64 b = c1 < seg_end ? c1 : seg_end;
+        if (a < b) {
+            const u64 ob = a - seg_start, oe = b - seg_start;       // segment-local output range
+            const int64_t n_tiles = ceil_div64((int64_t)(oe - ob), EX_TILE);
+            DevBuf<u32> tile_rec(ctx, n_tiles + 1);
+            COV_LAUNCH(ctx, OTTOCOV_K_EXPAND, 0, tile_search_kernel, (unsigned)ceil_div64(n_tiles + 1, 256), 256, 0,
+                       sg->rec_off.p, (int64_t)sg->n_rec, ob, oe, n_tiles, tile_rec.p);
+            const TypeArray& tgt = ctx->ta[sg->tgt_type];
+            u64* dst = dst_base + (a - c0);
+            const double bytes = 8.0 * (double)(oe - ob);
+            if (pl->sym)
+                COV_LAUNCH(ctx, OTTOCOV_K_EXPAND, bytes, (expand_kernel<false, true>), (unsigned)n_tiles, EX_THREADS, 0,
+                           sg->rec_src.p, sg->rec_lo.p, sg->rec_off.p, tile_rec.p, src.aid, tgt.aid, ob, oe, dst, n_dest);
+            else if (sg->self)
+                COV_LAUNCH(ctx, OTTOCOV_K_EXPAND, bytes, (expand_kernel<true, false>), (unsigned)n_tiles, EX_THREADS, 0,
+                           sg->rec_src.p, sg->rec_lo.p, sg->rec_off.p, tile_rec.p, src.aid, tgt.aid, ob, oe, dst, n_dest);
+            else
+                COV_LAUNCH(ctx, OTTOCOV_K_EXPAND, bytes, (expand_kernel<false, false>), (unsigned)n_tiles, EX_THREADS, 0,
+                           sg->rec_src.p, sg->rec_lo.p, sg->rec_off.p, tile_rec.p, src.aid, tgt.aid, ob, oe, dst, n_dest);
+        }
+        seg_start = seg_end;
+    }
+}
+
+static u64 auto_budget(ottocov_ctx* ctx) {
+    size_t free_b = 0, total_b = 0;
+    CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+    // blocks parked in our cache count as free; 16 B per pair for the double buffer plus <= 12 B per
+    // pair for the reduced table
+    u64 budget = (u64)((double)(free_b + ctx->cached_bytes) * 0.6 / 28.0);
+    return budget < (1u << 20) ? (1u << 20) : budget;
+}
+
+ottocov_table* count_impl(ottocov_ctx* ctx, const ottocov_spec* spec) {
     ottocov_count_info& ci = ctx->last_count;
     memset(&ci, 0, sizeof(ci));
-
-    // symmetric shortcut: one canonical key per unordered event pair, mirrored after the reduce.  Pays
-    // when the threshold leaves few rows to mirror; OTTOCOV_SYM_OFF / OTTOCOV_SYM_ON force the choice.
-    const u32 user_min = spec->min_count > 1 ? spec->min_count : 1;
-    const bool sym_kind = spec->next_mask == (1u << A);
-    const bool sym = sym_kind && !(spec->flags & 1u) && ((spec->flags & 2u) || user_min > 1);
-
-    // ---- window + records per target type ---------------------------------------------------------
-    std::vector<Segment*> segs;
-    struct SegGuard { std::vector<Segment*>& v; ~SegGuard() { for (auto* s : v) delete s; } } guard{segs};
-    u64 P = 0;
-    for (int B = 0; B < 3; ++B) {
-        if (!((spec->next_mask >> B) & 1)) continue;
-        const TypeArray& tgt = ctx->ta[B];
-        if (src.n == 0 || tgt.n == 0) continue;
-        Segment* sg = new Segment();
-        segs.push_back(sg);
-        sg->tgt_type = B;
-        sg->self = (A == B);
-        const u32* xr = nullptr;
-        if (!sg->self) xr = (B == (A + 1) % 3) ? src.xrank[0] : src.xrank[1];
-        DevBuf<u32> lo(ctx, src.n), cnt(ctx, src.n);
-        if (sym)
-            COV_LAUNCH(ctx, OTTOCOV_K_WINDOW, 16.0 * src.n, window_fwd_kernel, (unsigned)ceil_div64(src.n, 256), 256, 0,
-                       src.skey, src.n, W, lo.p, cnt.p);
-        else
-            COV_LAUNCH(ctx, OTTOCOV_K_WINDOW, 20.0 * src.n, window_kernel, (unsigned)ceil_div64(src.n, 256), 256, 0,
-                       src.skey, xr, src.n, tgt.skey, (u32)tgt.n, W, lo.p, cnt.p);
-        sg->rec_src.alloc(ctx, src.n); sg->rec_lo.alloc(ctx, src.n); sg->rec_off.alloc(ctx, src.n);
-        WindowRecords f;
-        f.lo = lo.p; f.cnt = cnt.p;
-        f.rec_src = sg->rec_src.p; f.rec_lo = sg->rec_lo.p; f.rec_off = sg->rec_off.p;
-        u64 tot[2];
-        scan_apply(ctx, OTTOCOV_K_WINDOW, f, src.n, tot, 2.0 * 4.0 * src.n + 8.0 * src.n + 16.0 * src.n);
-        sg->n_pairs = tot[0];
-        sg->n_rec = tot[1];
-        P += tot[0];
-    }
+    ExpandPlan* pl = make_plan(ctx, spec, false);
+    struct PlanGuard { ExpandPlan* p; ~PlanGuard() { delete p; } } plan_guard{pl};
+    const u64 P = pl->P;
+    const bool sym = pl->sym;
+    const int aid_bits = pl->aid_bits;
     ci.n_pairs = (int64_t)(sym ? 2 * P : P);       // ordered co-event pairs, as the reference counts them
     if (P == 0) { ci.n_chunks = 0; return make_empty_table(aid_bits); }
 
     // ---- chunking by pair budget ----------------------------------------------------------------------
-    u64 budget = spec->pair_budget > 0 ? (u64)spec->pair_budget : 0;
-    if (budget == 0) {
-        size_t free_b = 0, total_b = 0;
-        CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
-        // pool memory we already hold counts as free for our purposes; be conservative: 16 B per
-        // pair for the double buffer plus <= 12 B per pair for the reduced table
-        budget = (u64)((double)(free_b + ctx->cached_bytes) * 0.6 / 28.0);
-        if (budget < (1u << 20)) budget = 1u << 20;
-    }
+    u64 budget = spec->pair_budget > 0 ? (u64)spec->pair_budget : auto_budget(ctx);
     budget = (budget / EX_TILE) * EX_TILE;
     if (budget == 0) budget = EX_TILE;
 
-    const u32 fused_min = (P <= budget) ? user_min : 1;     // thresholds apply to complete sums only
+    const u32 fused_min = (P <= budget) ? pl->user_min : 1;     // thresholds apply to complete sums only
     std::vector<ottocov_table*> partials;
     struct PartGuard {
         ottocov_ctx* c; std::vector<ottocov_table*>& v;
@@ -303,32 +371,7 @@ ottocov_table* count_impl(ottocov_ctx* ctx, const ottocov_spec* spec) {
         const u64 c1 = (c0 + budget < P) ? c0 + budget : P;
         const u64 cn = c1 - c0;
         DevBuf<u64> keys(ctx, cn), alt(ctx, cn);
-        u64 seg_start = 0;
-        for (Segment* sg : segs) {
-            const u64 seg_end = seg_start + sg->n_pairs;
-            const u64 a = c0 > seg_start ? c0 : seg_start;
-            const u64 b = c1 < seg_end ? c1 : seg_end;
-            if (a < b) {
-                const u64 ob = a - seg_start, oe = b - seg_start;       // segment-local output range
-                const int64_t n_tiles = ceil_div64((int64_t)(oe - ob), EX_TILE);
-                DevBuf<u32> tile_rec(ctx, n_tiles + 1);
-                COV_LAUNCH(ctx, OTTOCOV_K_EXPAND, 0, tile_search_kernel, (unsigned)ceil_div64(n_tiles + 1, 256), 256, 0,
-                           sg->rec_off.p, (int64_t)sg->n_rec, ob, oe, n_tiles, tile_rec.p);
-                const TypeArray& tgt = ctx->ta[sg->tgt_type];
-                u64* dst = keys.p + (a - c0);
-                const double bytes = 8.0 * (double)(oe - ob);
-                if (sym)
-                    COV_LAUNCH(ctx, OTTOCOV_K_EXPAND, bytes, (expand_kernel<false, true>), (unsigned)n_tiles, EX_THREADS, 0,
-                               sg->rec_src.p, sg->rec_lo.p, sg->rec_off.p, tile_rec.p, src.aid, tgt.aid, ob, oe, dst);
-                else if (sg->self)
-                    COV_LAUNCH(ctx, OTTOCOV_K_EXPAND, bytes, (expand_kernel<true, false>), (unsigned)n_tiles, EX_THREADS, 0,
-                               sg->rec_src.p, sg->rec_lo.p, sg->rec_off.p, tile_rec.p, src.aid, tgt.aid, ob, oe, dst);
-                else
-                    COV_LAUNCH(ctx, OTTOCOV_K_EXPAND, bytes, (expand_kernel<false, false>), (unsigned)n_tiles, EX_THREADS, 0,
-                               sg->rec_src.p, sg->rec_lo.p, sg->rec_off.p, tile_rec.p, src.aid, tgt.aid, ob, oe, dst);
-            }
-            seg_start = seg_end;
-        }
+        expand_range(ctx, pl, c0, c1, keys.p, 0);
         u64* k = keys.p; u64* ka = alt.p; u32* v = nullptr; u32* va = nullptr;
         ci.sort_passes = radix_sort_pairs(ctx, k, ka, v, va, (int64_t)cn, fields, 2);
         ottocov_table* part = new ottocov_table();
@@ -344,17 +387,96 @@ ottocov_table* count_impl(ottocov_ctx* ctx, const ottocov_spec* spec) {
         partials.clear();
     } else {
         result = merge_tables_impl(ctx, partials.data(), (int)partials.size());
-        if (user_min > 1) {
-            ottocov_table* f = filter_table_impl(ctx, result, user_min);
+        if (pl->user_min > 1) {
+            ottocov_table* f = filter_table_impl(ctx, result, pl->user_min);
             dev_free(ctx, result->keys); dev_free(ctx, result->count); delete result;
             result = f;
         }
     }
     if (sym) {                                      // (a, b, c) -> also (b, a, c)
-        ottocov_table* full = mirror_table_impl(ctx, result);
+        ottocov_table* full = mirror_table_impl(ctx, result, false);
         dev_free(ctx, result->keys); dev_free(ctx, result->count); delete result;
         result = full;
     }
     ci.n_unique = result->n;
     return result;
+}
+
+// ---- multi-GPU building blocks: expand raw keys grouped by destination rank; reduce received keys --------
+void expand_prepare_impl(ottocov_ctx* ctx, const ottocov_spec* spec, int64_t* n_keys, int* symmetric) {
+    free_plan(ctx);
+    ExpandPlan* pl = make_plan(ctx, spec, true);
+    ctx->plan = pl;
+    memset(&ctx->last_count, 0, sizeof(ctx->last_count));
+    ctx->last_count.n_pairs = (int64_t)(pl->sym ? 2 * pl->P : pl->P);
+    *n_keys = (int64_t)pl->P;
+    *symmetric = pl->sym ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256) dest_count_kernel(const u64* __restrict__ keys, int64_t n, u32 n_dest,
+                                                         unsigned long long* __restrict__ counts) {
+    __shared__ unsigned int s_c[256];
+    s_c[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        atomicAdd(&s_c[(u32)(keys[i] >> 56)], 1u);
+    __syncthreads();
+    if (threadIdx.x < n_dest && s_c[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)s_c[threadIdx.x]);
+}
+
+void expand_run_impl(ottocov_ctx* ctx, int n_ranks, u64* buf_a, u64* buf_b, int* result_in_b, int64_t* rows_per_dest) {
+    ExpandPlan* pl = static_cast<ExpandPlan*>(ctx->plan);
+    if (!pl) COV_THROW(OTTOCOV_ERR_STATE, "ottocov_expand_run before ottocov_expand_prepare");
+    if (n_ranks < 1 || n_ranks > 256) COV_THROW(OTTOCOV_ERR_ARG, "n_ranks must be 1..256");
+    if (n_ranks > 1 && pl->aid_bits > 24) COV_THROW(OTTOCOV_ERR_ARG, "distributed expand needs aid < 2^24 (key bits 56..63 carry the destination)");
+    struct PlanFree { ottocov_ctx* c; ~PlanFree() { free_plan(c); } } pf{ctx};
+    *result_in_b = 0;
+    for (int r = 0; r < n_ranks; ++r) rows_per_dest[r] = 0;
+    const int64_t n = (int64_t)pl->P;
+    if (n == 0) return;
+    expand_range(ctx, pl, 0, pl->P, buf_a, n_ranks > 1 ? (u32)n_ranks : 0u);
+    if (n_ranks == 1) { rows_per_dest[0] = n; return; }
+    // rows per destination, then ONE stable radix pass on the destination bits
+    DevBuf<unsigned long long> cnt(ctx, 256);
+    CUDA_CHECK(cudaMemsetAsync(cnt.p, 0, 256 * sizeof(unsigned long long), ctx->stream));
+    COV_LAUNCH(ctx, OTTOCOV_K_PARTITION, 8.0 * n, dest_count_kernel, (int)imin64(ceil_div64(n, 2048), (int64_t)ctx->num_sms * 8),
+               256, 0, buf_a, n, (u32)n_ranks, cnt.p);
+    unsigned long long h[256];
+    CUDA_CHECK(cudaMemcpyAsync(h, cnt.p, 256 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    int bits = 1;
+    while ((1 << bits) < n_ranks) ++bits;
+    BitField f[1] = {{56, 56 + bits}};
+    u64* k = buf_a; u64* ka = buf_b; u32* v = nullptr; u32* va = nullptr;
+    radix_sort_pairs(ctx, k, ka, v, va, n, f, 1);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    for (int r = 0; r < n_ranks; ++r) rows_per_dest[r] = (int64_t)h[r];
+    *result_in_b = (k == buf_b) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256) strip_dest_kernel(u64* __restrict__ keys, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] &= 0x00FFFFFFFFFFFFFFull;
+}
+
+ottocov_table* reduce_pairs_impl(ottocov_ctx* ctx, u64* keys, int64_t n, int aid_bits, u32 min_count, int sym,
+                                 int strip_dest) {
+    if (aid_bits < 1 || aid_bits > 32) COV_THROW(OTTOCOV_ERR_ARG, "aid_bits must be 1..32");
+    ottocov_table* out = make_empty_table(aid_bits);
+    if (n == 0) return out;
+    try {
+        if (strip_dest)
+            COV_LAUNCH(ctx, OTTOCOV_K_PARTITION, 16.0 * n, strip_dest_kernel, (unsigned)ceil_div64(n, 256), 256, 0, keys, n);
+        DevBuf<u64> alt(ctx, n);
+        BitField fields[2] = {{0, aid_bits}, {32, 32 + aid_bits}};
+        u64* k = keys; u64* ka = alt.p; u32* v = nullptr; u32* va = nullptr;
+        ctx->last_count.sort_passes = radix_sort_pairs(ctx, k, ka, v, va, n, fields, 2);
+        reduce_sorted(ctx, k, nullptr, n, min_count > 1 ? min_count : 1, sym != 0, &out->keys, &out->count, &out->n);
+        ctx->last_count.n_chunks = 1;
+        ctx->last_count.n_unique = out->n;
+    } catch (...) {
+        delete out;
+        throw;
+    }
+    return out;
 }

@@ -87,6 +87,7 @@ struct ottocov_ctx {
     u32 scan_epoch = 0;
     u32* scan_ticket = nullptr;
     u64* scan_totals = nullptr;        // [8] grand totals of the last scan launch
+    void* plan = nullptr;              // ExpandPlan between ottocov_expand_prepare and ottocov_expand_run
     // top-k result
     int topk_k = 0;
     int64_t topk_n = 0;
@@ -154,6 +155,11 @@ void free_events(ottocov_ctx* ctx);
 
 // expand.cu
 ottocov_table* count_impl(ottocov_ctx* ctx, const ottocov_spec* spec);
+void free_plan(ottocov_ctx* ctx);
+void expand_prepare_impl(ottocov_ctx* ctx, const ottocov_spec* spec, int64_t* n_keys, int* symmetric);
+void expand_run_impl(ottocov_ctx* ctx, int n_ranks, u64* buf_a, u64* buf_b, int* result_in_b, int64_t* rows_per_dest);
+ottocov_table* reduce_pairs_impl(ottocov_ctx* ctx, u64* keys, int64_t n, int aid_bits, u32 min_count, int sym,
+                                 int strip_dest);
 
 // reduce.cu
 // sorted keys -> distinct keys + run lengths (vals == nullptr) or summed payload (vals != nullptr),
@@ -163,7 +169,8 @@ ottocov_table* count_impl(ottocov_ctx* ctx, const ottocov_spec* spec);
 void reduce_sorted(ottocov_ctx* ctx, const u64* keys, const u32* vals, int64_t n, u32 min_count, bool sym,
                    u64** out_keys, u32** out_count, int64_t* n_out);
 // half table (rows a <= b) -> full symmetric table
-ottocov_table* mirror_table_impl(ottocov_ctx* ctx, const ottocov_table* half);
+// transpose_only: return just the mirrored rows (b, a, c) of the off-diagonal rows, sorted
+ottocov_table* mirror_table_impl(ottocov_ctx* ctx, const ottocov_table* half, bool transpose_only);
 ottocov_table* merge_tables_impl(ottocov_ctx* ctx, ottocov_table* const* tabs, int n_tabs);
 ottocov_table* filter_table_impl(ottocov_ctx* ctx, const ottocov_table* t, u32 min_count);
 void fetch_table_impl(ottocov_ctx* ctx, const ottocov_table* t, int order, int64_t head,

@@ -386,19 +386,19 @@ struct MirrorRows {
     static constexpr int NC = 1;
     const u64* keys;
     const u32* count;
-    int64_t n;
+    int64_t n;          // rows copied through unchanged in front of the mirrored ones (0: transpose only)
     u64* okeys;
     u32* ocount;
     __device__ u64 value(int64_t i) const { return ((u32)(keys[i] >> 32) != (u32)keys[i]) ? 1ull : 0ull; }
     __device__ void apply(int64_t i, u64 v, const u64* pre) const {
         const u64 k = keys[i];
         const u32 c = count[i];
-        okeys[i] = k; ocount[i] = c;
+        if (n) { okeys[i] = k; ocount[i] = c; }
         if (v) { okeys[n + pre[0]] = (k << 32) | (k >> 32); ocount[n + pre[0]] = c; }
     }
 };
 
-ottocov_table* mirror_table_impl(ottocov_ctx* ctx, const ottocov_table* half) {
+ottocov_table* mirror_table_impl(ottocov_ctx* ctx, const ottocov_table* half, bool transpose_only) {
     ottocov_table* out = new ottocov_table();
     out->aid_bits = half->aid_bits;
     const int64_t n = half->n;
@@ -407,10 +407,11 @@ ottocov_table* mirror_table_impl(ottocov_ctx* ctx, const ottocov_table* half) {
         DevBuf<u64> keys(ctx, 2 * n), kalt;
         DevBuf<u32> count(ctx, 2 * n), calt;
         MirrorRows f;
-        f.keys = half->keys; f.count = half->count; f.n = n; f.okeys = keys.p; f.ocount = count.p;
+        f.keys = half->keys; f.count = half->count; f.n = transpose_only ? 0 : n; f.okeys = keys.p; f.ocount = count.p;
         u64 tot[1];
         scan_apply(ctx, OTTOCOV_K_ORDER, f, n, tot, 36.0 * n);
-        const int64_t m = n + (int64_t)tot[0];
+        const int64_t m = f.n + (int64_t)tot[0];
+        if (m == 0) return out;
         kalt.alloc(ctx, m); calt.alloc(ctx, m);
         u64* k = keys.p; u64* ka = kalt.p; u32* v = count.p; u32* va = calt.p;
         BitField fields[2] = {{0, half->aid_bits}, {32, 32 + half->aid_bits}};

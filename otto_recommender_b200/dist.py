@@ -95,6 +95,51 @@ def count_distributed(engine, name: str, group=None, free_local: bool = True):
     return shard
 
 
+def exchange_keys(send_keys: torch.Tensor, rows_per_dest: Sequence[int], group=None) -> torch.Tensor:
+    """All-to-all of raw 8-byte co-event keys already grouped by destination rank."""
+    world = dist.get_world_size(group)
+    dev = send_keys.device
+    send_sizes = torch.tensor(list(rows_per_dest), dtype=torch.int64, device=dev)
+    recv_sizes = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_to_all_single(recv_sizes, send_sizes, group=group)
+    recv_list = [int(x) for x in recv_sizes.tolist()]
+    recv = torch.empty(sum(recv_list), dtype=send_keys.dtype, device=dev)
+    dist.all_to_all_single(recv, send_keys, recv_list, [int(x) for x in rows_per_dest], group=group)
+    return recv
+
+
+def count_exchange_first(engine, name: str, min_count: int = 1, group=None):
+    """Exchange-before-reduce: the raw keys of this rank's sessions cross NVLink once (8 B per pair, half
+    of them for symmetric kinds), then every rank sorts and reduces only the pairs it owns -- per-rank
+    work is P / R, and the count threshold can be fused into the reduce because sums are complete.
+
+    Returns this rank's shard of the global (thresholded) table: all rows whose aid hashes to it."""
+    world = dist.get_world_size(group)
+    dev = torch.device("cuda", engine.device)
+    n_keys, sym = engine.expand_prepare(name, min_count=min_count)
+    buf_a = torch.empty(max(n_keys, 1), dtype=torch.int64, device=dev)
+    buf_b = torch.empty(max(n_keys, 1), dtype=torch.int64, device=dev)
+    grouped, rows = engine.expand_run(world, buf_a, buf_b)
+    recv = exchange_keys(grouped[:n_keys], rows, group) if world > 1 else grouped[:n_keys]
+    del buf_a, buf_b, grouped
+    bits = torch.tensor([engine.events_info()["aid_bits"]], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(bits, op=dist.ReduceOp.MAX, group=group)
+    half = engine.reduce_pairs(recv, recv.numel(), int(bits.item()), min_count, symmetric=sym, strip_dest=world > 1)
+    if not sym:
+        return half
+    if world == 1:
+        full = engine.mirror(half)
+        half.free()
+        return full
+    mirrored = engine.mirror(half, transpose_only=True)       # rows (b, a, c) live on rank hash(b)
+    theirs = reshard_table(engine, mirrored, group)
+    full = engine.merge([half, theirs])
+    for t in (half, mirrored, theirs):
+        t.free()
+    return full
+
+
 def gather_table(table, group=None, dst: int = 0):
     """Collect every rank's shard on `dst` as numpy (aid, aid_next, count); None elsewhere."""
     a, b, c = table.fetch(order="key")

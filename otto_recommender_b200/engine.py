@@ -216,6 +216,13 @@ class Engine:
               symmetric: Optional[bool] = None) -> Table:
         """One iteration of count_co_events' loop (count_co_events.py:64-72) on the loaded events.
         min_count > 1 fuses filter(count >= min_count) (count_co_events.py:172) into the reduce."""
+        spec = self._spec(name, type_this, next_types, window, pair_budget, min_count, symmetric)
+        h = ctypes.c_void_p()
+        self._sync_stream()
+        self._check(self._lib.ottocov_count(self._ctx, ctypes.byref(spec), ctypes.byref(h)))
+        return Table(self, h.value)
+
+    def _spec(self, name, type_this, next_types, window, pair_budget, min_count, symmetric):
         if name is not None:
             th, mask, w = self.config.spec(name)
         else:
@@ -226,10 +233,43 @@ class Engine:
             w = int(window)
         budget = self.config.PAIR_BUDGET if pair_budget is None else int(pair_budget)
         flags = 0 if symmetric is None else (2 if symmetric else 1)
-        spec = _lib.Spec(th, mask, w, budget, max(int(min_count), 0), flags)
+        return _lib.Spec(th, mask, w, budget, max(int(min_count), 0), flags)
+
+    # ---- exchange-before-reduce building blocks (multi-GPU) ---------------------------------------------
+    def expand_prepare(self, name: Optional[str] = None, *, type_this=None, next_types=None, window=None,
+                       min_count: int = 1, symmetric: Optional[bool] = None) -> Tuple[int, bool]:
+        """Window pass only: -> (number of keys expand_run will emit, keys are symmetric half pairs)."""
+        spec = self._spec(name, type_this, next_types, window, None, min_count, symmetric)
+        n, sym = ctypes.c_int64(), ctypes.c_int()
+        self._sync_stream()
+        self._check(self._lib.ottocov_expand_prepare(self._ctx, ctypes.byref(spec), ctypes.byref(n), ctypes.byref(sym)))
+        return int(n.value), bool(sym.value)
+
+    def expand_run(self, n_ranks: int, buf_a, buf_b):
+        """Emit the prepared keys grouped by destination rank into caller tensors (int64, CUDA).
+        -> (tensor holding the grouped keys, rows_per_dest)."""
+        rows = (ctypes.c_int64 * n_ranks)()
+        in_b = ctypes.c_int()
+        self._sync_stream()
+        self._check(self._lib.ottocov_expand_run(self._ctx, n_ranks, buf_a.data_ptr(), buf_b.data_ptr(),
+                                                 ctypes.byref(in_b), rows))
+        return (buf_b if in_b.value else buf_a), [int(x) for x in rows]
+
+    def reduce_pairs(self, keys, n: int, aid_bits: int, min_count: int = 1, symmetric: bool = False,
+                     strip_dest: bool = False) -> Table:
+        """Sort + run-length count of raw keys (an int64 CUDA tensor, used as scratch)."""
         h = ctypes.c_void_p()
         self._sync_stream()
-        self._check(self._lib.ottocov_count(self._ctx, ctypes.byref(spec), ctypes.byref(h)))
+        self._check(self._lib.ottocov_reduce_pairs(self._ctx, keys.data_ptr() if n else None, int(n), int(aid_bits),
+                                                   max(int(min_count), 0), int(symmetric), int(strip_dest),
+                                                   ctypes.byref(h)))
+        return Table(self, h.value)
+
+    def mirror(self, table: Table, transpose_only: bool = False) -> Table:
+        """Half table (rows aid <= aid_next) -> full symmetric table (or only the transposed rows)."""
+        h = ctypes.c_void_p()
+        self._sync_stream()
+        self._check(self._lib.ottocov_table_mirror(self._ctx, table._h, int(transpose_only), ctypes.byref(h)))
         return Table(self, h.value)
 
     def count_info(self) -> Dict[str, int]:

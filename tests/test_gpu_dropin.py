@@ -1,0 +1,130 @@
+"""GPU suite (-m gpu): the drop-in surface -- `python -m model.count_co_events` directory contract,
+part/merged parquet schemas, two-level thresholds, resume, and the consumer's per-aid top-N -- against
+the dataframe-shaped restatement of the reference (oracle/ref_restatement.py)."""
+import os
+
+import numpy as np
+import pyarrow as pa
+import pyarrow.parquet as pq
+import pytest
+
+from conftest import small_events
+from oracle import ref_restatement as rr
+from otto_recommender_b200 import count_co_events as cce
+from otto_recommender_b200 import retrieve
+from otto_recommender_b200.config import CoEventConfig
+
+pytestmark = pytest.mark.gpu
+
+
+def _write_parts(dir_sessions, s, a, t, y, n_parts):
+    os.makedirs(dir_sessions, exist_ok=True)
+    ids = np.unique(s)
+    cuts = np.linspace(0, len(ids), n_parts + 1).astype(int)
+    tables = []
+    for i in range(n_parts):
+        lo, hi = ids[cuts[i]], ids[cuts[i + 1] - 1]
+        m = (s >= lo) & (s <= hi)
+        tab = pa.table({"session": pa.array(s[m], pa.int32()), "aid": pa.array(a[m], pa.int32()),
+                        "ts": pa.array(t[m], pa.int32()), "type": pa.array(y[m], pa.int8())})
+        pq.write_table(tab, f"{dir_sessions}/{cuts[i]:07d}_{cuts[i + 1]:07d}.parquet")
+        tables.append(tab)
+    return tables
+
+
+@pytest.fixture()
+def data_dir(tmp_path, engine):
+    cfg = CoEventConfig(DIR_DATA=str(tmp_path))
+    cce.set_config(cfg)
+    cce._engine = engine
+    yield tmp_path
+    cce._engine = None
+
+
+def test_cli_three_phases_match_reference(data_dir):
+    alias = "tt"
+    s, a, t, y = small_events(41, n_sessions=4000, n_aids=25, max_len=30, shuffle=True, dup_frac=0.02)
+    is_test = (s % 5 == 0)
+    parts = {}
+    for pop, m, k in (("train_sessions", ~is_test, 3), ("test_sessions", is_test, 2)):
+        parts[pop] = _write_parts(f"{data_dir}/{alias}-parquet/{pop}", s[m], a[m], t[m], y[m], k)
+
+    cce.main(["--data_split_alias", alias])
+
+    stats = f"{data_dir}/{alias}-counts-co-event"
+    for name in rr.CO_EVENTS_TO_COUNT:
+        merged = {}
+        for pop, tabs in parts.items():
+            per_part = [rr.count_part(tab)[name] for tab in tabs]
+            # phase 1: one file per part, schema (aid i32, aid_next i32, count u32), any row order
+            files = sorted(os.listdir(f"{stats}/{pop}/{name}"))
+            assert len(files) == len(tabs)
+            for f, want in zip(files, per_part):
+                got = pq.read_table(f"{stats}/{pop}/{name}/{f}")
+                assert got.schema.names == ["aid", "aid_next", "count"]
+                assert got.schema.field("count").type == pa.uint32() and got.schema.field("aid").type == pa.int32()
+                assert rr.table_to_dict(got) == rr.table_to_dict(want)
+            # phase 2: per population, thresholded, count desc
+            merged[pop] = rr.merge_counts(name, per_part)
+            got = pq.read_table(f"{stats}/{pop}/{name}.parquet")
+            assert got.schema.names == ["aid", "aid_next", "count"] and got.schema.field("count").type == pa.int32()
+            for c in ("aid", "aid_next", "count"):
+                assert np.array_equal(got[c].to_numpy(), merged[pop][c].to_numpy()), (name, pop, c)
+        # phase 3: train + test; thresholds were applied per population first (two-level)
+        want = rr.merge_counts(name, [merged["train_sessions"], merged["test_sessions"]])
+        got = pq.read_table(f"{stats}/{name}.parquet")
+        for c in ("aid", "aid_next", "count"):
+            assert np.array_equal(got[c].to_numpy(), want[c].to_numpy()), (name, c)
+        assert want.num_rows > 0 or name in ("buy_to_buy", "cart_to_buy")
+        # consumer: per-aid top-N with derived columns (retrieve.py:18-63)
+        if want.num_rows:
+            df = retrieve.get_df_count_for_co_event_type(name, stats)
+            top = rr.top_n_per_aid(want, rr.RETRIEVAL_FIRST_N[name])
+            assert np.array_equal(df["aid"].to_numpy(), top["aid"].to_numpy())
+            assert np.array_equal(df["aid_next"].to_numpy(), top["aid_next"].to_numpy())
+            assert np.array_equal(df[f"{name}_count"].to_numpy(), top["count"].to_numpy())
+            assert np.array_equal(df[f"{name}_rank"].to_numpy(), top["rank"].to_numpy())
+            cnt = top["count"].to_numpy().astype(np.float64)
+            mx = np.maximum.reduceat(cnt, np.r_[0, np.flatnonzero(np.diff(top["aid"].to_numpy())) + 1])
+            seg = np.r_[0, np.cumsum(np.diff(top["aid"].to_numpy()) != 0)]
+            assert np.array_equal(df[f"{name}_count_rel"].to_numpy(), (cnt / mx[seg] * 100).astype(np.int8))
+            assert list(df.columns) == ["aid", "aid_next", f"{name}_count", f"{name}_count_pop", f"{name}_perc_pop",
+                                        f"{name}_rank", f"{name}_count_rel"]
+
+
+def test_resume_skips_existing_parts(data_dir):
+    alias = "rs"
+    s, a, t, y = small_events(43, n_sessions=300, n_aids=20)
+    _write_parts(f"{data_dir}/{alias}-parquet/train_sessions", s, a, t, y, 2)
+    out = f"{data_dir}/{alias}-counts-co-event/train_sessions"
+    cce.count_co_events_all_files(f"{data_dir}/{alias}-parquet/train_sessions", out)
+    f = sorted(os.listdir(f"{out}/click_to_click"))[0]
+    before = os.path.getmtime(f"{out}/click_to_click/{f}")
+    cce.count_co_events_all_files(f"{data_dir}/{alias}-parquet/train_sessions", out)            # all exist: skipped
+    assert os.path.getmtime(f"{out}/click_to_click/{f}") == before
+    os.remove(f"{out}/buy_to_buy/{f}")
+    cce.count_co_events_all_files(f"{data_dir}/{alias}-parquet/train_sessions", out)            # one missing: recomputed
+    assert os.path.exists(f"{out}/buy_to_buy/{f}")
+    assert os.path.getmtime(f"{out}/click_to_click/{f}") > before
+
+
+def test_frame_level_count_co_events(data_dir):
+    s, a, t, y = small_events(44, n_sessions=200, n_aids=15)
+    tab = rr.events_table(s, a, t, y)
+    got = cce.count_co_events(tab)
+    want = rr.count_part(tab)
+    for name in rr.CO_EVENTS_TO_COUNT:
+        g = got[name]
+        assert list(g.columns) == ["aid", "aid_next", "count"]
+        assert {(int(x), int(z)): int(c) for x, z, c in zip(g["aid"], g["aid_next"], g["count"])} == \
+            rr.table_to_dict(want[name])
+
+
+def test_fused_population_equals_phased(data_dir):
+    alias = "fp"
+    s, a, t, y = small_events(45, n_sessions=1500, n_aids=30)
+    tabs = _write_parts(f"{data_dir}/{alias}-parquet/train_sessions", s, a, t, y, 3)
+    fused = cce.count_population(f"{data_dir}/{alias}-parquet/train_sessions")
+    for name, tab in fused.items():
+        want = rr.merge_counts(name, [rr.count_part(x)[name] for x in tabs], exact=True, min_count_to_save=1)
+        assert tab.to_dict() == rr.table_to_dict(want), name

@@ -289,6 +289,38 @@ def test_partition_by_hash(engine):
         assert got == _dict(ka, kb, kc)
 
 
+@pytest.mark.parametrize("name,mc", [("click_to_click", 1), ("click_to_click", 3), ("click_to_cart_or_buy", 2),
+                                     ("cart_to_cart", 1)])
+def test_exchange_first_emulated_ranks(engine, name, mc):
+    """The multi-GPU flow on one GPU: keys grouped by destination rank, each 'rank' reduces its slice,
+    symmetric halves are mirrored; the union must equal the plain single-GPU table."""
+    s, a, t, y = small_events(51, n_sessions=900, n_aids=300, max_len=50)
+    info = engine.load_events(s, a, t, y)
+    want = engine.count(name, min_count=mc, symmetric=False).to_dict()
+    for R in (1, 2, 5, 8):
+        n_keys, sym = engine.expand_prepare(name, min_count=mc)
+        assert sym == (name in ("click_to_click", "cart_to_cart"))
+        buf_a = torch.empty(max(n_keys, 1), dtype=torch.int64, device="cuda")
+        buf_b = torch.empty(max(n_keys, 1), dtype=torch.int64, device="cuda")
+        grouped, rows = engine.expand_run(R, buf_a, buf_b)
+        assert sum(rows) == n_keys
+        off = np.concatenate([[0], np.cumsum(rows)])
+        got = {}
+        for r in range(R):
+            keys_r = grouped[off[r]:off[r + 1]].clone()
+            half = engine.reduce_pairs(keys_r, keys_r.numel(), info["aid_bits"], mc, symmetric=sym, strip_dest=R > 1)
+            ha, hb, hc = half.fetch()
+            assert np.all(hash_dest(ha, R) == r)
+            pieces = [half]
+            if sym:
+                pieces.append(engine.mirror(half, transpose_only=True))
+            for p in pieces:
+                for k, v in p.to_dict().items():
+                    assert k not in got
+                    got[k] = v
+        assert got == want, (name, mc, R)
+
+
 def test_errors_are_loud(engine):
     s, a, t, y = small_events(1, n_sessions=20)
     bad = y.copy(); bad[3] = 5

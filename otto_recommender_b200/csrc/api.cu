@@ -31,6 +31,21 @@ void ottocov_ctx::end(int family, double algo_bytes) {
     if (pe.family == family && pe.b) cudaEventRecord(pe.b, stream);
 }
 
+#include <chrono>
+void cov_trace(ottocov_ctx* ctx, const char* what) {
+    static int on = -1;
+    static std::chrono::steady_clock::time_point last;
+    if (on < 0) { const char* e = getenv("OTTOCOV_TRACE"); on = (e && atoi(e)) ? 1 : 0; last = std::chrono::steady_clock::now(); }
+    if (!on) return;
+    auto t0 = std::chrono::steady_clock::now();
+    cudaStreamSynchronize(ctx->stream);
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[trace] %-28s host %8.3f ms  (+drain %7.3f ms)\n", what,
+            std::chrono::duration<double, std::milli>(t0 - last).count(),
+            std::chrono::duration<double, std::milli>(t1 - t0).count());
+    last = t1;
+}
+
 // ---- caching allocator --------------------------------------------------------------------------------
 void* cov_alloc(ottocov_ctx* ctx, size_t bytes) {
     bytes = (bytes + 511) & ~(size_t)511;

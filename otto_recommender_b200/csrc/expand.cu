@@ -346,7 +346,9 @@ static u64 auto_budget(ottocov_ctx* ctx) {
 ottocov_table* count_impl(ottocov_ctx* ctx, const ottocov_spec* spec) {
     ottocov_count_info& ci = ctx->last_count;
     memset(&ci, 0, sizeof(ci));
+    cov_trace(ctx, "count: enter");
     ExpandPlan* pl = make_plan(ctx, spec, false);
+    cov_trace(ctx, "count: plan (window+scan)");
     struct PlanGuard { ExpandPlan* p; ~PlanGuard() { delete p; } } plan_guard{pl};
     const u64 P = pl->P;
     const bool sym = pl->sym;
@@ -356,6 +358,7 @@ ottocov_table* count_impl(ottocov_ctx* ctx, const ottocov_spec* spec) {
 
     // ---- chunking by pair budget ----------------------------------------------------------------------
     u64 budget = spec->pair_budget > 0 ? (u64)spec->pair_budget : auto_budget(ctx);
+    cov_trace(ctx, "count: budget");
     budget = (budget / EX_TILE) * EX_TILE;
     if (budget == 0) budget = EX_TILE;
 
@@ -371,13 +374,17 @@ ottocov_table* count_impl(ottocov_ctx* ctx, const ottocov_spec* spec) {
         const u64 c1 = (c0 + budget < P) ? c0 + budget : P;
         const u64 cn = c1 - c0;
         DevBuf<u64> keys(ctx, cn), alt(ctx, cn);
+        cov_trace(ctx, "count: alloc keys");
         expand_range(ctx, pl, c0, c1, keys.p, 0);
+        cov_trace(ctx, "count: expand");
         u64* k = keys.p; u64* ka = alt.p; u32* v = nullptr; u32* va = nullptr;
         ci.sort_passes = radix_sort_pairs(ctx, k, ka, v, va, (int64_t)cn, fields, 2);
+        cov_trace(ctx, "count: sort");
         ottocov_table* part = new ottocov_table();
         part->aid_bits = aid_bits;
         partials.push_back(part);
         reduce_sorted(ctx, k, nullptr, (int64_t)cn, fused_min, sym, &part->keys, &part->count, &part->n);
+        cov_trace(ctx, "count: reduce");
         ci.n_chunks += 1;
     }
 
@@ -398,6 +405,7 @@ ottocov_table* count_impl(ottocov_ctx* ctx, const ottocov_spec* spec) {
         dev_free(ctx, result->keys); dev_free(ctx, result->count); delete result;
         result = full;
     }
+    cov_trace(ctx, "count: mirror/merge");
     ci.n_unique = result->n;
     return result;
 }

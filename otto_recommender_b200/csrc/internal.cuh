@@ -34,6 +34,10 @@ struct CovError {
         }                                                                                  \
     } while (0)
 
+// OTTOCOV_TRACE=1: print host wall time between marks (each mark synchronises the stream) -- a poor
+// man's timeline for finding host-side gaps; off by default, never used in timed runs.
+void cov_trace(struct ottocov_ctx* ctx, const char* what);
+
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t imin64(int64_t a, int64_t b) { return a < b ? a : b; }
 

@@ -226,6 +226,22 @@ rs_onesweep_kernel(const u64* __restrict__ keys_in, u64* __restrict__ keys_out,
         s_gbase[tid] = digit_base[tid] + excl - (u64)dstart;
     }
 
+    if (dbg & 16) {
+        // -- D': direct scatter: every key goes straight to its global slot (no staging, no phase F).
+        // A tile's keys of one digit are adjacent in global memory, so L2 merges the 8-byte stores.
+        __syncthreads();                             // s_gbase of the look-back threads
+#pragma unroll
+        for (int i = 0; i < RS_IPT; ++i) {
+            if (i < my_n) {
+                const u32 d = (u32)(key[i] >> shift) & mask;
+                const u32 r = (i & 1) ? (rnk2[i >> 1] >> 16) : (rnk2[i >> 1] & 0xFFFFu);
+                const u64 g = s_gbase[d] + (u64)(my_whist[d] + r);
+                keys_out[g] = key[i];
+                if (HAS_VALS) vals_out[g] = val[i];
+            }
+        }
+        return;
+    }
     // -- D: scatter into the digit-ordered staging buffer ---------------------------------------------------
 #pragma unroll
     for (int i = 0; i < RS_IPT; ++i) {

@@ -60,13 +60,14 @@ class ClockSampler:
 
     def __init__(self, gpu_index: int = 0):
         self.gpu = gpu_index
-        self.rows = []
+        self.rows = []          # (host time the line arrived, line)
         self.proc = None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -75,7 +76,13 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if not self.proc:
@@ -88,7 +95,10 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r for (t, r) in self.rows if self.t0 is None or (self.t0 - 0.05 <= t <= (self.t1 or t) + 0.25)]
+        if not rows:
+            rows = [r for (_, r) in self.rows[-3:]]
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 9:
                 continue
@@ -224,6 +234,11 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # nvidia-smi is started BEFORE the warm-up (its NVML start-up stalls the driver for tens of ms) and
+    # keeps sampling every 100 ms; only samples that arrive inside the timed region are reported.
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         ci, rows_f = step_device()
     barrier()
@@ -240,16 +255,15 @@ def run_ours(args):
             print(f"[breakdown] memory {eng.memory_info()}", file=sys.stderr)
     eng.kernel_stats(reset=True)
     eng.set_profiling(True, families=["sort_pass"])       # the dominant kernel, timed live in the timed region
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     ev0.record()
     for _ in range(args.steps):
         ci, rows_f = step_device()
     ev1.record()
     barrier()
+    sampler.mark_end()
     ms = ev0.elapsed_time(ev1)
     stats = eng.kernel_stats(reset=True)
     eng.set_profiling(True)                                # one extra, untimed step with every family timed
@@ -310,10 +324,14 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel (radix distribution pass) -------------------------------------
     peak, peak_src = _peaks()
+    # achieved = algorithmic bytes of every distribution pass in the timed region / their CUDA-event time.
+    # The per-launch figures are those of the dominant launches (the 6 passes over this rank's keys:
+    # 16 B per key per pass), the same launch shape `traffic` was captured on with ncu.
     sp = stats["sort_pass"]
-    per_launch_ms = sp["ms"] / max(sp["launches"], 1)
-    per_launch_bytes = sp["algo_bytes"] / max(sp["launches"], 1)
-    achieved = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
+    achieved = sp["algo_bytes"] / (sp["ms"] * 1e-3) / 1e9 if sp["ms"] > 0 else 0.0
+    keys_sorted = pairs_local // 2          # click_to_click is symmetric: canonical half pairs
+    per_launch_bytes = 16.0 * keys_sorted
+    per_launch_ms = per_launch_bytes / (achieved * 1e9) * 1e3 if achieved > 0 else 0.0
     traffic = None
     tp = os.path.join(ROOT, "profiles", "sort_pass_traffic.json")
     if os.path.exists(tp):
@@ -365,7 +383,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--sessions", type=int, default=FULL_SESSIONS, help="sessions of the synthetic workload")

@@ -83,75 +83,46 @@ __global__ void __launch_bounds__(RS_RADIX) rs_scan_hist_kernel(u64* __restrict_
 //   F  staged keys leave as coalesced per-digit runs
 constexpr int RS_WINDOW = 4;
 
-// ALGO selects how lanes holding the same digit find each other (tuning knob, see DESIGN.md):
-//   0  match.any            1  NB ballots (one per digit bit)            2  atomicOr on a per-warp mask table
-template <bool HAS_VALS, int ALGO, int NB>
-__global__ void __launch_bounds__(RS_THREADS, 4)
-rs_onesweep_kernel(const u64* __restrict__ keys_in, u64* __restrict__ keys_out,
-                   const u32* __restrict__ vals_in, u32* __restrict__ vals_out, int64_t n, int shift,
-                   int bits, const u64* __restrict__ digit_base, u64* status, u32* ticket, u32 epoch, int dbg) {
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    u64* s_keys = reinterpret_cast<u64*>(s_raw);                              // [RS_TILE]
-    u32* s_whist = reinterpret_cast<u32*>(s_keys + RS_TILE);                  // [RS_WARPS][RS_RADIX]
-    u32* s_dstart = s_whist + RS_WARPS * RS_RADIX;                            // [RS_RADIX]
-    u64* s_gbase = reinterpret_cast<u64*>(s_dstart + RS_RADIX);               // [RS_RADIX]
-    u32* s_scan = reinterpret_cast<u32*>(s_gbase + RS_RADIX);                 // [RS_WARPS + 1] (+pad)
-    u32* s_tile = s_scan + 16;                                                // [1] (+pad to 16)
-    u32* s_match = s_tile + 16;                                               // [RS_WARPS][RS_RADIX] if ALGO == 2
-    u32* s_vals = s_match + (ALGO == 2 ? RS_WARPS * RS_RADIX : 0);            // [RS_TILE] if HAS_VALS
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const u32 radix = 1u << bits, mask = radix - 1u;
-
-    if (tid == 0) *s_tile = atomicAdd(ticket, 1u);
-    for (int j = tid; j < RS_WARPS * RS_RADIX; j += RS_THREADS) {
-        s_whist[j] = 0;
-        if (ALGO == 2) s_match[j] = 0;
+// lanes of the warp whose digit equals this lane's: one ballot per digit bit, 4 SASS instructions per bit
+// (test bit -> predicate, VOTE, predicated NOT, AND).  Bits at and above NB are zero in every lane.
+template <int NB>
+__device__ __forceinline__ u32 match_digit_ballot(u32 d) {
+    u32 peers = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        u32 m;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+            "and.b32 t, %1, %2;\n\t"
+            "setp.ne.u32 p, t, 0;\n\t"
+            "vote.sync.ballot.b32 %0, p, 0xffffffff;\n\t"
+            "@!p not.b32 %0, %0;\n\t}"
+            : "=r"(m)
+            : "r"(d), "r"(1u << b));
+        peers &= m;
     }
-    __syncthreads();
-    const int64_t tile = *s_tile;
-    const int64_t tile_base = tile * RS_TILE;
-    const int tile_n = (int)min((int64_t)RS_TILE, n - tile_base);
+    return peers;
+}
 
-    // -- A: load (warp-striped: every access is a coalesced 256 B row) ------------------------------
-    u64 key[RS_IPT];
-    u32 val[RS_IPT];
-    const int64_t lbase = tile_base + (int64_t)warp * 32 * RS_IPT + lane;
-    const int my_n = (int)min((int64_t)RS_IPT, (n - lbase + 31) / 32);        // valid items of this lane (may be <= 0)
+// Stable rank of each of the lane's RS_IPT keys inside the warp's 512-key segment (rows of 32 keys);
+// bumps the warp's running digit counters.  FULL = every row is valid (all tiles but the last).
+template <int ALGO, int NB, bool FULL>
+__device__ __forceinline__ void rank_rows(const u64 (&key)[RS_IPT], int shift, u32 mask, u32 radix, int my_n, int lane,
+                                          u32 lt, u32* my_whist, u32* mm, u32 (&rnk2)[RS_IPT / 2]) {
 #pragma unroll
     for (int i = 0; i < RS_IPT; ++i) {
-        const int64_t idx = lbase + i * 32;
-        key[i] = (i < my_n) ? ld_stream_u64(keys_in + idx) : ~0ull;
-        if (HAS_VALS) val[i] = (i < my_n) ? __ldcs(vals_in + idx) : 0u;
-    }
-
-    // -- B: stable rank of every key inside its warp's 512-key segment; the per-warp digit counts fall
-    //       out of the same pass.  Lanes holding the same digit are found with one ballot per digit
-    //       bit (match.any is far slower than `bits` ballots on this part); the lowest such lane
-    //       bumps the warp's running counter for the digit, no atomics needed.
-    u32* my_whist = s_whist + warp * RS_RADIX;
-    const u32 lt = lanemask_lt();
-    u32 rnk2[RS_IPT / 2];                       // two 16-bit ranks per register
-#pragma unroll
-    for (int i = 0; i < RS_IPT; ++i) {
-        const bool valid = i < my_n;
+        const bool valid = FULL || i < my_n;
         const u32 d = (u32)(key[i] >> shift) & mask;
         u32 peers;
-        if (dbg & 2) {
-            peers = 1u << lane;
-        } else if (ALGO == 0) {
+        if (ALGO == 0) {
             peers = __match_any_sync(0xffffffffu, valid ? d : radix);      // `radix` never matches a digit
         } else if (ALGO == 1) {
-            const u32 vm = __ballot_sync(0xffffffffu, valid);
-            peers = valid ? vm : ~vm;
-#pragma unroll
-            for (int b = 0; b < NB; ++b) {                                 // bits above `bits` are zero everywhere
-                const bool bit = (d >> b) & 1u;
-                const u32 m = __ballot_sync(0xffffffffu, bit);
-                peers &= bit ? m : ~m;
+            peers = match_digit_ballot<NB>(d);
+            if (!FULL) {
+                const u32 vm = __ballot_sync(0xffffffffu, valid);
+                peers &= valid ? vm : ~vm;
             }
         } else {
-            u32* mm = s_match + warp * RS_RADIX;
             if (valid) atomicOr(&mm[d], 1u << lane);
             __syncwarp();
             peers = valid ? mm[d] : (1u << lane);
@@ -169,6 +140,106 @@ rs_onesweep_kernel(const u64* __restrict__ keys_in, u64* __restrict__ keys_out,
         if (i & 1) rnk2[i >> 1] |= r << 16; else rnk2[i >> 1] = r;
         __syncwarp();
     }
+}
+
+// ALGO selects how lanes holding the same digit find each other (tuning knob, see DESIGN.md):
+//   0  match.any            1  NB ballots (one per digit bit)            2  atomicOr on a per-warp mask table
+// phases A, D and F for one tile; FULL = all 4096 slots valid (every tile but the last): no predicates
+template <bool HAS_VALS, bool FULL>
+__device__ __forceinline__ void load_rows(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in, int64_t lbase,
+                                          int my_n, u64 (&key)[RS_IPT], u32 (&val)[RS_IPT]) {
+#pragma unroll
+    for (int i = 0; i < RS_IPT; ++i) {
+        const bool valid = FULL || i < my_n;
+        key[i] = valid ? ld_stream_u64(keys_in + lbase + i * 32) : ~0ull;
+        if (HAS_VALS) val[i] = valid ? __ldcs(vals_in + lbase + i * 32) : 0u;
+    }
+}
+
+template <bool HAS_VALS, bool FULL>
+__device__ __forceinline__ void stage_rows(const u64 (&key)[RS_IPT], const u32 (&val)[RS_IPT], const u32 (&rnk2)[RS_IPT / 2],
+                                           int shift, u32 mask, int my_n, const u32* my_whist, u64* s_keys, u32* s_vals) {
+#pragma unroll
+    for (int i = 0; i < RS_IPT; ++i) {
+        if (FULL || i < my_n) {
+            const u32 d = (u32)(key[i] >> shift) & mask;
+            const u32 r = (i & 1) ? (rnk2[i >> 1] >> 16) : (rnk2[i >> 1] & 0xFFFFu);
+            const u32 pos = my_whist[d] + r;
+            s_keys[pos] = key[i];
+            if (HAS_VALS) s_vals[pos] = val[i];
+        }
+    }
+}
+
+// s_gptr[d] = byte address of keys_out[global slot of the tile's first key of digit d] - 8 * (slot of that key in
+// the staging buffer), so the key staged at slot j goes to s_gptr[d] + 8 j: one 64-bit add per key.
+template <bool HAS_VALS, bool FULL>
+__device__ __forceinline__ void write_rows(const u64* s_keys, const u32* s_vals, const u64* s_gptr, int shift, u32 mask,
+                                           int tid, int tile_n, const u64* keys_out, u32* vals_out) {
+    const u64 toff = (u64)tid * 8u;
+#pragma unroll
+    for (int i = 0; i < RS_IPT; ++i) {
+        const int j = tid + i * RS_THREADS;
+        if (FULL || j < tile_n) {
+            const u64 k = s_keys[j];
+            const u32 d = (u32)(k >> shift) & mask;
+            const u64 a = s_gptr[d] + toff + (u64)(i * RS_THREADS * 8);
+            __stcs(reinterpret_cast<u64*>(a), k);
+            if (HAS_VALS) {
+                const u64 g = (a - reinterpret_cast<u64>(keys_out)) >> 3;
+                vals_out[g] = s_vals[j];
+            }
+        }
+    }
+}
+
+template <bool HAS_VALS, int ALGO, int NB>
+__global__ void __launch_bounds__(RS_THREADS, 4)
+rs_onesweep_kernel(const u64* __restrict__ keys_in, u64* __restrict__ keys_out,
+                   const u32* __restrict__ vals_in, u32* __restrict__ vals_out, int64_t n, int shift,
+                   int bits, const u64* __restrict__ digit_base, u64* status, u32* ticket, u32 epoch) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    u64* s_keys = reinterpret_cast<u64*>(s_raw);                              // [RS_TILE]
+    u32* s_whist = reinterpret_cast<u32*>(s_keys + RS_TILE);                  // [RS_WARPS][RS_RADIX]
+    u32* s_dstart = s_whist + RS_WARPS * RS_RADIX;                            // [RS_RADIX]
+    u64* s_gptr = reinterpret_cast<u64*>(s_dstart + RS_RADIX);                // [RS_RADIX]
+    u32* s_scan = reinterpret_cast<u32*>(s_gptr + RS_RADIX);                  // [RS_WARPS + 1] (+pad)
+    u32* s_tile = s_scan + 16;                                                // [1] (+pad to 16)
+    u32* s_match = s_tile + 16;                                               // [RS_WARPS][RS_RADIX] if ALGO == 2
+    u32* s_vals = s_match + (ALGO == 2 ? RS_WARPS * RS_RADIX : 0);            // [RS_TILE] if HAS_VALS
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 radix = 1u << bits, mask = radix - 1u;
+
+    if (tid == 0) *s_tile = atomicAdd(ticket, 1u);
+    for (int j = tid; j < RS_WARPS * RS_RADIX; j += RS_THREADS) {
+        s_whist[j] = 0;
+        if (ALGO == 2) s_match[j] = 0;
+    }
+    __syncthreads();
+    const int64_t tile = *s_tile;
+    const int64_t tile_base = tile * RS_TILE;
+    const int tile_n = (int)min((int64_t)RS_TILE, n - tile_base);
+    const bool full = tile_n == RS_TILE;
+
+    // -- A: load (warp-striped: every access is a coalesced 256 B row) ------------------------------
+    u64 key[RS_IPT];
+    u32 val[RS_IPT];
+    const int64_t lbase = tile_base + (int64_t)warp * 32 * RS_IPT + lane;
+    const int my_n = (int)min((int64_t)RS_IPT, (n - lbase + 31) / 32);        // valid items of this lane (may be <= 0)
+    if (full) load_rows<HAS_VALS, true>(keys_in, vals_in, lbase, my_n, key, val);
+    else load_rows<HAS_VALS, false>(keys_in, vals_in, lbase, my_n, key, val);
+
+    // -- B: stable rank of every key inside its warp's 512-key segment; the per-warp digit counts fall
+    //       out of the same pass.  Lanes holding the same digit are found with one ballot per digit
+    //       bit (match.any is far slower than `bits` ballots on this part); the lowest such lane
+    //       bumps the warp's running counter for the digit, no atomics needed.
+    u32* my_whist = s_whist + warp * RS_RADIX;
+    const u32 lt = lanemask_lt();
+    u32 rnk2[RS_IPT / 2];                       // two 16-bit ranks per register
+    u32* mm = (ALGO == 2) ? s_match + warp * RS_RADIX : nullptr;
+    if (full) rank_rows<ALGO, NB, true>(key, shift, mask, radix, my_n, lane, lt, my_whist, mm, rnk2);
+    else rank_rows<ALGO, NB, false>(key, shift, mask, radix, my_n, lane, lt, my_whist, mm, rnk2);
     __syncthreads();
 
     // -- C: offsets over warps, tile totals, digit starts; publish the aggregate ----------------------
@@ -198,7 +269,7 @@ rs_onesweep_kernel(const u64* __restrict__ keys_in, u64* __restrict__ keys_out,
     // -- E: decoupled look-back, RS_WINDOW predecessors per round trip -----------------------------------
     if (tid < (int)radix) {
         u64 excl = 0;
-        if (tile > 0 && !(dbg & 1)) {
+        if (tile > 0) {
             int64_t t = tile - 1;
             while (true) {
                 u64 v[RS_WINDOW];
@@ -223,50 +294,17 @@ rs_onesweep_kernel(const u64* __restrict__ keys_in, u64* __restrict__ keys_out,
             }
             st_volatile_u64(mine, ST_FLAG_PREFIX | tag | (excl + (u64)total));
         }
-        s_gbase[tid] = digit_base[tid] + excl - (u64)dstart;
+        s_gptr[tid] = reinterpret_cast<u64>(keys_out) + (digit_base[tid] + excl - (u64)dstart) * 8u;
     }
 
-    if (dbg & 16) {
-        // -- D': direct scatter: every key goes straight to its global slot (no staging, no phase F).
-        // A tile's keys of one digit are adjacent in global memory, so L2 merges the 8-byte stores.
-        __syncthreads();                             // s_gbase of the look-back threads
-#pragma unroll
-        for (int i = 0; i < RS_IPT; ++i) {
-            if (i < my_n) {
-                const u32 d = (u32)(key[i] >> shift) & mask;
-                const u32 r = (i & 1) ? (rnk2[i >> 1] >> 16) : (rnk2[i >> 1] & 0xFFFFu);
-                const u64 g = s_gbase[d] + (u64)(my_whist[d] + r);
-                keys_out[g] = key[i];
-                if (HAS_VALS) vals_out[g] = val[i];
-            }
-        }
-        return;
-    }
     // -- D: scatter into the digit-ordered staging buffer ---------------------------------------------------
-#pragma unroll
-    for (int i = 0; i < RS_IPT; ++i) {
-        if (i < my_n) {
-            const u32 d = (u32)(key[i] >> shift) & mask;
-            const u32 r = (i & 1) ? (rnk2[i >> 1] >> 16) : (rnk2[i >> 1] & 0xFFFFu);
-            const u32 pos = my_whist[d] + r;
-            s_keys[pos] = key[i];
-            if (HAS_VALS) s_vals[pos] = val[i];
-        }
-    }
+    if (full) stage_rows<HAS_VALS, true>(key, val, rnk2, shift, mask, my_n, my_whist, s_keys, s_vals);
+    else stage_rows<HAS_VALS, false>(key, val, rnk2, shift, mask, my_n, my_whist, s_keys, s_vals);
     __syncthreads();
 
     // -- F: coalesced per-digit runs out --------------------------------------------------------------------
-#pragma unroll
-    for (int i = 0; i < RS_IPT; ++i) {
-        const int j = tid + i * RS_THREADS;
-        if (j < tile_n && !(dbg & 4)) {
-            const u64 k = s_keys[j];
-            const u32 d = (u32)(k >> shift) & mask;
-            const u64 g = (dbg & 8) ? (u64)(tile_base + j) : s_gbase[d] + (u64)j;
-            keys_out[g] = k;
-            if (HAS_VALS) vals_out[g] = s_vals[j];
-        }
-    }
+    if (full) write_rows<HAS_VALS, true>(s_keys, s_vals, s_gptr, shift, mask, tid, tile_n, keys_out, vals_out);
+    else write_rows<HAS_VALS, false>(s_keys, s_vals, s_gptr, shift, mask, tid, tile_n, keys_out, vals_out);
 }
 
 static size_t rs_smem_bytes(bool has_vals, int algo) {
@@ -337,10 +375,8 @@ int radix_sort_pairs(ottocov_ctx* ctx, u64*& keys, u64*& alt, u32*& vals, u32*& 
     ensure_sweep_state(ctx, (size_t)n_tiles * RS_RADIX);
     CUDA_CHECK(cudaMemsetAsync(ctx->sweep_ticket, 0, RS_MAX_PASSES * sizeof(u32), ctx->stream));
 
-    static int algo = -1, dbg = 0;
+    static int algo = -1;
     if (algo < 0) {
-        const char* g = getenv("OTTOCOV_RS_DEBUG");           // timing experiments only (results are wrong)
-        dbg = g ? atoi(g) : 0;
         const char* e = getenv("OTTOCOV_RS_ALGO");            // tuning knob, default = ballots
         algo = e ? atoi(e) : 1;
         if (algo < 0 || algo > 2) algo = 1;
@@ -361,7 +397,7 @@ int radix_sort_pairs(ottocov_ctx* ctx, u64*& keys, u64*& alt, u32*& vals, u32*& 
             }                                                                                               \
             COV_LAUNCH(ctx, OTTOCOV_K_SORT_PASS, pass_bytes, kern, (unsigned)n_tiles, RS_THREADS, smem, keys, alt, \
                        (const u32*)vals, valt, n, pl.shift[p], bits, ghist.p + (size_t)p * RS_RADIX,        \
-                       ctx->sweep_status, ctx->sweep_ticket + p, epoch, dbg);                               \
+                       ctx->sweep_status, ctx->sweep_ticket + p, epoch);                                    \
         } while (0)
 #define RS_DISPATCH(HV)                                                                                     \
         if (algo == 0) RS_LAUNCH(HV, 0, 8);                                                                 \

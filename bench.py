@@ -237,7 +237,7 @@ def run_ours(args):
     # nvidia-smi is started BEFORE the warm-up (its NVML start-up stalls the driver for tens of ms) and
     # keeps sampling every 100 ms; only samples that arrive inside the timed region are reported.
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not args.no_clock_sampler:
         sampler.start()
     for _ in range(args.warmup):
         ci, rows_f = step_device()
@@ -334,7 +334,7 @@ def run_ours(args):
     per_launch_ms = per_launch_bytes / (achieved * 1e9) * 1e3 if achieved > 0 else 0.0
     traffic = None
     tp = os.path.join(ROOT, "profiles", "sort_pass_traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and world == 1 and args.sessions == FULL_SESSIONS:     # captured on exactly this launch shape
         try:
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:
@@ -390,6 +390,7 @@ def main():
     ap.add_argument("--cpu-sample-sessions", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="per-API-call wall times on stderr")
+    ap.add_argument("--no-clock-sampler", action="store_true", help="do not run nvidia-smi during the timed region")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

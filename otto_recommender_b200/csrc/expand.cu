@@ -105,7 +105,7 @@ struct WindowRecords {
     u64* rec_off;
     __device__ u64 value(int64_t j) const {
         const u64 c = cnt[j];
-        return c | ((u64)(c != 0) << 52);
+        return c | ((u64)(c != 0) << SCAN_NC2_SHIFT);
     }
     __device__ void apply(int64_t j, u64 v, const u64* pre) const {
         if (!v) return;

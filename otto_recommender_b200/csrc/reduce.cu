@@ -64,6 +64,7 @@ rle_kernel(const u64* __restrict__ keys, const u32* __restrict__ vals, int64_t n
     __shared__ u32 s_wkeep[RLE_WARPS];
     __shared__ u64 s_outbase;
     __shared__ u32 s_tile;
+    __shared__ u32 s_first_head;           // the tile's first key starts a run: no carry-in to fetch
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
     __syncthreads();
@@ -99,6 +100,7 @@ rle_kernel(const u64* __restrict__ keys, const u32* __restrict__ vals, int64_t n
         if (lane == 31) knext = (r == ITEMS - 1) ? edge_next : nrow_first;
         const bool head = valid && (idx == 0 || key[r] != kprev);
         const bool end = valid && (idx == n - 1 || key[r] != knext);
+        if (r == 0 && threadIdx.x == 0) s_first_head = head ? 1u : 0u;
         const u32 hm = __ballot_sync(0xffffffffu, head);
         const u32 m = hm & le;
         const bool has = m != 0;
@@ -138,8 +140,7 @@ rle_kernel(const u64* __restrict__ keys, const u32* __restrict__ vals, int64_t n
         // carry-in: only needed when the tile does not open with a head; walk back to the nearest tile
         // that contains one (tile 0 always does)
         u64 c_in = 0;
-        const bool first_is_head = (tile == 0) || (keys[tile * TILE] != keys[tile * TILE - 1]);
-        if (!first_is_head) {
+        if (!s_first_head) {
             for (int64_t t = tile - 1; t >= 0; --t) {
                 u64 x;
                 while (true) {

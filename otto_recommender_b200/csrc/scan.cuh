@@ -6,8 +6,8 @@
 //     static constexpr int NC;                    number of counters (1..3)
 //     __device__ u64  value(int64_t i) const;      the counters of element i, packed
 //     __device__ void apply(int64_t i, u64 packed_value, const u64* prefix /*[NC]*/) const;
-// Packing inside one tile: NC==1 -> the full 64 bits; NC==2 -> counter 0 in bits [0,52), counter 1
-// in [52,64) (a 0/1 flag everywhere it is used); NC==3 -> 21 bits each (0/1 flags).  Across tiles the
+// Packing inside one tile: NC==1 -> the full 64 bits; NC==2 -> counter 0 in bits [0,50), counter 1
+// in [50,64) (a 0/1 flag everywhere it is used: <= 4096 per tile); NC==3 -> 21 bits each (0/1 flags).  Across tiles the
 // counters travel unpacked, one 64-bit status word per (tile, counter):
 //     flag(2) | epoch(6) | value(56)        flag 1 = tile aggregate, 2 = inclusive prefix
 // The epoch changes with every launch, so the status array is never cleared between launches.
@@ -17,15 +17,17 @@
 // exclusive prefix over earlier tiles by a 32-wide look-back, then every element is handed to
 // F::apply with its global prefix.
 //
-// Element order inside a tile: warp w owns elements [w*32*ITEMS, (w+1)*32*ITEMS); in round r its lane
+// 512 threads x 8 rows = 4096 elements per tile.  Element order inside a tile: warp w owns elements [w*32*ITEMS, (w+1)*32*ITEMS); in round r its lane
 // l handles element w*32*ITEMS + r*32 + l, so every warp access is a coalesced 32-wide row.
 #pragma once
 #include "internal.cuh"
 
-constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_THREADS = 512;
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 constexpr int SCAN_MAX_NC = 3;
+constexpr int SCAN_NC2_SHIFT = 50;             // NC == 2: counter 1 lives in bits [50, 64)
+static_assert(SCAN_TILE < (1 << (64 - SCAN_NC2_SHIFT)) && SCAN_TILE < (1 << 21), "per-tile flag counters would overflow");
 
 constexpr u64 SC_VALUE_MASK = (1ull << 56) - 1;
 constexpr u64 SC_FLAG_AGG = 1ull << 62;
@@ -36,8 +38,8 @@ __device__ __forceinline__ void scan_unpack(u64 p, u64* c) {
     if (NC == 1) {
         c[0] = p;
     } else if (NC == 2) {
-        c[0] = p & ((1ull << 52) - 1);
-        c[1] = p >> 52;
+        c[0] = p & ((1ull << SCAN_NC2_SHIFT) - 1);
+        c[1] = p >> SCAN_NC2_SHIFT;
     } else {
         c[0] = p & 0x1FFFFF;
         c[1] = (p >> 21) & 0x1FFFFF;
@@ -117,18 +119,18 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_onepass_kernel(F f, int64_t
     }
     if (lane == 0) s_warp_tot[warp] = carry;
     __syncthreads();
-    if (warp == 0) {
+    if (warp < F::NC) {                          // warp k resolves counter k: the NC look-backs run side by side
         u64 t = (lane < SCAN_THREADS / 32) ? s_warp_tot[lane] : 0ull;
         t = warp_sum_u64(t);
         u64 c[SCAN_MAX_NC];
         scan_unpack<F::NC>(t, c);
+        u64 mine = c[0];
 #pragma unroll
-        for (int k = 0; k < F::NC; ++k) {
-            const u64 pre = warp_lookback_sum(status + tile * F::NC + k, F::NC, tile, c[k], epoch);
-            if (lane == 0) {
-                s_tile_pref[k] = pre;
-                if (tile == n_tiles - 1) totals[k] = pre + c[k];
-            }
+        for (int k = 1; k < F::NC; ++k) mine = (warp == k) ? c[k] : mine;
+        const u64 pre = warp_lookback_sum(status + tile * F::NC + warp, F::NC, tile, mine, epoch);
+        if (lane == 0) {
+            s_tile_pref[warp] = pre;
+            if (tile == n_tiles - 1) totals[warp] = pre + mine;
         }
     }
     __syncthreads();

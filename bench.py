@@ -39,6 +39,7 @@ NAME = "click_to_click"
 FULL_SESSIONS = 12_900_000
 N_AIDS = 1_800_000
 MIN_COUNT = 10
+AID_BITS = (N_AIDS - 1).bit_length()      # catalogue size is known: no all-reduce for the key width
 TOP_K = 20
 
 
@@ -188,7 +189,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from otto_recommender_b200 import Engine
-    from otto_recommender_b200.dist import count_exchange_first, shard_bounds
+    from otto_recommender_b200.dist import count_exchange_first, count_exchange_push, shard_bounds
     from otto_recommender_b200.synth import SynthSpec, generate
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -215,11 +216,12 @@ def run_ours(args):
     torch.cuda.empty_cache()
 
     eng = Engine(device=local_rank)
+    exchange = count_exchange_first if args.exchange == "nccl" else count_exchange_push
 
     def step_device():
         eng.load_events(*cols)
         if world > 1:                                     # raw keys cross NVLink once, reduce where they land
-            f = count_exchange_first(eng, NAME, MIN_COUNT)
+            f = exchange(eng, NAME, MIN_COUNT, aid_bits=AID_BITS)
             ci = eng.count_info()
         else:                                             # threshold fused into the run-length reduce
             f = eng.count(NAME, min_count=MIN_COUNT)
@@ -290,7 +292,7 @@ def run_ours(args):
     def step_e2e():
         eng.load_events(*host_cols)                       # H2D inside
         if world > 1:
-            f = count_exchange_first(eng, NAME, MIN_COUNT)
+            f = exchange(eng, NAME, MIN_COUNT, aid_bits=AID_BITS)
         else:
             f = eng.count(NAME, min_count=MIN_COUNT)
         ax, nv, ay, ac = eng.topk(f, TOP_K, pinned=True)   # D2H inside
@@ -359,7 +361,9 @@ def run_ours(args):
                         f"{rows_global:,} event rows / {N_AIDS:,} aids (BASELINE configs[1])",
             "pairs_per_step": pairs_global, "table_rows_sum_over_ranks": uniq_sum,
             "thresholded_rows_rank0": rows_f, "sort_passes": ci["sort_passes"], "chunks": ci["n_chunks"],
-            "parallelism": f"session-sharded x{world}, hash(aid) all-to-all" if world > 1 else "single GPU",
+            "parallelism": (f"session-sharded x{world}, keys re-sharded by hash(aid): " +
+                            ("fused partition + peer stores over NVLink" if args.exchange == "push" else "NCCL all-to-all"))
+            if world > 1 else "single GPU",
             "l2": "inputs (event columns, pair keys) are far larger than the 126 MB L2; no flush needed",
         },
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms_per_step,
@@ -390,6 +394,8 @@ def main():
     ap.add_argument("--cpu-sample-sessions", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="per-API-call wall times on stderr")
+    ap.add_argument("--exchange", default="push", choices=["push", "nccl"],
+                    help="N > 1: fused partition + peer-store kernel over NVLink (push) or NCCL all-to-all (nccl)")
     ap.add_argument("--no-clock-sampler", action="store_true", help="do not run nvidia-smi during the timed region")
     args = ap.parse_args()
     if args.impl == "reference":

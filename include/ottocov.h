@@ -181,6 +181,13 @@ uint32_t ottocov_hash_dest(uint32_t aid, uint32_t n_ranks);
 int ottocov_expand_prepare(ottocov_ctx* ctx, const ottocov_spec* spec, int64_t* n_keys, int* symmetric);
 int ottocov_expand_run(ottocov_ctx* ctx, int n_ranks, uint64_t* buf_a_dev, uint64_t* buf_b_dev,
                        int* result_in_b, int64_t* rows_per_dest);
+/* Fused partition + exchange: with buf_b_dev == NULL ottocov_expand_run only expands the stamped keys into
+ * buf_a_dev and counts them per destination; ottocov_push_keys then runs the ONE distribution pass with
+ * each destination's run starting at dest_ptrs[rank] -- a device BYTE address inside that rank's receive
+ * buffer, mapped into this process (CUDA IPC / torch symmetric memory), so the keys cross NVLink as the
+ * coalesced stores of the partition kernel itself.  dest_ptrs is a HOST array [n_ranks]; the caller
+ * exchanged the per-destination counts first and synchronises the ranks around the call. */
+int ottocov_push_keys(ottocov_ctx* ctx, const uint64_t* keys_dev, int64_t n, int n_ranks, const uint64_t* dest_ptrs);
 int ottocov_reduce_pairs(ottocov_ctx* ctx, uint64_t* keys_dev, int64_t n, int aid_bits, uint32_t min_count,
                          int symmetric, int strip_dest, ottocov_table** out);
 int ottocov_table_mirror(ottocov_ctx* ctx, const ottocov_table* t, int transpose_only, ottocov_table** out);

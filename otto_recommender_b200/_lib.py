@@ -58,6 +58,7 @@ SYMBOLS = {
     "ottocov_count": (c_int, [c_void_p, POINTER(Spec), POINTER(c_void_p)]),
     "ottocov_expand_prepare": (c_int, [c_void_p, POINTER(Spec), POINTER(c_int64), POINTER(c_int)]),
     "ottocov_expand_run": (c_int, [c_void_p, c_int, c_void_p, c_void_p, POINTER(c_int), POINTER(c_int64)]),
+    "ottocov_push_keys": (c_int, [c_void_p, c_void_p, c_int64, c_int, POINTER(c_uint64)]),
     "ottocov_reduce_pairs": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_uint32, c_int, c_int, POINTER(c_void_p)]),
     "ottocov_table_mirror": (c_int, [c_void_p, c_void_p, c_int, POINTER(c_void_p)]),
     "ottocov_get_count_info": (c_int, [c_void_p, POINTER(CountInfo)]),

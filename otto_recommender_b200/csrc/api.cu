@@ -297,6 +297,13 @@ int ottocov_expand_run(ottocov_ctx* ctx, int n_ranks, uint64_t* buf_a_dev, uint6
     API_END(ctx)
 }
 
+int ottocov_push_keys(ottocov_ctx* ctx, const uint64_t* keys_dev, int64_t n, int n_ranks, const uint64_t* dest_ptrs) {
+    API_BEGIN(ctx)
+    if (n < 0 || !dest_ptrs || (n > 0 && !keys_dev)) COV_THROW(OTTOCOV_ERR_ARG, "bad argument");
+    push_keys_impl(ctx, (const u64*)keys_dev, n, n_ranks, (const u64*)dest_ptrs);
+    API_END(ctx)
+}
+
 int ottocov_reduce_pairs(ottocov_ctx* ctx, uint64_t* keys_dev, int64_t n, int aid_bits, uint32_t min_count,
                          int symmetric, int strip_dest, ottocov_table** out) {
     API_BEGIN(ctx)

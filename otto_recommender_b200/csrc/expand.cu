@@ -452,6 +452,11 @@ void expand_run_impl(ottocov_ctx* ctx, int n_ranks, u64* buf_a, u64* buf_b, int*
                256, 0, buf_a, n, (u32)n_ranks, cnt.p);
     unsigned long long h[256];
     CUDA_CHECK(cudaMemcpyAsync(h, cnt.p, 256 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    if (!buf_b) {                    // caller will push the keys itself (ottocov_push_keys): no local grouping
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        for (int r = 0; r < n_ranks; ++r) rows_per_dest[r] = (int64_t)h[r];
+        return;
+    }
     int bits = 1;
     while ((1 << bits) < n_ranks) ++bits;
     BitField f[1] = {{56, 56 + bits}};
@@ -460,6 +465,13 @@ void expand_run_impl(ottocov_ctx* ctx, int n_ranks, u64* buf_a, u64* buf_b, int*
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     for (int r = 0; r < n_ranks; ++r) rows_per_dest[r] = (int64_t)h[r];
     *result_in_b = (k == buf_b) ? 1 : 0;
+}
+
+void push_keys_impl(ottocov_ctx* ctx, const u64* keys, int64_t n, int n_ranks, const u64* dest_ptrs_host) {
+    if (n_ranks < 2 || n_ranks > 256) COV_THROW(OTTOCOV_ERR_ARG, "n_ranks must be 2..256");
+    int bits = 1;
+    while ((1 << bits) < n_ranks) ++bits;
+    radix_partition_push(ctx, keys, n, 56, bits, dest_ptrs_host, n_ranks);
 }
 
 __global__ void __launch_bounds__(256) strip_dest_kernel(u64* __restrict__ keys, int64_t n) {

@@ -152,6 +152,9 @@ struct BitField { int lo, hi; };   // sort on key bits [lo, hi)
 int radix_sort_pairs(ottocov_ctx* ctx, u64*& keys, u64*& alt, u32*& vals, u32*& valt, int64_t n,
                      const BitField* fields, int n_fields);
 
+void radix_partition_push(ottocov_ctx* ctx, const u64* keys, int64_t n, int shift, int bits,
+                          const u64* ptr_base_host, int n_digits);
+
 // events.cu
 void load_events_impl(ottocov_ctx* ctx, const int32_t* session, const int32_t* aid,
                       const int32_t* ts, const int8_t* type, int64_t n, int where);
@@ -162,6 +165,7 @@ ottocov_table* count_impl(ottocov_ctx* ctx, const ottocov_spec* spec);
 void free_plan(ottocov_ctx* ctx);
 void expand_prepare_impl(ottocov_ctx* ctx, const ottocov_spec* spec, int64_t* n_keys, int* symmetric);
 void expand_run_impl(ottocov_ctx* ctx, int n_ranks, u64* buf_a, u64* buf_b, int* result_in_b, int64_t* rows_per_dest);
+void push_keys_impl(ottocov_ctx* ctx, const u64* keys, int64_t n, int n_ranks, const u64* dest_ptrs_host);
 ottocov_table* reduce_pairs_impl(ottocov_ctx* ctx, u64* keys, int64_t n, int aid_bits, u32 min_count, int sym,
                                  int strip_dest);
 

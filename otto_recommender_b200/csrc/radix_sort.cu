@@ -197,7 +197,8 @@ template <bool HAS_VALS, int ALGO, int NB>
 __global__ void __launch_bounds__(RS_THREADS, 4)
 rs_onesweep_kernel(const u64* __restrict__ keys_in, u64* __restrict__ keys_out,
                    const u32* __restrict__ vals_in, u32* __restrict__ vals_out, int64_t n, int shift,
-                   int bits, const u64* __restrict__ digit_base, u64* status, u32* ticket, u32 epoch) {
+                   int bits, const u64* __restrict__ digit_base, const u64* __restrict__ ptr_base, u64* status,
+                   u32* ticket, u32 epoch) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     u64* s_keys = reinterpret_cast<u64*>(s_raw);                              // [RS_TILE]
     u32* s_whist = reinterpret_cast<u32*>(s_keys + RS_TILE);                  // [RS_WARPS][RS_RADIX]
@@ -294,7 +295,10 @@ rs_onesweep_kernel(const u64* __restrict__ keys_in, u64* __restrict__ keys_out,
             }
             st_volatile_u64(mine, ST_FLAG_PREFIX | tag | (excl + (u64)total));
         }
-        s_gptr[tid] = reinterpret_cast<u64>(keys_out) + (digit_base[tid] + excl - (u64)dstart) * 8u;
+        // ptr_base (fused partition + exchange): digit d is a destination rank and its run starts at a
+        // byte address inside that rank's receive buffer, mapped into this process over NVLink
+        s_gptr[tid] = ptr_base ? ptr_base[tid] + (excl - (u64)dstart) * 8u
+                               : reinterpret_cast<u64>(keys_out) + (digit_base[tid] + excl - (u64)dstart) * 8u;
     }
 
     // -- D: scatter into the digit-ordered staging buffer ---------------------------------------------------
@@ -397,7 +401,7 @@ int radix_sort_pairs(ottocov_ctx* ctx, u64*& keys, u64*& alt, u32*& vals, u32*& 
             }                                                                                               \
             COV_LAUNCH(ctx, OTTOCOV_K_SORT_PASS, pass_bytes, kern, (unsigned)n_tiles, RS_THREADS, smem, keys, alt, \
                        (const u32*)vals, valt, n, pl.shift[p], bits, ghist.p + (size_t)p * RS_RADIX,        \
-                       ctx->sweep_status, ctx->sweep_ticket + p, epoch);                                    \
+                       (const u64*)nullptr, ctx->sweep_status, ctx->sweep_ticket + p, epoch);                                    \
         } while (0)
 #define RS_DISPATCH(HV)                                                                                     \
         if (algo == 0) RS_LAUNCH(HV, 0, 8);                                                                 \
@@ -413,4 +417,34 @@ int radix_sort_pairs(ottocov_ctx* ctx, u64*& keys, u64*& alt, u32*& vals, u32*& 
         if (has_vals) { u32* tv = vals; vals = valt; valt = tv; }
     }
     return pl.n;
+}
+
+// One stable distribution pass on key bits [shift, shift + bits) whose per-digit output runs start at the
+// byte addresses in ptr_base_host[digit] (device addresses; digits are destination ranks and the
+// addresses may be peer memory mapped over NVLink): partition and exchange fused into one kernel.
+void radix_partition_push(ottocov_ctx* ctx, const u64* keys, int64_t n, int shift, int bits,
+                          const u64* ptr_base_host, int n_digits) {
+    if (n <= 0) return;
+    if (bits < 1 || bits > RS_MAX_BITS || n_digits > (1 << bits)) COV_THROW(OTTOCOV_ERR_ARG, "bad digit width for push");
+    DevBuf<u64> pb(ctx, RS_RADIX);
+    u64 h[RS_RADIX];
+    for (int d = 0; d < RS_RADIX; ++d) h[d] = d < n_digits ? ptr_base_host[d] : 0;
+    CUDA_CHECK(cudaMemcpyAsync(pb.p, h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+    const int64_t n_tiles = ceil_div64(n, RS_TILE);
+    ensure_sweep_state(ctx, (size_t)n_tiles * RS_RADIX);
+    CUDA_CHECK(cudaMemsetAsync(ctx->sweep_ticket, 0, RS_MAX_PASSES * sizeof(u32), ctx->stream));
+    const u32 epoch = next_epoch(ctx);
+    auto kern = (bits <= 4) ? rs_onesweep_kernel<false, 1, 4> : rs_onesweep_kernel<false, 1, 8>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<false, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(true, 2)));
+        CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<false, 1, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<false, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(true, 2)));
+        CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<false, 1, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        attr_done = true;
+    }
+    COV_LAUNCH(ctx, OTTOCOV_K_PARTITION, 16.0 * n, kern, (unsigned)n_tiles, RS_THREADS, rs_smem_bytes(false, 1), keys,
+               (u64*)nullptr, (const u32*)nullptr, (u32*)nullptr, n, shift, bits, (const u64*)nullptr, (const u64*)pb.p,
+               ctx->sweep_status, ctx->sweep_ticket, epoch);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));      // `h` lives on this stack frame
 }

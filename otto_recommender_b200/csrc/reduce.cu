@@ -547,9 +547,59 @@ struct ToDest {
     }
 };
 
+// dest rank stamped into key bits 56..63 (valid while aids stay below 2^24), counted per destination
+__global__ void __launch_bounds__(256) stamp_dest_kernel(const u64* __restrict__ keys, int64_t n, u32 n_ranks,
+                                                         u64* __restrict__ out, unsigned long long* __restrict__ counts) {
+    __shared__ unsigned int s_c[256];
+    s_c[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const u64 k = keys[i];
+        const u32 d = hash_dest((u32)(k >> 32), n_ranks);
+        out[i] = k | ((u64)d << 56);
+        atomicAdd(&s_c[d], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < n_ranks && s_c[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)s_c[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(256) unstamp_copy_kernel(const u64* __restrict__ keys, const u32* __restrict__ cnt,
+                                                           int64_t n, u64* __restrict__ okeys, u32* __restrict__ ocnt) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    okeys[i] = keys[i] & 0x00FFFFFFFFFFFFFFull;
+    ocnt[i] = cnt[i];
+}
+
 void partition_table_impl(ottocov_ctx* ctx, const ottocov_table* t, int n_ranks, u64* keys_out,
                           u32* count_out, int64_t* rows_per_dest) {
-    u64 base = 0;
+    const int64_t n = t->n;
+    for (int r = 0; r < n_ranks; ++r) rows_per_dest[r] = 0;
+    if (n == 0) return;
+    if (t->aid_bits <= 24 && n_ranks <= 256) {
+        // one stamping pass + ONE stable radix pass on the destination bits (one host sync in total)
+        DevBuf<u64> k0(ctx, n), k1(ctx, n);
+        DevBuf<u32> c0(ctx, n), c1(ctx, n);
+        DevBuf<unsigned long long> cnt(ctx, 256);
+        CUDA_CHECK(cudaMemsetAsync(cnt.p, 0, 256 * sizeof(unsigned long long), ctx->stream));
+        COV_LAUNCH(ctx, OTTOCOV_K_PARTITION, 16.0 * n, stamp_dest_kernel, (int)imin64(ceil_div64(n, 1024), (int64_t)ctx->num_sms * 8),
+                   256, 0, t->keys, n, (u32)n_ranks, k0.p, cnt.p);
+        CUDA_CHECK(cudaMemcpyAsync(c0.p, t->count, n * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->stream));
+        unsigned long long h[256];
+        CUDA_CHECK(cudaMemcpyAsync(h, cnt.p, 256 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        int bits = 1;
+        while ((1 << bits) < n_ranks) ++bits;
+        BitField f[1] = {{56, 56 + bits}};
+        u64* k = k0.p; u64* ka = k1.p; u32* v = c0.p; u32* va = c1.p;
+        radix_sort_pairs(ctx, k, ka, v, va, n, f, 1);
+        COV_LAUNCH(ctx, OTTOCOV_K_PARTITION, 24.0 * n, unstamp_copy_kernel, (unsigned)ceil_div64(n, 256), 256, 0, k, v, n,
+                   keys_out, count_out);
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        for (int r = 0; r < n_ranks; ++r) rows_per_dest[r] = (int64_t)h[r];
+        return;
+    }
+    u64 base = 0;                    // general fallback: one compaction per destination
     for (int r = 0; r < n_ranks; ++r) {
         ToDest f;
         f.keys = t->keys; f.count = t->count; f.n_ranks = (u32)n_ranks; f.dest = (u32)r;

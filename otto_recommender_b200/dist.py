@@ -108,7 +108,21 @@ def exchange_keys(send_keys: torch.Tensor, rows_per_dest: Sequence[int], group=N
     return recv
 
 
-def count_exchange_first(engine, name: str, min_count: int = 1, group=None):
+def global_aid_bits(engine, group=None) -> int:
+    """Significant aid bits over all ranks' loaded events (bounds the radix passes).  One all-reduce per
+    load_events call (every rank loads the same number of times, so all ranks take the same branch)."""
+    gen = engine.load_generation
+    cached = getattr(engine, "_global_aid_bits", None)
+    if cached is not None and cached[0] == gen:
+        return cached[1]
+    bits = torch.tensor([engine.events_info()["aid_bits"]], dtype=torch.int64, device=torch.device("cuda", engine.device))
+    if dist.get_world_size(group) > 1:
+        dist.all_reduce(bits, op=dist.ReduceOp.MAX, group=group)
+    engine._global_aid_bits = (gen, int(bits.item()))
+    return engine._global_aid_bits[1]
+
+
+def count_exchange_first(engine, name: str, min_count: int = 1, group=None, aid_bits: Optional[int] = None):
     """Exchange-before-reduce: the raw keys of this rank's sessions cross NVLink once (8 B per pair, half
     of them for symmetric kinds), then every rank sorts and reduces only the pairs it owns -- per-rank
     work is P / R, and the count threshold can be fused into the reduce because sums are complete.
@@ -122,10 +136,9 @@ def count_exchange_first(engine, name: str, min_count: int = 1, group=None):
     grouped, rows = engine.expand_run(world, buf_a, buf_b)
     recv = exchange_keys(grouped[:n_keys], rows, group) if world > 1 else grouped[:n_keys]
     del buf_a, buf_b, grouped
-    bits = torch.tensor([engine.events_info()["aid_bits"]], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.all_reduce(bits, op=dist.ReduceOp.MAX, group=group)
-    half = engine.reduce_pairs(recv, recv.numel(), int(bits.item()), min_count, symmetric=sym, strip_dest=world > 1)
+    if aid_bits is None:                 # pass it when the catalogue size is known: saves an all-reduce
+        aid_bits = global_aid_bits(engine, group)
+    half = engine.reduce_pairs(recv, recv.numel(), aid_bits, min_count, symmetric=sym, strip_dest=world > 1)
     if not sym:
         return half
     if world == 1:
@@ -133,6 +146,73 @@ def count_exchange_first(engine, name: str, min_count: int = 1, group=None):
         half.free()
         return full
     mirrored = engine.mirror(half, transpose_only=True)       # rows (b, a, c) live on rank hash(b)
+    theirs = reshard_table(engine, mirrored, group)
+    full = engine.merge([half, theirs])
+    for t in (half, mirrored, theirs):
+        t.free()
+    return full
+
+
+class PushExchange:
+    """Receive buffers in symmetric memory (torch.distributed._symmetric_memory): every rank's buffer is
+    mapped into every other rank's address space over NVLink, so the partition kernel of
+    ottocov_push_keys stores each key directly where its owner will sort it.  One instance per
+    (engine, process group); grows by collective agreement when a step would not fit."""
+
+    def __init__(self, engine, group=None):
+        self.engine, self.group = engine, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.dev = torch.device("cuda", engine.device)
+        self.capacity = 0            # allocated on first use: the size must be identical on every rank
+
+    def _alloc(self, capacity: int):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.capacity = int(capacity)
+        self.recv = symm_mem.empty(self.capacity, dtype=torch.int64, device=self.dev)
+        gname = self.group.group_name if self.group is not None else dist.group.WORLD.group_name
+        self.handle = symm_mem.rendezvous(self.recv, gname)
+        self.peer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
+
+    def exchange(self, keys: torch.Tensor, n_keys: int, rows_per_dest: Sequence[int]) -> torch.Tensor:
+        """keys: stamped, NOT grouped (expand_run with buf_b=None).  Returns this rank's received keys."""
+        mine = torch.tensor(list(rows_per_dest), dtype=torch.int64, device=self.dev)
+        allc = torch.empty(self.world * self.world, dtype=torch.int64, device=self.dev)
+        dist.all_gather_into_tensor(allc, mine, group=self.group)
+        m = allc.view(self.world, self.world).cpu().numpy()          # m[src, dst]
+        incoming = m.sum(axis=0)
+        need = int(incoming.max())
+        if need > self.capacity:                                      # same decision and size on every rank
+            self._alloc(int(need * 1.25) + 4096)
+        offs = m[: self.rank, :].sum(axis=0)                          # my slot range in every destination
+        dest_ptrs = [self.peer_ptrs[d] + int(offs[d]) * 8 for d in range(self.world)]
+        self.handle.barrier(channel=0)                                # nobody still reads its receive buffer
+        self.engine.push_keys(keys, n_keys, dest_ptrs)
+        self.handle.barrier(channel=1)                                # every push has landed
+        return self.recv[: int(incoming[self.rank])]
+
+
+_push_exchanges = {}
+
+
+def count_exchange_push(engine, name: str, min_count: int = 1, group=None, aid_bits: Optional[int] = None):
+    """count_exchange_first with the NCCL all-to-all replaced by the fused partition + peer-store kernel."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return count_exchange_first(engine, name, min_count, group, aid_bits)
+    dev = torch.device("cuda", engine.device)
+    n_keys, sym = engine.expand_prepare(name, min_count=min_count)
+    buf_a = torch.empty(max(n_keys, 1), dtype=torch.int64, device=dev)
+    keys, rows = engine.expand_run(world, buf_a, None)
+    ex = _push_exchanges.get((id(engine), id(group)))
+    if ex is None:
+        ex = _push_exchanges[(id(engine), id(group))] = PushExchange(engine, group)
+    recv = ex.exchange(keys, n_keys, rows)
+    if aid_bits is None:
+        aid_bits = global_aid_bits(engine, group)
+    half = engine.reduce_pairs(recv, recv.numel(), aid_bits, min_count, symmetric=sym, strip_dest=True)
+    if not sym:
+        return half
+    mirrored = engine.mirror(half, transpose_only=True)
     theirs = reshard_table(engine, mirrored, group)
     full = engine.merge([half, theirs])
     for t in (half, mirrored, theirs):

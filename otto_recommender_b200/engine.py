@@ -106,6 +106,7 @@ class Engine:
             raise OttocovError(rc, msg.decode() if msg else "ottocov_create failed")
         self._ctx = ctx
         self._stream = None
+        self.load_generation = 0          # bumped by every load_events call
         if profiling:
             self.set_profiling(True)
 
@@ -199,6 +200,7 @@ class Engine:
         n = len(ks)
         if not (len(ka) == len(kt) == len(ky) == n):
             raise ValueError("columns differ in length")
+        self.load_generation += 1
         self._check(self._lib.ottocov_load_events(self._ctx, ps, pa, pt, py, n, ws))
         return self.events_info()
 
@@ -245,15 +247,24 @@ class Engine:
         self._check(self._lib.ottocov_expand_prepare(self._ctx, ctypes.byref(spec), ctypes.byref(n), ctypes.byref(sym)))
         return int(n.value), bool(sym.value)
 
-    def expand_run(self, n_ranks: int, buf_a, buf_b):
-        """Emit the prepared keys grouped by destination rank into caller tensors (int64, CUDA).
-        -> (tensor holding the grouped keys, rows_per_dest)."""
+    def expand_run(self, n_ranks: int, buf_a, buf_b=None):
+        """Emit the prepared keys into caller tensors (int64, CUDA), grouped by destination rank when
+        buf_b is given (else only stamped + counted: see push_keys).
+        -> (tensor holding the keys, rows_per_dest)."""
         rows = (ctypes.c_int64 * n_ranks)()
         in_b = ctypes.c_int()
         self._sync_stream()
-        self._check(self._lib.ottocov_expand_run(self._ctx, n_ranks, buf_a.data_ptr(), buf_b.data_ptr(),
+        self._check(self._lib.ottocov_expand_run(self._ctx, n_ranks, buf_a.data_ptr(),
+                                                 buf_b.data_ptr() if buf_b is not None else None,
                                                  ctypes.byref(in_b), rows))
         return (buf_b if in_b.value else buf_a), [int(x) for x in rows]
+
+    def push_keys(self, keys, n: int, dest_ptrs: Sequence[int]):
+        """Fused partition + exchange: one distribution pass over stamped keys whose per-destination runs
+        start at dest_ptrs[rank] (device byte addresses, typically peer memory)."""
+        arr = (ctypes.c_uint64 * len(dest_ptrs))(*[int(p) for p in dest_ptrs])
+        self._sync_stream()
+        self._check(self._lib.ottocov_push_keys(self._ctx, keys.data_ptr() if n else None, int(n), len(dest_ptrs), arr))
 
     def reduce_pairs(self, keys, n: int, aid_bits: int, min_count: int = 1, symmetric: bool = False,
                      strip_dest: bool = False) -> Table:

@@ -321,6 +321,32 @@ def test_exchange_first_emulated_ranks(engine, name, mc):
         assert got == want, (name, mc, R)
 
 
+def test_push_keys_emulated_peers(engine):
+    """ottocov_push_keys with every 'peer' receive buffer living at an offset of one local tensor: the
+    result must be exactly the grouped output of the two-buffer expand_run."""
+    s, a, t, y = small_events(52, n_sessions=1200, n_aids=400, max_len=40)
+    engine.load_events(s, a, t, y)
+    for R in (2, 3, 8):
+        n_keys, _ = engine.expand_prepare("click_to_click", min_count=2)
+        a0 = torch.empty(n_keys, dtype=torch.int64, device="cuda"); b0 = torch.empty_like(a0)
+        grouped, rows = engine.expand_run(R, a0, b0)
+        want = grouped.clone()
+        n2, _ = engine.expand_prepare("click_to_click", min_count=2)
+        assert n2 == n_keys
+        a1 = torch.empty(n_keys, dtype=torch.int64, device="cuda")
+        keys, rows2 = engine.expand_run(R, a1, None)
+        assert rows2 == rows
+        recv = torch.full((n_keys + 8 * R,), -1, dtype=torch.int64, device="cuda")     # 8-key guard gaps
+        off = np.concatenate([[0], np.cumsum(rows)])
+        ptrs = [recv.data_ptr() + 8 * (int(off[d]) + 8 * d) for d in range(R)]
+        engine.push_keys(keys, n_keys, ptrs)
+        torch.cuda.synchronize()
+        for d in range(R):
+            lo = int(off[d]) + 8 * d
+            assert torch.equal(recv[lo:lo + rows[d]], want[int(off[d]):int(off[d + 1])])
+            assert bool((recv[lo + rows[d]:lo + rows[d] + 8] == -1).all())               # nothing spilled past the run
+
+
 def test_errors_are_loud(engine):
     s, a, t, y = small_events(1, n_sessions=20)
     bad = y.copy(); bad[3] = 5

@@ -7,7 +7,8 @@ import numpy as np
 import torch
 import torch.distributed as dist
 from otto_recommender_b200 import Engine
-from otto_recommender_b200.dist import count_distributed, count_exchange_first, gather_table, shard_bounds, hash_dest
+from otto_recommender_b200.dist import (count_distributed, count_exchange_first, count_exchange_push, gather_table,
+                                        shard_bounds, hash_dest)
 from otto_recommender_b200.synth import SynthSpec, generate
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -22,9 +23,10 @@ eng = Engine(local)
 eng.load_events(*[d[k][m].contiguous() for k in ("session", "aid", "ts", "type")])
 ok = True
 cases = [(name, flow, mc) for name in ("click_to_click", "click_to_cart_or_buy", "cart_to_cart", "cart_to_buy", "buy_to_buy")
-         for flow, mc in (("reduce_first", 1), ("exchange_first", 1), ("exchange_first", 3))]
+         for flow, mc in (("reduce_first", 1), ("exchange_first", 1), ("exchange_first", 3), ("push", 1), ("push", 3))]
 for name, flow, mc in cases:
-    shard = count_distributed(eng, name) if flow == "reduce_first" else count_exchange_first(eng, name, mc)
+    shard = (count_distributed(eng, name) if flow == "reduce_first" else
+             count_exchange_first(eng, name, mc) if flow == "exchange_first" else count_exchange_push(eng, name, mc))
     a, bb, c = shard.fetch()
     assert np.all(hash_dest(a, world) == rank), "row on the wrong rank"
     got = gather_table(shard)

@@ -7,7 +7,7 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_double, c_int, c_int32, c_int64, c_uint32, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libottocov.so")
+_SO = os.path.join(_HERE, os.environ.get("OTTOCOV_SO_NAME", "libottocov.so"))     # tuning builds only
 _lib = None
 
 K_FAMILIES = 11

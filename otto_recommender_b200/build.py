@@ -15,7 +15,8 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "_obj")
-SO = os.path.join(HERE, "libottocov.so")
+SO = os.path.join(HERE, os.environ.get("OTTOCOV_SO_NAME", "libottocov.so"))      # tuning builds: other name + -D flags
+EXTRA_DEFS = os.environ.get("OTTOCOV_NVCC_DEFS", "").split()
 SOURCES = ["api.cu", "radix_sort.cu", "events.cu", "expand.cu", "reduce.cu", "topk.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -47,7 +48,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(src: str) -> str:
         obj = os.path.join(OBJ, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *EXTRA_DEFS, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log = r.stdout + r.stderr
         with open(obj + ".log", "w") as fh:

@@ -81,7 +81,10 @@ __global__ void __launch_bounds__(RS_RADIX) rs_scan_hist_kernel(u64* __restrict_
 //   D  keys go to their slot of the digit-ordered staging buffer (the warps without look-back duty do
 //      this while the first `radix` threads are still walking)
 //   F  staged keys leave as coalesced per-digit runs
-constexpr int RS_WINDOW = 4;
+#ifndef OTTOCOV_RS_WINDOW
+#define OTTOCOV_RS_WINDOW 4
+#endif
+constexpr int RS_WINDOW = OTTOCOV_RS_WINDOW;
 
 // lanes of the warp whose digit equals this lane's: one ballot per digit bit, 4 SASS instructions per bit
 // (test bit -> predicate, VOTE, predicated NOT, AND).  Bits at and above NB are zero in every lane.

@@ -46,6 +46,13 @@ void cov_trace(ottocov_ctx* ctx, const char* what) {
     last = t1;
 }
 
+void cov_readback(ottocov_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes) {
+    if (bytes > 4096) COV_THROW(OTTOCOV_ERR_ARG, "read-back larger than the pinned pad");
+    CUDA_CHECK(cudaMemcpyAsync(ctx->pinned, dev_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    memcpy(host_dst, ctx->pinned, bytes);
+}
+
 // ---- caching allocator --------------------------------------------------------------------------------
 void* cov_alloc(ottocov_ctx* ctx, size_t bytes) {
     bytes = (bytes + 511) & ~(size_t)511;
@@ -170,6 +177,7 @@ int ottocov_create(int device, ottocov_ctx** out) {
         CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
         if (prop.major < 10) COV_THROW(OTTOCOV_ERR_CUDA, "device %d is sm_%d%d; libottocov is built for sm_100a only", device, prop.major, prop.minor);
         ctx->num_sms = prop.multiProcessorCount;
+        CUDA_CHECK(cudaHostAlloc(&ctx->pinned, 4096, cudaHostAllocDefault));
         // keep freed blocks in the stream-ordered pool: the pipeline re-allocates the same sizes
         cudaMemPool_t pool;
         CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -201,6 +209,7 @@ int ottocov_destroy(ottocov_ctx* ctx) {
     cov_trim(ctx);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->sweep_ticket) cudaFree(ctx->sweep_ticket);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (ProfEvent& pe : ctx->prof_pending) { if (pe.a) cudaEventDestroy(pe.a); if (pe.b) cudaEventDestroy(pe.b); }
     for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
     (void)cudaGetLastError();

@@ -183,8 +183,7 @@ void load_events_impl(ottocov_ctx* ctx, const int32_t* session, const int32_t* a
         COV_LAUNCH(ctx, OTTOCOV_K_LOAD, 13.0 * n, ev_stats_kernel, grid, 256, 0, session, aid, ts, type, n, d_st.p);
     }
     EvStats st;
-    CUDA_CHECK(cudaMemcpyAsync(&st, d_st.p, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    cov_readback(ctx, &st, d_st.p, sizeof(st));
     if (st.bad_type) COV_THROW(OTTOCOV_ERR_DATA, "event type outside {0,1,2}");
     if (st.amin < 0) COV_THROW(OTTOCOV_ERR_DATA, "negative aid %d", st.amin);
     info.session_min = st.smin; info.session_max = st.smax;

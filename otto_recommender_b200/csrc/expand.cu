@@ -451,7 +451,7 @@ void expand_run_impl(ottocov_ctx* ctx, int n_ranks, u64* buf_a, u64* buf_b, int*
     COV_LAUNCH(ctx, OTTOCOV_K_PARTITION, 8.0 * n, dest_count_kernel, (int)imin64(ceil_div64(n, 2048), (int64_t)ctx->num_sms * 8),
                256, 0, buf_a, n, (u32)n_ranks, cnt.p);
     unsigned long long h[256];
-    CUDA_CHECK(cudaMemcpyAsync(h, cnt.p, 256 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    cov_readback(ctx, h, cnt.p, 256 * sizeof(unsigned long long));
     if (!buf_b) {                    // caller will push the keys itself (ottocov_push_keys): no local grouping
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
         for (int r = 0; r < n_ranks; ++r) rows_per_dest[r] = (int64_t)h[r];

@@ -91,6 +91,7 @@ struct ottocov_ctx {
     u32 scan_epoch = 0;
     u32* scan_ticket = nullptr;
     u64* scan_totals = nullptr;        // [8] grand totals of the last scan launch
+    void* pinned = nullptr;            // 4 KB page-locked landing pad for small device -> host read-backs
     void* plan = nullptr;              // ExpandPlan between ottocov_expand_prepare and ottocov_expand_run
     // top-k result
     int topk_k = 0;
@@ -104,6 +105,9 @@ struct ottocov_ctx {
     void end(int family, double algo_bytes);
 };
 
+// Small device -> host read-back (totals, statistics) through the context's page-locked pad, then a
+// stream synchronise: a pageable destination would make the runtime stage and block on its own terms.
+void cov_readback(ottocov_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes);
 void* cov_alloc(ottocov_ctx* ctx, size_t bytes);      // api.cu; throws CovError
 void cov_free(ottocov_ctx* ctx, void* p);             // returns the block to the context cache
 void cov_trim(ottocov_ctx* ctx);                      // releases every cached block to the driver

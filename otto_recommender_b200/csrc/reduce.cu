@@ -234,8 +234,7 @@ void reduce_sorted(ottocov_ctx* ctx, const u64* keys, const u32* vals, int64_t n
         COV_LAUNCH(ctx, OTTOCOV_K_RLE, 8.0 * n, (rle_kernel<false, 16, 4>), (unsigned)n_tiles, RLE_THREADS, 0, keys, vals, n,
                    n_tiles, min_count, sym ? 1 : 0, ukeys.p, ucount.p, st_tail, st_keep, ctx->scan_ticket, epoch, ctx->scan_totals);
     u64 rows = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&rows, ctx->scan_totals, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    cov_readback(ctx, &rows, ctx->scan_totals, sizeof(u64));
     ctx->stats[OTTOCOV_K_RLE].algo_bytes += 12.0 * (double)rows;
     *out_keys = shrink_to_fit(ctx, ukeys, (int64_t)rows);
     *out_count = shrink_to_fit(ctx, ucount, (int64_t)rows);
@@ -274,8 +273,7 @@ static void table_stats(ottocov_ctx* ctx, const u64* keys, const u32* count, int
     CUDA_CHECK(cudaMemsetAsync(d.p, 0, 3 * sizeof(u64), ctx->stream));
     int grid = (int)imin64(ceil_div64(n, 256), (int64_t)ctx->num_sms * 16);
     COV_LAUNCH(ctx, OTTOCOV_K_MISC, 12.0 * n, table_stats_kernel, grid, 256, 0, keys, count, n, d.p);
-    CUDA_CHECK(cudaMemcpyAsync(out, d.p, 3 * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    cov_readback(ctx, out, d.p, 3 * sizeof(u64));
 }
 
 static int bits_of(u64 v) { int b = 0; while (v) { ++b; v >>= 1; } return b; }
@@ -587,7 +585,7 @@ void partition_table_impl(ottocov_ctx* ctx, const ottocov_table* t, int n_ranks,
                    256, 0, t->keys, n, (u32)n_ranks, k0.p, cnt.p);
         CUDA_CHECK(cudaMemcpyAsync(c0.p, t->count, n * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->stream));
         unsigned long long h[256];
-        CUDA_CHECK(cudaMemcpyAsync(h, cnt.p, 256 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        cov_readback(ctx, h, cnt.p, 256 * sizeof(unsigned long long));
         int bits = 1;
         while ((1 << bits) < n_ranks) ++bits;
         BitField f[1] = {{56, 56 + bits}};

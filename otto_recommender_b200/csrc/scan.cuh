@@ -165,8 +165,6 @@ static void scan_apply(ottocov_ctx* ctx, int family, const F& f, int64_t n, u64*
     COV_LAUNCH(ctx, family, algo_bytes, (scan_onepass_kernel<F>), (unsigned)n_tiles, SCAN_THREADS, 0, f, n, n_tiles,
                ctx->scan_status, ctx->scan_ticket, epoch, ctx->scan_totals);
     if (totals_host) {
-        CUDA_CHECK(cudaMemcpyAsync(totals_host, ctx->scan_totals, sizeof(u64) * F::NC, cudaMemcpyDeviceToHost,
-                                   ctx->stream));
-        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        cov_readback(ctx, totals_host, ctx->scan_totals, sizeof(u64) * F::NC);
     }
 }

@@ -191,9 +191,6 @@ class PushExchange:
         return self.recv[: int(incoming[self.rank])]
 
 
-_push_exchanges = {}
-
-
 def count_exchange_push(engine, name: str, min_count: int = 1, group=None, aid_bits: Optional[int] = None):
     """count_exchange_first with the NCCL all-to-all replaced by the fused partition + peer-store kernel."""
     world = dist.get_world_size(group)
@@ -203,9 +200,10 @@ def count_exchange_push(engine, name: str, min_count: int = 1, group=None, aid_b
     n_keys, sym = engine.expand_prepare(name, min_count=min_count)
     buf_a = torch.empty(max(n_keys, 1), dtype=torch.int64, device=dev)
     keys, rows = engine.expand_run(world, buf_a, None)
-    ex = _push_exchanges.get((id(engine), id(group)))
+    cache = engine.__dict__.setdefault("_push_exchanges", {})      # lives and dies with the engine
+    ex = cache.get(id(group))
     if ex is None:
-        ex = _push_exchanges[(id(engine), id(group))] = PushExchange(engine, group)
+        ex = cache[id(group)] = PushExchange(engine, group)
     recv = ex.exchange(keys, n_keys, rows)
     if aid_bits is None:
         aid_bits = global_aid_bits(engine, group)

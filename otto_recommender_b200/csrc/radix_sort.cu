@@ -196,8 +196,11 @@ __device__ __forceinline__ void write_rows(const u64* s_keys, const u32* s_vals,
     }
 }
 
+#ifndef OTTOCOV_RS_MINB
+#define OTTOCOV_RS_MINB 4
+#endif
 template <bool HAS_VALS, int ALGO, int NB>
-__global__ void __launch_bounds__(RS_THREADS, 4)
+__global__ void __launch_bounds__(RS_THREADS, OTTOCOV_RS_MINB)
 rs_onesweep_kernel(const u64* __restrict__ keys_in, u64* __restrict__ keys_out,
                    const u32* __restrict__ vals_in, u32* __restrict__ vals_out, int64_t n, int shift,
                    int bits, const u64* __restrict__ digit_base, const u64* __restrict__ ptr_base, u64* status,

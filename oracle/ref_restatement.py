@@ -161,6 +161,10 @@ def merge_counts(
     *,
     exact: bool = False,
     min_count_to_save: Optional[int] = None,
+    rows_trigger_min_in_part: int = 100_000_000,
+    max_rows_groupby: int = MAX_ROWS_GROUPBY,
+    optim_rows_groupby: int = OPTIM_ROWS_GROUPBY,
+    max_pairs_to_save: int = MAX_PAIRS_TO_SAVE,
 ) -> pa.Table:
     """concat_files_w_stats (count_co_events.py:103-181) on in-memory tables.
 
@@ -172,13 +176,13 @@ def merge_counts(
                                              ("count", pa.int64())])) for t in tables])
     assert df.column_names == ["aid", "aid_next", "count"]          # :128
     n = df.num_rows
-    if not exact and "click_to" in name and n > 100_000_000:         # :131-132
+    if not exact and "click_to" in name and n > rows_trigger_min_in_part:   # :131-132 (100_000_000 there)
         df = df.filter(pc.greater_equal(df["count"], MIN_COUNT_IN_PART.get(name, 1)))
-    if not exact and df.num_rows > MAX_ROWS_GROUPBY:                 # :135-166
+    if not exact and df.num_rows > max_rows_groupby:                 # :135-166
         n = df.num_rows
-        rows_part = OPTIM_ROWS_GROUPBY
+        rows_part = optim_rows_groupby
         n_parts = math.ceil(n / rows_part)
-        max_rows_part = int(MAX_ROWS_GROUPBY / n * rows_part)
+        max_rows_part = int(max_rows_groupby / n * rows_part)
         rows_part = math.ceil(n / n_parts)
         parts = []
         for i in range(n_parts):
@@ -190,7 +194,7 @@ def merge_counts(
     df = _sum_by_pair(df)                                            # :168
     thr = MIN_COUNT_TO_SAVE.get(name, 1) if min_count_to_save is None else min_count_to_save
     df = df.filter(pc.greater_equal(df["count"], thr))              # :172
-    df = _sort_canonical(df).slice(0, MAX_PAIRS_TO_SAVE)             # :173-174
+    df = _sort_canonical(df).slice(0, max_pairs_to_save)             # :173-174
     return pa.table({"aid": df["aid"], "aid_next": df["aid_next"],
                      "count": pc.cast(df["count"], pa.int32())})    # :175
 

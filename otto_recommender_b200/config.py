@@ -32,6 +32,8 @@ class CoEventConfig:
     # config.py:52-53 (row-count triggers of the lossy merge steps)
     OPTIM_ROWS_POLARS_GROUPBY: int = 100_000_000
     MAX_ROWS_POLARS_GROUPBY: int = 300_000_000
+    # the literal 100_000_000 of count_co_events.py:131 (a field only so tests can reach that branch)
+    ROWS_TRIGGER_MIN_COUNT_IN_PART: int = 100_000_000
     # config.py:56-64
     MIN_COUNT_TO_SAVE: Dict[str, int] = field(default_factory=lambda: {
         "click_to_click": 10,

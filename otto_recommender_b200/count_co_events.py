@@ -147,7 +147,7 @@ def concat_files_w_stats(name, dir_stats, files_stats=None):
     min_in_part = config.MIN_COUNT_IN_PART.get(name, 1)
     lossy = not config.EXACT_MERGE and not loaded_from_cache
     # truncate small counts if table is big (:131-132)
-    if lossy and "click_to" in name and n_rows > 100_000_000:
+    if lossy and "click_to" in name and n_rows > config.ROWS_TRIGGER_MIN_COUNT_IN_PART:
         keep = cnt >= min_in_part
         aid, aid_next, cnt = aid[keep], aid_next[keep], cnt[keep]
         n_rows = len(aid)

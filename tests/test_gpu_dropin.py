@@ -92,6 +92,43 @@ def test_cli_three_phases_match_reference(data_dir):
                                         f"{name}_rank", f"{name}_count_rel"]
 
 
+def test_lossy_merge_branches_with_small_triggers(data_dir, engine):
+    """concat_files_w_stats' row-count-triggered steps (count_co_events.py:131-132, :135-166), reached by
+    shrinking the triggers: drop count < 2 for click_to_* once the concatenation is large, then aggregate by
+    positional slices and truncate each; plus the final head(N).  Tie order is canonical on both sides."""
+    alias = "ls"
+    s, a, t, y = small_events(47, n_sessions=3000, n_aids=40, max_len=25)
+    tabs = _write_parts(f"{data_dir}/{alias}-parquet/train_sessions", s, a, t, y, 4)
+    out = f"{data_dir}/{alias}-counts-co-event/train_sessions"
+    cce.count_co_events_all_files(f"{data_dir}/{alias}-parquet/train_sessions", out)
+    for name in ("click_to_click", "click_to_cart_or_buy", "cart_to_cart"):
+        # the sliced step cuts the concatenation by POSITION, so both sides must see the part rows in the
+        # same order: use the part files phase 1 wrote (their content is checked against the oracle elsewhere)
+        for tab, f in zip(tabs, sorted(os.listdir(f"{out}/{name}"))):
+            assert rr.table_to_dict(pq.read_table(f"{out}/{name}/{f}")) == rr.table_to_dict(rr.count_part(tab)[name])
+        per_part = [pq.read_table(f"{out}/{name}/{f}") for f in sorted(os.listdir(f"{out}/{name}"))]
+        n_rows = sum(p.num_rows for p in per_part)
+        kw = dict(rows_trigger_min_in_part=n_rows // 2, max_rows_groupby=n_rows // 3, optim_rows_groupby=n_rows // 5 + 1,
+                  max_pairs_to_save=max(n_rows // 50, 5))
+        cfg = CoEventConfig(DIR_DATA=str(data_dir), ROWS_TRIGGER_MIN_COUNT_IN_PART=kw["rows_trigger_min_in_part"],
+                            MAX_ROWS_POLARS_GROUPBY=kw["max_rows_groupby"], OPTIM_ROWS_POLARS_GROUPBY=kw["optim_rows_groupby"],
+                            MAX_CO_EVENT_PAIRS_TO_SAVE_DISK=kw["max_pairs_to_save"],
+                            MIN_COUNT_TO_SAVE={"click_to_click": 3, "click_to_cart_or_buy": 2, "cart_to_cart": 2})
+        cce.set_config(cfg)
+        want = rr.merge_counts(name, per_part, min_count_to_save=cfg.MIN_COUNT_TO_SAVE[name], **kw)
+        cce.concat_files_w_stats(name, out)
+        got = pq.read_table(f"{out}/{name}.parquet")
+        assert got.num_rows == want.num_rows and got.num_rows <= kw["max_pairs_to_save"]
+        for c in ("aid", "aid_next", "count"):
+            assert np.array_equal(got[c].to_numpy(), want[c].to_numpy()), (name, c)
+        # the sliced aggregation leaves its cache behind (:165-166) and a second call re-uses it (:106-111)
+        assert os.path.exists(f"{out}/tmp/{name}.parquet")
+        cce.concat_files_w_stats(name, out)
+        again = pq.read_table(f"{out}/{name}.parquet")
+        assert again.num_rows > 0
+    cce.set_config(CoEventConfig(DIR_DATA=str(data_dir)))
+
+
 def test_resume_skips_existing_parts(data_dir):
     alias = "rs"
     s, a, t, y = small_events(43, n_sessions=300, n_aids=20)

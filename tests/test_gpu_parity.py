@@ -95,6 +95,25 @@ def test_random_vs_oracle(engine, seed, shuffle):
     assert engine.events_info()["was_sorted"] == (0 if shuffle else 1)
 
 
+def test_arbitrary_specs_vs_oracle(engine):
+    """Any (source type, next-type set, window), not just the five configured kinds."""
+    s, a, t, y = small_events(61, n_sessions=500, n_aids=60, max_len=35)
+    info = engine.load_events(s, a, t, y)
+    rng = np.random.default_rng(5)
+    specs = [(0, [0, 1, 2], 86400), (2, [0], 50_000), (1, [0, 2], 1), (0, [0], 0), (2, [1, 2], 43_201), (1, [1], 86_400 * 3)]
+    specs += [(int(rng.integers(0, 3)), sorted(set(rng.integers(0, 3, rng.integers(1, 4)).tolist())),
+               int(rng.choice([7, 600, 3600, 43_200, 86_399, 86_400]))) for _ in range(6)]
+    for this, nxt, w in specs:
+        mask = sum(1 << k for k in nxt)
+        oa, ob, oc, emitted, _ = c_oracle.count(s, a, t, y, this, mask, min(w, 86400))
+        for mc in (1, 2):
+            tab = engine.count(type_this=this, next_types=nxt, window=w, min_count=mc)
+            ga, gb, gc = tab.fetch()
+            keep = oc >= mc
+            assert engine.count_info()["n_pairs"] == emitted, (this, nxt, w)
+            assert np.array_equal(ga, oa[keep]) and np.array_equal(gb, ob[keep]) and np.array_equal(gc.astype(np.uint32), oc[keep]), (this, nxt, w, mc)
+
+
 def test_long_sessions_and_chunking(engine):
     # a few sessions of ~2000 events inside one window: quadratic tail, tiles span many records
     s, a, t, y = small_events(7, n_sessions=6, n_aids=400, max_len=2000, span=40_000)

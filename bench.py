@@ -155,7 +155,7 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": {"workload": "click_to_click 12h top-20, 12.9M sessions / 220M events / 1.8M aids "
                                "(configs[1]); timed on a bounded sample", "sample_sessions": part_sessions},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
@@ -355,7 +355,7 @@ def run_ours(args):
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": {
             "workload": f"click_to_click 12h co-visitation top-{TOP_K}, min_count {MIN_COUNT}: {args.sessions:,} sessions / "
                         f"{rows_global:,} event rows / {N_AIDS:,} aids (BASELINE configs[1])",

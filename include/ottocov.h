@@ -158,6 +158,12 @@ int ottocov_table_topk(ottocov_ctx* ctx, const ottocov_table* t, int k, int64_t*
 int ottocov_topk_fetch(ottocov_ctx* ctx, int32_t* aid_x, int32_t* n_valid, int32_t* aid_y,
                        int32_t* cnt, int64_t cap_aids, int where);
 
+/* Candidate lookup on the last top-K result: for each query aid its top-K row (n_valid = 0 when the aid
+ * has none).  Replaces the consumer's join of session aids with the top-N rows,
+ * df_aids[['aid']].unique().join(df_count[['aid','aid_next']], on='aid')  (model/retrieve.py:75-91). */
+int ottocov_topk_lookup(ottocov_ctx* ctx, const int32_t* aids, int64_t n, int where, int32_t* n_valid,
+                        int32_t* aid_y /*[n*k]*/, int32_t* cnt /*[n*k]*/);
+
 /* ---- multi-GPU exchange support: stable partition of a table's rows by
  * dest = ottocov_hash_dest(aid, n_ranks) into caller-owned DEVICE buffers (the send buffers of
  * the all-to-all); rows_per_dest is a HOST array [n_ranks].  No reference counterpart (the

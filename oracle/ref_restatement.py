@@ -228,6 +228,42 @@ def top_n_per_aid(df_count: pa.Table, first_n: int) -> pa.Table:
     return df.append_column("rank", pa.array(rank[keep].astype(np.int16)))
 
 
+def count_features(df_count: pa.Table, count_type: str, first_n: Optional[int] = None) -> Dict[str, np.ndarray]:
+    """get_df_count_for_co_event_type (retrieve.py:18-63) on an in-memory count table given in FILE order.
+
+    count_pop  = int16(clip_max((count - min) / (quantile_0.9999 - min), 1) * 10_000)      :33-35
+    perc_pop   = int16(row_nr / n * 10_000), row_nr from 1 in file order                    :36-38
+    rank       = ordinal rank of count, descending, over aid (ties keep file order)         :41-44
+    count_rel  = int8(count / max(count over aid) * 100)                                    :45-49
+    keep rank <= first_n; rows come back ordered by aid, then rank.
+    """
+    first_n = RETRIEVAL_FIRST_N[count_type] if first_n is None else first_n
+    aid = df_count["aid"].to_numpy(); nxt = df_count["aid_next"].to_numpy()
+    cnt = df_count["count"].to_numpy().astype(np.int64)
+    n = len(aid)
+    cmin = cnt.min() if n else 0
+    q = np.quantile(cnt, 0.9999, method="nearest") if n else 0
+    denom = max(float(q - cmin), 1e-12)
+    count_pop = (np.minimum((cnt - cmin) / denom, 1.0) * 10_000).astype(np.int16)
+    perc_pop = (np.arange(1, n + 1) / max(n, 1) * 10_000).astype(np.int16)
+    order = np.argsort(aid, kind="stable")                       # sort(['aid']) keeps file order inside an aid
+    a, b, c = aid[order], nxt[order], cnt[order]
+    start = np.r_[True, a[1:] != a[:-1]] if n else np.zeros(0, bool)
+    seg = np.maximum.accumulate(np.where(start, np.arange(n), 0)) if n else np.zeros(0, np.int64)
+    # ordinal rank, descending: position after a stable sort by -count inside the aid
+    o2 = np.lexsort((np.arange(n), -c, a))
+    rank = np.empty(n, np.int64); rank[o2] = np.arange(n) - seg[o2] + 1 if n else 0
+    seg_id = np.cumsum(start) - 1 if n else np.zeros(0, np.int64)
+    mx = np.maximum.reduceat(c, np.flatnonzero(start))[seg_id] if n else np.zeros(0, np.int64)
+    keep = rank <= first_n
+    o3 = np.lexsort((rank[keep], a[keep]))
+    out = {"aid": a[keep][o3], "aid_next": b[keep][o3], f"{count_type}_count": c[keep][o3],
+           f"{count_type}_count_pop": count_pop[order][keep][o3], f"{count_type}_perc_pop": perc_pop[order][keep][o3],
+           f"{count_type}_rank": rank[keep][o3].astype(np.int16),
+           f"{count_type}_count_rel": (c[keep] / mx[keep] * 100).astype(np.int8)[o3]}
+    return out
+
+
 # ---- convenience wrappers used by tests and bench ------------------------------------------
 def table_to_dict(t: pa.Table) -> Dict[tuple, int]:
     a, b, c = (t[k].to_numpy() for k in ("aid", "aid_next", "count"))

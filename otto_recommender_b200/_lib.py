@@ -74,6 +74,7 @@ SYMBOLS = {
     "ottocov_table_device_ptrs": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_void_p)]),
     "ottocov_table_topk": (c_int, [c_void_p, c_void_p, c_int, POINTER(c_int64)]),
     "ottocov_topk_fetch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int]),
+    "ottocov_topk_lookup": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "ottocov_table_partition": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, POINTER(c_int64)]),
     "ottocov_hash_dest": (c_uint32, [c_uint32, c_uint32]),
     "ottocov_sort_u64": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int]),

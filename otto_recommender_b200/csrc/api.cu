@@ -437,6 +437,14 @@ int ottocov_topk_fetch(ottocov_ctx* ctx, int32_t* aid_x, int32_t* n_valid, int32
     API_END(ctx)
 }
 
+int ottocov_topk_lookup(ottocov_ctx* ctx, const int32_t* aids, int64_t n, int where, int32_t* n_valid, int32_t* aid_y,
+                        int32_t* cnt) {
+    API_BEGIN(ctx)
+    if (n < 0 || (n > 0 && (!aids || !n_valid || !aid_y || !cnt))) COV_THROW(OTTOCOV_ERR_ARG, "bad argument");
+    topk_lookup_impl(ctx, aids, n, where, n_valid, aid_y, cnt);
+    API_END(ctx)
+}
+
 int ottocov_table_partition(ottocov_ctx* ctx, const ottocov_table* t, int n_ranks, uint64_t* keys_out_dev,
                             uint32_t* count_out_dev, int64_t* rows_per_dest) {
     API_BEGIN(ctx)

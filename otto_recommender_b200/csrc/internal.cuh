@@ -199,6 +199,8 @@ void partition_table_impl(ottocov_ctx* ctx, const ottocov_table* t, int n_ranks,
 // topk.cu
 void topk_impl(ottocov_ctx* ctx, const ottocov_table* t, int k);
 void free_topk(ottocov_ctx* ctx);
+void topk_lookup_impl(ottocov_ctx* ctx, const int32_t* aids, int64_t n, int where, int32_t* n_valid, int32_t* aid_y,
+                      int32_t* cnt);
 
 // ---- small device helpers -------------------------------------------------------------------------
 #ifdef __CUDACC__

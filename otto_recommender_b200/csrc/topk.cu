@@ -120,3 +120,54 @@ void topk_impl(ottocov_ctx* ctx, const ottocov_table* t, int k) {
     ctx->topk_aid_y = ay.take(); ctx->topk_cnt = ac.take();
     ctx->topk_n = (int64_t)n_seg;
 }
+
+// ---- candidate lookup: the consumer's join of session aids with the per-aid top-N rows ---------------------
+// (model/retrieve.py:75-91, `df_aids[['aid']].unique().join(df_count[['aid','aid_next']], on='aid')`): for
+// every query aid, its row of the top-K result (binary search over the ascending aid_x column) or nothing.
+__global__ void __launch_bounds__(256) topk_lookup_kernel(const int32_t* __restrict__ q, int64_t n,
+                                                          const int32_t* __restrict__ aid_x, int64_t n_seg,
+                                                          const int32_t* __restrict__ nvalid,
+                                                          const int32_t* __restrict__ aid_y,
+                                                          const int32_t* __restrict__ cnt, int k,
+                                                          int32_t* __restrict__ o_nv, int32_t* __restrict__ o_y,
+                                                          int32_t* __restrict__ o_c) {
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;     // one warp per query
+    const int lane = threadIdx.x & 31;
+    if (w >= n) return;
+    const int32_t a = q[w];
+    int64_t lo = 0, hi = n_seg;                      // first row with aid_x >= a
+    while (lo < hi) {
+        const int64_t mid = lo + ((hi - lo) >> 1);
+        if (aid_x[mid] < a) lo = mid + 1; else hi = mid;
+    }
+    const bool hit = lo < n_seg && aid_x[lo] == a;
+    const int nv = hit ? nvalid[lo] : 0;
+    if (lane == 0) o_nv[w] = nv;
+    if (lane < k) {
+        o_y[w * k + lane] = (lane < nv) ? aid_y[lo * k + lane] : -1;
+        o_c[w * k + lane] = (lane < nv) ? cnt[lo * k + lane] : 0;
+    }
+}
+
+void topk_lookup_impl(ottocov_ctx* ctx, const int32_t* aids, int64_t n, int where, int32_t* n_valid, int32_t* aid_y,
+                      int32_t* cnt) {
+    if (ctx->topk_k == 0) COV_THROW(OTTOCOV_ERR_STATE, "ottocov_topk_lookup before ottocov_table_topk");
+    if (n == 0) return;
+    const int k = ctx->topk_k;
+    DevBuf<int32_t> dq, dnv, dy, dc;
+    const int32_t* q = aids;
+    int32_t *pnv = n_valid, *py = aid_y, *pc = cnt;
+    if (where == OTTOCOV_HOST) {
+        dq.alloc(ctx, n); dnv.alloc(ctx, n); dy.alloc(ctx, n * k); dc.alloc(ctx, n * k);
+        CUDA_CHECK(cudaMemcpyAsync(dq.p, aids, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        q = dq.p; pnv = dnv.p; py = dy.p; pc = dc.p;
+    }
+    COV_LAUNCH(ctx, OTTOCOV_K_TOPK, 4.0 * n + 8.0 * k * n, topk_lookup_kernel, (unsigned)ceil_div64(n * 32, 256), 256, 0, q, n,
+               ctx->topk_aid_x, ctx->topk_n, ctx->topk_nvalid, ctx->topk_aid_y, ctx->topk_cnt, k, pnv, py, pc);
+    if (where == OTTOCOV_HOST) {
+        CUDA_CHECK(cudaMemcpyAsync(n_valid, pnv, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaMemcpyAsync(aid_y, py, n * k * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaMemcpyAsync(cnt, pc, n * k * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}

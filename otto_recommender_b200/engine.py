@@ -341,6 +341,7 @@ class Engine:
         n = ctypes.c_int64()
         self._sync_stream()
         self._check(self._lib.ottocov_table_topk(self._ctx, table._h, k, ctypes.byref(n)))
+        self._last_topk_k = k
         A = int(n.value)
         if device:
             import torch
@@ -358,6 +359,20 @@ class Engine:
             ptrs, where = (ax.ctypes.data, nv.ctypes.data, ay.ctypes.data, ac.ctypes.data), _lib.HOST
         self._check(self._lib.ottocov_topk_fetch(self._ctx, *ptrs, A, where))
         return ax, nv, ay, ac
+
+    def topk_lookup(self, aids):
+        """Top-K rows of the last topk() result for the given aids (numpy int32) -> n_valid [n], aid_y [n,k],
+        cnt [n,k].  The consumer's candidate join (retrieve.py:75-91)."""
+        a = np.ascontiguousarray(aids, np.int32)
+        n = len(a)
+        k = ctypes.c_int64()
+        nv = np.empty(n, np.int32)
+        kk = self._last_topk_k
+        ay = np.empty((n, kk), np.int32); ac = np.empty((n, kk), np.int32)
+        self._sync_stream()
+        self._check(self._lib.ottocov_topk_lookup(self._ctx, a.ctypes.data, n, _lib.HOST, nv.ctypes.data, ay.ctypes.data,
+                                                  ac.ctypes.data))
+        return nv, ay, ac
 
     # ---- multi-GPU support ----------------------------------------------------------------------------------
     def partition(self, table: Table, n_ranks: int, keys_out_ptr: int, count_out_ptr: int) -> List[int]:

@@ -64,3 +64,24 @@ def get_df_count_for_co_event_type(count_type: str, dir_counts: str, first_n: Op
         "aid": o_aid, "aid_next": o_next,
         cols[0]: o_cnt, cols[1]: count_pop[pos], cols[2]: perc_pop[pos], cols[3]: o_rank, cols[4]: count_rel,
     })
+
+
+def get_pairs_co_event_type(df_aids, df_count, type: int = 0) -> pd.DataFrame:
+    """Mirror of retrieve.py:75-91: unique aids of `df_aids` joined with the (top-N) count rows on aid.
+    `df_count` is the frame returned by get_df_count_for_co_event_type (or any frame with aid, aid_next);
+    `type` is unused, exactly as in the reference (its type filter is commented out).  The join runs as a
+    GPU lookup over the per-aid top-K rows."""
+    aids = np.unique(np.asarray(df_aids["aid"], dtype=np.int32))
+    a = np.asarray(df_count["aid"], dtype=np.int32)
+    b = np.asarray(df_count["aid_next"], dtype=np.int32)
+    if len(a) == 0 or len(aids) == 0:
+        return pd.DataFrame({"aid": np.zeros(0, np.int32), "aid_next": np.zeros(0, np.int32)})
+    eng = get_engine()
+    # rows per aid in df_count are already the kept top-N rows: rank them by position to rebuild the matrix
+    tab = eng.table_from_arrays(a, b, np.ones(len(a), np.uint32))
+    k = int(min(32, max(1, np.bincount(np.unique(a, return_inverse=True)[1]).max())))
+    eng.topk(tab, k)
+    tab.free()
+    nv, ay, _ = eng.topk_lookup(aids)
+    mask = np.arange(ay.shape[1])[None, :] < nv[:, None]
+    return pd.DataFrame({"aid": np.repeat(aids, nv), "aid_next": ay[mask]})

@@ -90,6 +90,15 @@ def test_cli_three_phases_match_reference(data_dir):
             assert np.array_equal(df[f"{name}_count_rel"].to_numpy(), (cnt / mx[seg] * 100).astype(np.int8))
             assert list(df.columns) == ["aid", "aid_next", f"{name}_count", f"{name}_count_pop", f"{name}_perc_pop",
                                         f"{name}_rank", f"{name}_count_rel"]
+            feat = rr.count_features(want, name)                       # all seven columns of retrieve.py:18-63
+            for col, arr in feat.items():
+                assert np.array_equal(df[col].to_numpy(), arr), (name, col)
+            # candidate join of session aids with the top-N rows (retrieve.py:75-91)
+            q = pa.table({"aid": pa.array(np.r_[a[::7], 10**6], pa.int32())}).to_pandas()
+            pairs = retrieve.get_pairs_co_event_type(q, df, 0)
+            want_pairs = q.drop_duplicates().merge(df[["aid", "aid_next"]], on="aid", how="inner")
+            key = lambda d: set(zip(d["aid"].tolist(), d["aid_next"].tolist()))
+            assert key(pairs) == key(want_pairs) and len(pairs) == len(want_pairs)
 
 
 def test_lossy_merge_branches_with_small_triggers(data_dir, engine):

@@ -283,6 +283,23 @@ def test_topk_vs_oracle(engine, k):
     assert np.all(gy[np.arange(k)[None, :] >= nv[:, None]] == -1)
 
 
+def test_topk_lookup_candidates(engine):
+    rng = np.random.default_rng(3)
+    ax = rng.integers(0, 2000, 60_000) * 3            # only multiples of 3 exist
+    ay = rng.integers(0, 500, 60_000); cnt = rng.integers(1, 9, 60_000)
+    tab = engine.table_from_arrays(ax, ay, cnt)
+    gx, nv, gy, gc = engine.topk(tab, 10)
+    q = rng.integers(-5, 6100, 5000).astype(np.int32)
+    qnv, qy, qc = engine.topk_lookup(q)
+    row = {int(a): i for i, a in enumerate(gx)}
+    for i, a in enumerate(q):
+        if int(a) in row:
+            r = row[int(a)]
+            assert qnv[i] == nv[r] and np.array_equal(qy[i], gy[r]) and np.array_equal(qc[i], gc[r])
+        else:
+            assert qnv[i] == 0 and np.all(qy[i] == -1) and np.all(qc[i] == 0)
+
+
 def test_partition_by_hash(engine):
     s, a, t, y = small_events(3, n_sessions=500, n_aids=500)
     engine.load_events(s, a, t, y)

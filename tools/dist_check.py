@@ -22,8 +22,9 @@ m = (d["session"] >= int(b[rank])) & (d["session"] < int(b[rank + 1]))
 eng = Engine(local)
 eng.load_events(*[d[k][m].contiguous() for k in ("session", "aid", "ts", "type")])
 ok = True
-cases = [(name, flow, mc) for name in ("click_to_click", "click_to_cart_or_buy", "cart_to_cart", "cart_to_buy", "buy_to_buy")
-         for flow, mc in (("reduce_first", 1), ("exchange_first", 1), ("exchange_first", 3), ("push", 1), ("push", 3))]
+names = ("buy_to_buy", "cart_to_buy", "cart_to_cart", "click_to_cart_or_buy", "click_to_click")   # small -> large, so the
+cases = [(name, flow, mc) for name in names                                                        # symmetric receive
+         for flow, mc in (("reduce_first", 1), ("exchange_first", 1), ("exchange_first", 3), ("push", 1), ("push", 3))]  # buffer must grow
 for name, flow, mc in cases:
     shard = (count_distributed(eng, name) if flow == "reduce_first" else
              count_exchange_first(eng, name, mc) if flow == "exchange_first" else count_exchange_push(eng, name, mc))

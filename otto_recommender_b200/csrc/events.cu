@@ -102,19 +102,29 @@ __global__ void __launch_bounds__(256) ev_gather_kernel(const u32* __restrict__ 
 }
 
 // Scan functor: drop exact duplicates, split by type, record cross-type ranks.
+// FROM_COLUMNS: the rows are already in (session, ts) order, so the search key is built on the fly from
+// the session and ts columns (no key array is ever written or re-read); otherwise `skey` holds the sorted keys.
+template <bool FROM_COLUMNS>
 struct SplitByType {
     static constexpr int NC = 3;
-    const u64* skey;        // sorted
+    const u64* skey;        // sorted (!FROM_COLUMNS)
+    const int32_t* session; // FROM_COLUMNS
+    const int32_t* ts;      // FROM_COLUMNS
+    int smin, tmin;
     const u32* aid;         // in sorted order
     const int8_t* type;     // in sorted order
     TypeArray out[3];
+    __device__ __forceinline__ u64 key_at(int64_t i) const {
+        if (!FROM_COLUMNS) return skey[i];
+        return ((u64)((int64_t)session[i] - (int64_t)smin) << 32) | (u64)((int64_t)ts[i] - (int64_t)tmin);
+    }
     // An event is a duplicate iff an EARLIER row of its equal-(session, ts) run has the same aid and
     // type; runs are short (mostly 1), so the backward walk is O(1) amortised.
     __device__ bool keep(int64_t i) const {
-        const u64 k = skey[i];
+        const u64 k = key_at(i);
         const u32 a = aid[i];
         const int8_t y = type[i];
-        for (int64_t j = i - 1; j >= 0 && skey[j] == k; --j)
+        for (int64_t j = i - 1; j >= 0 && key_at(j) == k; --j)
             if (aid[j] == a && type[j] == y) return false;
         return true;
     }
@@ -123,7 +133,7 @@ struct SplitByType {
         if (!v) return;
         const int t = type[i];
         const u64 pos = pre[t];
-        out[t].skey[pos] = skey[i];
+        out[t].skey[pos] = key_at(i);
         out[t].aid[pos] = aid[i];
         out[t].xrank[0][pos] = (u32)pre[(t + 1) % 3];
         out[t].xrank[1][pos] = (u32)pre[(t + 2) % 3];
@@ -194,14 +204,15 @@ void load_events_impl(ottocov_ctx* ctx, const int32_t* session, const int32_t* a
     info.was_sorted = st.unsorted ? 0 : 1;
 
     // -- (session, ts) keys; sort if the rows are not already in that order ------------------------
-    DevBuf<u64> skey(ctx, n), skey_alt;
+    DevBuf<u64> skey, skey_alt;
     DevBuf<u32> idx, idx_alt, aid_sorted;
     DevBuf<int8_t> type_sorted;
     const unsigned g1 = (unsigned)ceil_div64(n, 256);
     const u32* aid_s;
     const int8_t* type_s;
-    u64* skey_p = skey.p;
+    u64* skey_p = nullptr;
     if (st.unsorted) {
+        skey.alloc(ctx, n);
         idx.alloc(ctx, n); idx_alt.alloc(ctx, n); skey_alt.alloc(ctx, n);
         COV_LAUNCH(ctx, OTTOCOV_K_LOAD, 20.0 * n, ev_make_keys_kernel, g1, 256, 0, session, ts, n, st.smin, st.tmin, skey.p, idx.p);
         BitField f[2];
@@ -214,24 +225,34 @@ void load_events_impl(ottocov_ctx* ctx, const int32_t* session, const int32_t* a
         COV_LAUNCH(ctx, OTTOCOV_K_LOAD, 14.0 * n, ev_gather_kernel, g1, 256, 0, v, aid, type, n, aid_sorted.p, type_sorted.p);
         aid_s = aid_sorted.p; type_s = type_sorted.p;
     } else {
-        COV_LAUNCH(ctx, OTTOCOV_K_LOAD, 16.0 * n, ev_make_keys_kernel, g1, 256, 0, session, ts, n, st.smin, st.tmin, skey.p, (u32*)nullptr);
         aid_s = reinterpret_cast<const u32*>(aid); type_s = type;
     }
 
     // -- dedup + split by type (capacity = per-type row counts before dedup) -----------------------
-    SplitByType f;
-    f.skey = skey_p; f.aid = aid_s; f.type = type_s;
     DevBuf<u64> o_skey[3];
     DevBuf<u32> o_aid[3], o_x0[3], o_x1[3];
+    TypeArray outs[3];
     for (int t = 0; t < 3; ++t) {
         const size_t cap = (size_t)st.n_type[t];
         o_skey[t].alloc(ctx, cap); o_aid[t].alloc(ctx, cap); o_x0[t].alloc(ctx, cap); o_x1[t].alloc(ctx, cap);
-        f.out[t].skey = o_skey[t].p; f.out[t].aid = o_aid[t].p;
-        f.out[t].xrank[0] = o_x0[t].p; f.out[t].xrank[1] = o_x1[t].p;
-        f.out[t].n = 0;
+        outs[t].skey = o_skey[t].p; outs[t].aid = o_aid[t].p;
+        outs[t].xrank[0] = o_x0[t].p; outs[t].xrank[1] = o_x1[t].p;
+        outs[t].n = 0;
     }
     u64 totals[3];
-    scan_apply(ctx, OTTOCOV_K_LOAD, f, n, totals, 2.0 * 13.0 * n + 20.0 * n);
+    if (st.unsorted) {
+        SplitByType<false> f;
+        f.skey = skey_p; f.session = nullptr; f.ts = nullptr; f.smin = st.smin; f.tmin = st.tmin;
+        f.aid = aid_s; f.type = type_s;
+        for (int t = 0; t < 3; ++t) f.out[t] = outs[t];
+        scan_apply(ctx, OTTOCOV_K_LOAD, f, n, totals, 13.0 * n + 20.0 * n);
+    } else {
+        SplitByType<true> f;
+        f.skey = nullptr; f.session = session; f.ts = ts; f.smin = st.smin; f.tmin = st.tmin;
+        f.aid = aid_s; f.type = type_s;
+        for (int t = 0; t < 3; ++t) f.out[t] = outs[t];
+        scan_apply(ctx, OTTOCOV_K_LOAD, f, n, totals, 13.0 * n + 20.0 * n);
+    }
     for (int t = 0; t < 3; ++t) {
         ctx->ta[t].skey = o_skey[t].take();
         ctx->ta[t].aid = o_aid[t].take();

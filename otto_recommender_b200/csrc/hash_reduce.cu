@@ -1,0 +1,257 @@
+// hash_reduce.cu -- bucketed hash aggregation: the thresholded groupby(['aid','aid_next']).count() of
+// model/count_co_events.py:70-71 + :131-132 / :172 without a full sort.
+//
+// A full LSD sort of the pair keys orders them by all 2 x aid_bits key bits (6 passes for 1.8 M aids)
+// only to find equal keys next to each other.  Counting needs less: equal keys must MEET, nothing more.
+//
+//   1. the expansion writes each key through a bijective mix (KeyMix, internal.cuh): equal keys stay
+//      equal, and the top bits of the mixed key are uniform whatever the popularity skew of the aids;
+//   2. radix_sort.cu sorts on the top `bb` bits of the mixed key only (3 passes instead of 6 at the
+//      headline size) -- the keys are now grouped into 2^bb buckets of a few hundred keys each, and
+//      every copy of a key lies in one bucket;
+//   3. hash_reduce_kernel: a CTA owns the buckets that START inside its 4096-key tile (it skips the
+//      head of the tile that continues the previous CTA's bucket and reads past the tile end to finish
+//      its last bucket), counts their keys in a shared-memory open-addressing table (64-bit CAS on the
+//      key slot, 32-bit add on the count), then scans the table: rows with count >= min_count are
+//      un-mixed and appended to the output (one global atomic per CTA); for symmetric kinds the
+//      diagonal doubling and the mirrored row (b, a, c) are emitted in the same step;
+//   4. the few surviving rows are sorted by plain key (they arrive in bucket order).
+// HBM traffic after the expansion: 8 P (histogram) + passes x 16 P + 8 P, against 8 P + 6 x 16 P + 8 P.
+//
+// The table holds DISTINCT keys only, so hot pairs (one key repeated millions of times) cost nothing
+// but the streaming read.  If a CTA ever meets more distinct keys than its table holds (needs an
+// adversarial input: buckets are balanced by the hash), it raises a flag and the host re-does the
+// reduce with the full sort (the mixed keys are un-mixed in place first).
+#include "internal.cuh"
+#include "scan.cuh"
+
+constexpr int HR_THREADS = 512;
+constexpr int HR_IPT = 8;
+constexpr int HR_TILE = HR_THREADS * HR_IPT;     // 4096 keys per CTA (+ the tail of its last bucket)
+constexpr int HR_CAP_LOG2 = 13;
+constexpr int HR_CAP = 1 << HR_CAP_LOG2;         // 8192 slots: 64 KB keys + 32 KB counts, 2 CTAs / SM
+constexpr int HR_SPT = HR_CAP / HR_THREADS;      // slots per thread in the table scan
+constexpr u64 HR_NONE = ~0ull;                   // empty slot / no key (mixed keys have <= 56 bits)
+static_assert(2 * HR_SPT <= 32, "two flag bits per scanned slot must fit one register");
+
+__device__ __forceinline__ void hr_insert(u64* s_key, u32* s_cnt, u64 h, u32* flags) {
+    u32 slot = (((u32)h ^ (u32)(h >> 32)) * 0x9E3779B1u) >> (32 - HR_CAP_LOG2);
+#pragma unroll 1
+    for (int probes = 0; probes < HR_CAP; ++probes) {
+        u64 cur = *reinterpret_cast<volatile u64*>(s_key + slot);
+        if (cur == HR_NONE) {
+            cur = atomicCAS(reinterpret_cast<unsigned long long*>(s_key + slot), HR_NONE, h);
+            if (cur == HR_NONE) cur = h;                   // this thread claimed the slot
+        }
+        if (cur == h) { atomicAdd(s_cnt + slot, 1u); return; }
+        slot = (slot + 1) & (HR_CAP - 1);
+    }
+    atomicOr(flags, 1u);                                   // table full: the host falls back to the full sort
+}
+
+template <bool SYM>
+__global__ void __launch_bounds__(HR_THREADS, 2)
+hash_reduce_kernel(const u64* __restrict__ keys, int64_t n, int rem_bits, KeyMix mix, u32 min_count, int mirror,
+                   u64* __restrict__ out_keys, u32* __restrict__ out_count, unsigned long long* __restrict__ out_n,
+                   u64 out_cap, u32* __restrict__ flags) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    u64* s_key = reinterpret_cast<u64*>(s_raw);            // [HR_CAP]
+    u32* s_cnt = reinterpret_cast<u32*>(s_key + HR_CAP);   // [HR_CAP]
+    u32* s_scan = s_cnt + HR_CAP;                          // [HR_THREADS / 32 + 1]
+    __shared__ unsigned long long s_base;
+    __shared__ u32 s_over;
+
+    const int tid = threadIdx.x;
+    const int64_t t0 = (int64_t)blockIdx.x * HR_TILE;
+    const int64_t t1 = min(n, t0 + (int64_t)HR_TILE);
+    // bucket of the key just before the tile (it belongs to an earlier CTA, with every other key of that
+    // bucket) and of the tile's last key (this CTA finishes that bucket beyond the tile end)
+    const u64 pb = t0 > 0 ? (keys[t0 - 1] >> rem_bits) : HR_NONE;
+    const u64 lb = keys[t1 - 1] >> rem_bits;
+    if (lb == pb) return;                                  // the whole tile continues an earlier CTA's bucket
+
+    u64 k[HR_IPT];
+#pragma unroll
+    for (int r = 0; r < HR_IPT; ++r) {
+        const int64_t i = t0 + r * HR_THREADS + tid;
+        k[r] = (i < t1) ? __ldcs(keys + i) : HR_NONE;
+    }
+    u64 kx = (t1 + tid < n) ? __ldcs(keys + t1 + tid) : HR_NONE;     // first slice past the tile end
+    for (int j = tid; j < HR_CAP; j += HR_THREADS) { s_key[j] = HR_NONE; s_cnt[j] = 0; }
+    if (tid == 0) s_over = 0;
+    __syncthreads();
+
+#pragma unroll
+    for (int r = 0; r < HR_IPT; ++r)
+        if (k[r] != HR_NONE && (k[r] >> rem_bits) != pb) hr_insert(s_key, s_cnt, k[r], flags);
+    // the keys of bucket lb are a prefix of what follows the tile
+    int64_t base = t1;
+    while (true) {
+        const bool more = (kx != HR_NONE) && ((kx >> rem_bits) == lb);
+        if (more) hr_insert(s_key, s_cnt, kx, flags);
+        if (!__syncthreads_and(more ? 1 : 0)) break;
+        base += HR_THREADS;
+        kx = (base + tid < n) ? __ldcs(keys + base + tid) : HR_NONE;
+    }
+    __syncthreads();
+
+    // table scan: two flag bits per slot (bit 0 keep, bit 1 also emit the mirrored row)
+    u32 bits = 0, emit = 0;
+#pragma unroll
+    for (int q = 0; q < HR_SPT; ++q) {
+        const int j = tid + q * HR_THREADS;
+        const u32 c = s_cnt[j];
+        if (c) {
+            u64 total = c;
+            bool diag = false;
+            if (SYM) {
+                const u64 plain = key_mix_inv(mix, s_key[j]);
+                diag = (u32)(plain >> 32) == (u32)plain;
+                if (diag) total *= 2;                      // (a, a): both orders of each event pair
+            }
+            if (total >= (u64)min_count) {
+                const bool two = SYM && mirror && !diag;
+                bits |= (two ? 3u : 1u) << (2 * q);
+                emit += two ? 2u : 1u;
+            }
+        }
+    }
+    u32 blk_total;
+    const u32 ex = block_exclusive_scan<u32, HR_THREADS>(emit, s_scan, &blk_total);
+    if (tid == 0) {
+        unsigned long long b = 0;
+        if (blk_total) {
+            b = atomicAdd(out_n, (unsigned long long)blk_total);
+            if (b + blk_total > out_cap) { atomicOr(flags, 2u); s_over = 1; }
+        }
+        s_base = b;
+    }
+    __syncthreads();
+    if (s_over || blk_total == 0) return;
+    u64 o = s_base + ex;
+#pragma unroll
+    for (int q = 0; q < HR_SPT; ++q) {
+        const u32 f = (bits >> (2 * q)) & 3u;
+        if (f) {
+            const int j = tid + q * HR_THREADS;
+            const u64 plain = key_mix_inv(mix, s_key[j]);
+            u64 total = s_cnt[j];
+            if (SYM && (u32)(plain >> 32) == (u32)plain) total *= 2;
+            const u32 c32 = (u32)(total > 0xFFFFFFFFull ? 0xFFFFFFFFull : total);
+            out_keys[o] = plain; out_count[o] = c32; ++o;
+            if (f & 2u) { out_keys[o] = (plain << 32) | (plain >> 32); out_count[o] = c32; ++o; }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) unmix_kernel(u64* __restrict__ keys, int64_t n, KeyMix mix) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = key_mix_inv(mix, keys[i]);
+}
+
+__global__ void __launch_bounds__(256) mix_kernel(u64* __restrict__ keys, int64_t n, KeyMix mix, u64 keep_mask) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u64 k = keys[i] & keep_mask;
+    keys[i] = key_mix_fwd(mix, (u32)(k >> 32), (u32)k);
+}
+
+void mix_keys_inplace(ottocov_ctx* ctx, u64* keys, int64_t n, const KeyMix& mix, bool strip_dest) {
+    if (n <= 0) return;
+    COV_LAUNCH(ctx, OTTOCOV_K_PARTITION, 16.0 * n, mix_kernel, (unsigned)ceil_div64(n, 256), 256, 0, keys, n, mix,
+               strip_dest ? 0x00FFFFFFFFFFFFFFull : ~0ull);
+}
+
+bool hashed_reduce_supported(int aid_bits) { return aid_bits >= 1 && 2 * aid_bits <= 56; }
+
+static size_t hr_smem_bytes() { return (size_t)HR_CAP * 8 + (size_t)HR_CAP * 4 + 32 * 4; }
+
+ottocov_table* hashed_reduce(ottocov_ctx* ctx, u64* keys, u64* alt, int64_t n, const KeyMix& mix, u32 min_count,
+                             bool sym, bool mirror, int* passes_out) {
+    ottocov_table* out = new ottocov_table();
+    out->aid_bits = mix.ab;
+    if (passes_out) *passes_out = 0;
+    if (n <= 0) return out;
+    if (min_count < 1) min_count = 1;
+    try {
+        // ---- group the keys into buckets of <= avg_target keys on average (top bits of the mixed key) ----
+        static int64_t avg_target = 0;
+        static int force_fallback = 0;
+        if (!avg_target) {
+            const char* e = getenv("OTTOCOV_HR_AVG");                  // tuning knob
+            avg_target = e ? atoll(e) : 512;
+            if (avg_target < 16 || avg_target > 2048) avg_target = 512;
+            const char* f = getenv("OTTOCOV_HR_FORCE_FALLBACK");        // test knob: exercise the overflow path
+            force_fallback = (f && atoi(f)) ? 1 : 0;
+        }
+        int bb = 0;
+        while (bb < mix.kb && (n >> bb) > avg_target) ++bb;
+        const int rem_bits = mix.kb - bb;
+        BitField bucket_field[1] = {{rem_bits, mix.kb}};
+        u64* k = keys; u64* ka = alt; u32* v = nullptr; u32* va = nullptr;
+        const int passes = radix_sort_pairs(ctx, k, ka, v, va, n, bucket_field, 1);
+        if (passes_out) *passes_out = passes;
+
+        // ---- count inside the buckets ------------------------------------------------------------------------
+        const u64 cap = (u64)(sym ? 2 : 1) * ((u64)n / min_count) + 1024;
+        DevBuf<u64> ok(ctx, cap);
+        DevBuf<u32> oc(ctx, cap);
+        DevBuf<unsigned long long> ctr(ctx, 2);             // [0] rows written, [1] flags (low 32 bits)
+        CUDA_CHECK(cudaMemsetAsync(ctr.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
+        static bool attr_done = false;
+        if (!attr_done) {
+            CUDA_CHECK(cudaFuncSetAttribute(hash_reduce_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hr_smem_bytes()));
+            CUDA_CHECK(cudaFuncSetAttribute(hash_reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hr_smem_bytes()));
+            CUDA_CHECK(cudaFuncSetAttribute(hash_reduce_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            CUDA_CHECK(cudaFuncSetAttribute(hash_reduce_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            attr_done = true;
+        }
+        const unsigned grid = (unsigned)ceil_div64(n, HR_TILE);
+        u32* flags = reinterpret_cast<u32*>(ctr.p + 1);
+        if (sym)
+            COV_LAUNCH(ctx, OTTOCOV_K_RLE, 8.0 * n, hash_reduce_kernel<true>, grid, HR_THREADS, hr_smem_bytes(), k, n, rem_bits,
+                       mix, min_count, mirror ? 1 : 0, ok.p, oc.p, ctr.p, cap, flags);
+        else
+            COV_LAUNCH(ctx, OTTOCOV_K_RLE, 8.0 * n, hash_reduce_kernel<false>, grid, HR_THREADS, hr_smem_bytes(), k, n, rem_bits,
+                       mix, min_count, 0, ok.p, oc.p, ctr.p, cap, flags);
+        unsigned long long h[2];
+        cov_readback(ctx, h, ctr.p, sizeof(h));
+        const int64_t rows = (int64_t)h[0];
+        BitField full[2] = {{0, mix.ab}, {32, 32 + mix.ab}};
+
+        if ((h[1] & 0xFFFFFFFFull) != 0 || force_fallback) {
+            // ---- fallback: plain keys back, full sort, run-length reduce ---------------------------------------
+            ok.release(); oc.release();
+            COV_LAUNCH(ctx, OTTOCOV_K_MISC, 16.0 * n, unmix_kernel, (unsigned)ceil_div64(n, 256), 256, 0, k, n, mix);
+            const int p2 = radix_sort_pairs(ctx, k, ka, v, va, n, full, 2);
+            if (passes_out) *passes_out += p2;
+            reduce_sorted(ctx, k, nullptr, n, min_count, sym, &out->keys, &out->count, &out->n);
+            if (sym && mirror) {
+                ottocov_table* fullt = mirror_table_impl(ctx, out, false);
+                dev_free(ctx, out->keys); dev_free(ctx, out->count); delete out;
+                out = fullt;
+            }
+            return out;
+        }
+        ctx->stats[OTTOCOV_K_RLE].algo_bytes += 12.0 * (double)rows;
+        if (rows == 0) return out;
+
+        // ---- the survivors arrive in bucket order: sort them by plain key -----------------------------------
+        DevBuf<u64> ok2(ctx, rows);
+        DevBuf<u32> oc2(ctx, rows);
+        u64* sk = ok.p; u64* ska = ok2.p; u32* sv = oc.p; u32* sva = oc2.p;
+        radix_sort_pairs(ctx, sk, ska, sv, sva, rows, full, 2);
+        if (sk != ok2.p) {               // result sits in the (over-sized) output buffers: keep the tight copy
+            CUDA_CHECK(cudaMemcpyAsync(ok2.p, sk, rows * sizeof(u64), cudaMemcpyDeviceToDevice, ctx->stream));
+            CUDA_CHECK(cudaMemcpyAsync(oc2.p, sv, rows * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        out->keys = ok2.take();
+        out->count = oc2.take();
+        out->n = rows;
+    } catch (...) {
+        dev_free(ctx, out->keys); dev_free(ctx, out->count);
+        delete out;
+        throw;
+    }
+    return out;
+}

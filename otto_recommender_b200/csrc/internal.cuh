@@ -147,6 +147,58 @@ static inline void dev_free(ottocov_ctx* ctx, void* p) { if (p) cov_free(ctx, p)
         CUDA_CHECK(cudaGetLastError());                                                       \
     } while (0)
 
+// ---- bijective key mix (bucketed hash reduce, hash_reduce.cu) --------------------------------------
+// A pair key (aid << 32 | aid_next, both < 2^ab) is compacted to kb = 2 ab bits and scrambled by an
+// invertible multiply / xor-shift / multiply / xor-shift on kb bits.  Equal keys stay equal, the top
+// bits of the result are uniform whatever the popularity skew of the aids, and the plain key is
+// recovered exactly by running the steps backwards with the modular inverses of the multipliers.
+struct KeyMix {
+    int ab = 0, kb = 0, s = 0;   // aid bits, key bits, xor-shift distance (2 s >= kb: self-inverse)
+    u64 mask = 0;
+    u64 m1 = 0, m2 = 0, m1inv = 0, m2inv = 0;
+};
+
+static inline u64 inv_odd_u64(u64 m) {          // Newton iteration: exact inverse mod 2^64 of an odd m
+    u64 x = m;                                   // correct to 3 bits
+    for (int i = 0; i < 6; ++i) x *= 2ull - m * x;
+    return x;
+}
+
+static inline KeyMix make_key_mix(int aid_bits) {
+    KeyMix m;
+    m.ab = aid_bits;
+    m.kb = 2 * aid_bits;
+    m.s = (m.kb + 1) / 2;
+    m.mask = m.kb >= 64 ? ~0ull : ((1ull << m.kb) - 1ull);
+    m.m1 = 0x9E3779B97F4A7C15ull;
+    m.m2 = 0xBF58476D1CE4E5B9ull;
+    m.m1inv = inv_odd_u64(m.m1);
+    m.m2inv = inv_odd_u64(m.m2);
+    return m;
+}
+
+#ifdef __CUDACC__
+#define COV_HD __host__ __device__ __forceinline__
+#else
+#define COV_HD static inline
+#endif
+COV_HD u64 key_mix_fwd(const KeyMix& m, u32 x, u32 y) {
+    u64 h = (((u64)x << m.ab) | (u64)y);
+    h = (h * m.m1) & m.mask;
+    h ^= h >> m.s;
+    h = (h * m.m2) & m.mask;
+    h ^= h >> m.s;
+    return h;
+}
+COV_HD u64 key_mix_inv(const KeyMix& m, u64 h) {     // -> plain key aid << 32 | aid_next
+    h ^= h >> m.s;
+    h = (h * m.m2inv) & m.mask;
+    h ^= h >> m.s;
+    h = (h * m.m1inv) & m.mask;
+    const u64 x = h >> m.ab, y = h & ((1ull << m.ab) - 1ull);
+    return (x << 32) | y;
+}
+
 // ---- device building blocks (implemented in the .cu files) -------------------------------------
 // radix_sort.cu
 struct BitField { int lo, hi; };   // sort on key bits [lo, hi)
@@ -195,6 +247,17 @@ ottocov_table* table_from_packed_impl(ottocov_ctx* ctx, const u64* keys, const u
                                       int64_t n, int where);
 void partition_table_impl(ottocov_ctx* ctx, const ottocov_table* t, int n_ranks, u64* keys_out,
                           u32* count_out, int64_t* rows_per_dest);
+
+// hash_reduce.cu
+// Bucketed hash aggregation of n MIXED keys (key_mix_fwd; bits above mix.kb clear).  keys/alt are a
+// double buffer of n keys each and are used as scratch.  Returns the table of plain keys whose count is
+// >= min_count, sorted by key.  sym: keys are canonical half pairs (diagonal totals doubled); mirror
+// (sym only): also emit the transposed off-diagonal rows, i.e. return the full symmetric table.
+bool hashed_reduce_supported(int aid_bits);
+ottocov_table* hashed_reduce(ottocov_ctx* ctx, u64* keys, u64* alt, int64_t n, const KeyMix& mix, u32 min_count,
+                             bool sym, bool mirror, int* passes_out);
+// plain keys (optionally with a destination stamp in bits 56..63) -> mixed keys, in place
+void mix_keys_inplace(ottocov_ctx* ctx, u64* keys, int64_t n, const KeyMix& mix, bool strip_dest);
 
 // topk.cu
 void topk_impl(ottocov_ctx* ctx, const ottocov_table* t, int k);

@@ -7,11 +7,12 @@
 // distribution pass):
 //   * one up-front kernel builds the digit histograms of ALL passes in a single read;
 //   * each pass is one kernel.  A CTA takes the next tile (atomic ticket, so a CTA only ever waits
-//     for tiles that already started), histograms its 4096 keys by digit, publishes the per-digit
-//     tile counts at once, ranks the keys with warp match-any into a digit-ordered staging buffer in
-//     shared memory, resolves the per-digit exclusive prefix over earlier tiles by decoupled
-//     look-back on epoch-tagged 64-bit status words and writes the keys out as coalesced per-digit
-//     runs.
+//     for tiles that already started), ranks its 4096 keys by digit (one ballot per digit bit finds
+//     the lanes with the same digit; running per-warp counters make the rank stable), publishes the
+//     per-digit tile counts, resolves the per-digit exclusive prefix over earlier tiles by decoupled
+//     look-back on epoch-tagged 64-bit status words, stages the keys in digit order in shared memory
+//     and writes them out as coalesced per-digit runs.  With `ptr_base` the per-digit runs start at
+//     caller-given byte addresses instead (peer memory: the fused partition + exchange of dist.py).
 //   * status word = flag(2) | epoch(6) | value(56).  The epoch changes every pass, so the status
 //     array is never re-zeroed between passes.
 // Only the significant bit fields are sorted: for co-event keys that is 2 x aid_bits (42 bits for
@@ -145,7 +146,8 @@ __device__ __forceinline__ void rank_rows(const u64 (&key)[RS_IPT], int shift, u
     }
 }
 
-// ALGO selects how lanes holding the same digit find each other (tuning knob):
+// ALGO selects how lanes holding the same digit find each other (tuning knob OTTOCOV_RS_ALGO, measured in
+// experiments/README.md; 1 is the default):
 //   0  match.any            1  NB ballots (one per digit bit)            2  atomicOr on a per-warp mask table
 // phases A, D and F for one tile; FULL = all 4096 slots valid (every tile but the last): no predicates
 template <bool HAS_VALS, bool FULL>

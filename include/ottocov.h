@@ -53,7 +53,10 @@ typedef struct ottocov_table ottocov_table;
 
 /* One co-event kind = one entry of config.MAP_NAME_COUNT_TYPE + MAP_MAX_TIME_TO_NEXT
  * (reference config.py:43-49, 81-88). */
-enum { OTTOCOV_SYM_OFF = 1, OTTOCOV_SYM_ON = 2 };
+enum { OTTOCOV_SYM_OFF = 1, OTTOCOV_SYM_ON = 2,
+       OTTOCOV_HASH_OFF = 4, OTTOCOV_HASH_ON = 8 };   /* see ottocov_spec.flags */
+/* bits of ottocov_reduce_pairs' strip_dest argument above bit 0 */
+enum { OTTOCOV_REDUCE_HASH_ON = 2, OTTOCOV_REDUCE_HASH_OFF = 4 };
 
 typedef struct {
     int32_t type_this;       /* source event type: 0 click, 1 cart, 2 order                       */
@@ -67,6 +70,12 @@ typedef struct {
                              /* (count(a,b) == count(b,a)): the engine may expand each unordered    */
                              /* event pair once and mirror the reduced table.  Auto does so when    */
                              /* min_count > 1.  OTTOCOV_SYM_OFF / OTTOCOV_SYM_ON force the choice.   */
+                             /* Reduce-by-key strategy: full radix sort + run-length reduce, or the  */
+                             /* bucketed hash reduce (keys written through a bijective mix, sorted   */
+                             /* on the top hash bits only, counted in shared-memory tables).  Auto   */
+                             /* takes the hash reduce when min_count > 1 (few rows left to bring     */
+                             /* back into key order); OTTOCOV_HASH_OFF / OTTOCOV_HASH_ON force it.    */
+                             /* Both produce the same table bit for bit.                              */
 } ottocov_spec;
 
 typedef struct {
@@ -180,8 +189,9 @@ uint32_t ottocov_hash_dest(uint32_t aid, uint32_t n_ranks);
  *   ottocov_expand_run      emits them into caller-owned DEVICE buffers (each >= n_keys); the grouped
  *                           keys end in buf_b when *result_in_b, else in buf_a; rows_per_dest is HOST
  *   ottocov_reduce_pairs    sort + run-length count of received keys (keys_dev is used as scratch);
- *                           symmetric = keys are half pairs (diagonal counts are doubled), strip_dest =
- *                           clear key bits 56..63 first
+ *                           symmetric = keys are half pairs (diagonal counts are doubled), strip_dest
+ *                           bit 0 = clear key bits 56..63 first; OTTOCOV_REDUCE_HASH_ON / _OFF in the
+ *                           same argument force the reduce strategy (auto: hash reduce iff min_count > 1)
  *   ottocov_table_mirror    half table (rows a <= b) -> full symmetric table, or only the transposed
  *                           off-diagonal rows (transpose_only), which belong to rank hash(b) */
 int ottocov_expand_prepare(ottocov_ctx* ctx, const ottocov_spec* spec, int64_t* n_keys, int* symmetric);

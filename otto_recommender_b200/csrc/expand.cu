@@ -132,21 +132,24 @@ __global__ void __launch_bounds__(256) tile_search_kernel(const u64* __restrict_
     tile_rec[t] = (u32)(lo - 1);
 }
 
-template <bool CANON>
-__device__ __forceinline__ u64 make_pair_key(u32 a, u32 b, u32 n_dest) {
+// MIX: the key is written through the bijective mix of internal.cuh (bucketed hash reduce); never together
+// with a destination stamp (the multi-GPU path mixes on the receiving side).
+template <bool CANON, bool MIX>
+__device__ __forceinline__ u64 make_pair_key(u32 a, u32 b, u32 n_dest, const KeyMix& mix) {
     u32 x = a, y = b;
     if (CANON) { x = a < b ? a : b; y = a < b ? b : a; }
+    if (MIX) return key_mix_fwd(mix, x, y);
     u64 k = ((u64)x << 32) | (u64)y;
     if (n_dest > 1) k |= (u64)hash_dest(x, n_dest) << 56;      // destination rank of the row (x, .)
     return k;
 }
 
-template <bool SELF, bool CANON>
+template <bool SELF, bool CANON, bool MIX>
 __global__ void __launch_bounds__(EX_THREADS)
 expand_kernel(const u32* __restrict__ rec_src, const u32* __restrict__ rec_lo,
               const u64* __restrict__ rec_off, const u32* __restrict__ tile_rec,
               const u32* __restrict__ aid_src, const u32* __restrict__ aid_tgt, u64 out_begin,
-              u64 out_end, u64* __restrict__ dst, u32 n_dest) {
+              u64 out_end, u64* __restrict__ dst, u32 n_dest, KeyMix mix) {
     __shared__ u32 s_off[EX_TILE + 1];
     __shared__ u32 s_lo[EX_TILE + 1];
     __shared__ u32 s_aid[EX_TILE + 1];
@@ -195,12 +198,12 @@ expand_kernel(const u32* __restrict__ rec_src, const u32* __restrict__ rec_lo,
         u32 j = lo;
         u32 tgt = s_lo[j] + (k - s_off[j]);
         if (SELF) tgt += (tgt >= s_src[j]);
-        const u64 key0 = make_pair_key<CANON>(s_aid[j], aid_tgt[tgt], n_dest);
+        const u64 key0 = make_pair_key<CANON, MIX>(s_aid[j], aid_tgt[tgt], n_dest, mix);
         if (k + 1 < n_out) {
             if (j + 1 < n_rec && s_off[j + 1] <= k + 1) ++j;
             u32 tgt1 = s_lo[j] + (k + 1 - s_off[j]);
             if (SELF) tgt1 += (tgt1 >= s_src[j]);
-            const u64 key1 = make_pair_key<CANON>(s_aid[j], aid_tgt[tgt1], n_dest);
+            const u64 key1 = make_pair_key<CANON, MIX>(s_aid[j], aid_tgt[tgt1], n_dest, mix);
             if (vec_ok) {
                 ulonglong2 v; v.x = key0; v.y = key1;
                 __stcs(reinterpret_cast<ulonglong2*>(tile_dst + k), v);
@@ -304,8 +307,11 @@ static ExpandPlan* make_plan(ottocov_ctx* ctx, const ottocov_spec* spec, bool di
 
 // keys of plan outputs [c0, c1) -> dst[0 .. c1-c0).  n_dest > 1 also stamps hash(aid of the key) % n_dest
 // into key bits [56, 64) so one radix pass on those bits groups the keys by destination rank.
-static void expand_range(ottocov_ctx* ctx, const ExpandPlan* pl, u64 c0, u64 c1, u64* dst_base, u32 n_dest) {
+// mix != nullptr: keys are written mixed (bucketed hash reduce), n_dest must be 0.
+static void expand_range(ottocov_ctx* ctx, const ExpandPlan* pl, u64 c0, u64 c1, u64* dst_base, u32 n_dest,
+                         const KeyMix* mix = nullptr) {
     const TypeArray& src = ctx->ta[pl->A];
+    const KeyMix mx = mix ? *mix : KeyMix();
     u64 seg_start = 0;
     for (Segment* sg : pl->segs) {
         const u64 seg_end = seg_start + sg->n_pairs;
@@ -320,15 +326,19 @@ static void expand_range(ottocov_ctx* ctx, const ExpandPlan* pl, u64 c0, u64 c1,
             const TypeArray& tgt = ctx->ta[sg->tgt_type];
             u64* dst = dst_base + (a - c0);
             const double bytes = 8.0 * (double)(oe - ob);
-            if (pl->sym)
-                COV_LAUNCH(ctx, OTTOCOV_K_EXPAND, bytes, (expand_kernel<false, true>), (unsigned)n_tiles, EX_THREADS, 0,
-                           sg->rec_src.p, sg->rec_lo.p, sg->rec_off.p, tile_rec.p, src.aid, tgt.aid, ob, oe, dst, n_dest);
-            else if (sg->self)
-                COV_LAUNCH(ctx, OTTOCOV_K_EXPAND, bytes, (expand_kernel<true, false>), (unsigned)n_tiles, EX_THREADS, 0,
-                           sg->rec_src.p, sg->rec_lo.p, sg->rec_off.p, tile_rec.p, src.aid, tgt.aid, ob, oe, dst, n_dest);
-            else
-                COV_LAUNCH(ctx, OTTOCOV_K_EXPAND, bytes, (expand_kernel<false, false>), (unsigned)n_tiles, EX_THREADS, 0,
-                           sg->rec_src.p, sg->rec_lo.p, sg->rec_off.p, tile_rec.p, src.aid, tgt.aid, ob, oe, dst, n_dest);
+#define EX_LAUNCH(SELF_, CANON_, MIX_)                                                                              \
+            COV_LAUNCH(ctx, OTTOCOV_K_EXPAND, bytes, (expand_kernel<SELF_, CANON_, MIX_>), (unsigned)n_tiles, EX_THREADS, 0, \
+                       sg->rec_src.p, sg->rec_lo.p, sg->rec_off.p, tile_rec.p, src.aid, tgt.aid, ob, oe, dst, n_dest, mx)
+            if (mix) {
+                if (pl->sym) EX_LAUNCH(false, true, true);
+                else if (sg->self) EX_LAUNCH(true, false, true);
+                else EX_LAUNCH(false, false, true);
+            } else {
+                if (pl->sym) EX_LAUNCH(false, true, false);
+                else if (sg->self) EX_LAUNCH(true, false, false);
+                else EX_LAUNCH(false, false, false);
+            }
+#undef EX_LAUNCH
         }
         seg_start = seg_end;
     }
@@ -363,6 +373,13 @@ ottocov_table* count_impl(ottocov_ctx* ctx, const ottocov_spec* spec) {
     if (budget == 0) budget = EX_TILE;
 
     const u32 fused_min = (P <= budget) ? pl->user_min : 1;     // thresholds apply to complete sums only
+    // bucketed hash reduce (hash_reduce.cu) instead of full sort + run-length reduce: pays when a threshold
+    // leaves few rows to bring back into key order; OTTOCOV_HASH_ON / OTTOCOV_HASH_OFF force the choice
+    const bool hashed = hashed_reduce_supported(aid_bits) && !(spec->flags & OTTOCOV_HASH_OFF) &&
+                        ((spec->flags & OTTOCOV_HASH_ON) || fused_min > 1);
+    const bool single = P <= budget;
+    const KeyMix mix = make_key_mix(aid_bits);
+    bool mirrored = false;
     std::vector<ottocov_table*> partials;
     struct PartGuard {
         ottocov_ctx* c; std::vector<ottocov_table*>& v;
@@ -375,6 +392,18 @@ ottocov_table* count_impl(ottocov_ctx* ctx, const ottocov_spec* spec) {
         const u64 cn = c1 - c0;
         DevBuf<u64> keys(ctx, cn), alt(ctx, cn);
         cov_trace(ctx, "count: alloc keys");
+        if (hashed) {
+            expand_range(ctx, pl, c0, c1, keys.p, 0, &mix);
+            cov_trace(ctx, "count: expand (mixed keys)");
+            int passes = 0;
+            mirrored = sym && single;                  // the mirrored rows come out of the same table scan
+            ottocov_table* part = hashed_reduce(ctx, keys.p, alt.p, (int64_t)cn, mix, fused_min, sym, mirrored, &passes);
+            partials.push_back(part);
+            ci.sort_passes = passes;
+            cov_trace(ctx, "count: bucket passes + hash reduce");
+            ci.n_chunks += 1;
+            continue;
+        }
         expand_range(ctx, pl, c0, c1, keys.p, 0);
         cov_trace(ctx, "count: expand");
         u64* k = keys.p; u64* ka = alt.p; u32* v = nullptr; u32* va = nullptr;
@@ -400,7 +429,7 @@ ottocov_table* count_impl(ottocov_ctx* ctx, const ottocov_spec* spec) {
             result = f;
         }
     }
-    if (sym) {                                      // (a, b, c) -> also (b, a, c)
+    if (sym && !mirrored) {                         // (a, b, c) -> also (b, a, c)
         ottocov_table* full = mirror_table_impl(ctx, result, false);
         dev_free(ctx, result->keys); dev_free(ctx, result->count); delete result;
         result = full;
@@ -484,8 +513,23 @@ ottocov_table* reduce_pairs_impl(ottocov_ctx* ctx, u64* keys, int64_t n, int aid
     if (aid_bits < 1 || aid_bits > 32) COV_THROW(OTTOCOV_ERR_ARG, "aid_bits must be 1..32");
     ottocov_table* out = make_empty_table(aid_bits);
     if (n == 0) return out;
+    const bool strip = (strip_dest & 1) != 0;
+    const bool hashed = hashed_reduce_supported(aid_bits) && !(strip_dest & OTTOCOV_REDUCE_HASH_OFF) &&
+                        ((strip_dest & OTTOCOV_REDUCE_HASH_ON) || min_count > 1);
+    if (hashed) {
+        delete out;
+        const KeyMix mix = make_key_mix(aid_bits);
+        mix_keys_inplace(ctx, keys, n, mix, strip);     // the strip pass, now also mixing
+        DevBuf<u64> alt(ctx, n);
+        int passes = 0;
+        out = hashed_reduce(ctx, keys, alt.p, n, mix, min_count > 1 ? min_count : 1, sym != 0, false, &passes);
+        ctx->last_count.sort_passes = passes;
+        ctx->last_count.n_chunks = 1;
+        ctx->last_count.n_unique = out->n;
+        return out;
+    }
     try {
-        if (strip_dest)
+        if (strip)
             COV_LAUNCH(ctx, OTTOCOV_K_PARTITION, 16.0 * n, strip_dest_kernel, (unsigned)ceil_div64(n, 256), 256, 0, keys, n);
         DevBuf<u64> alt(ctx, n);
         BitField fields[2] = {{0, aid_bits}, {32, 32 + aid_bits}};

@@ -29,35 +29,81 @@ constexpr int HR_THREADS = 512;
 constexpr int HR_IPT = 8;
 constexpr int HR_TILE = HR_THREADS * HR_IPT;     // 4096 keys per CTA (+ the tail of its last bucket)
 constexpr int HR_CAP_LOG2 = 13;
-constexpr int HR_CAP = 1 << HR_CAP_LOG2;         // 8192 slots: 64 KB keys + 32 KB counts, 2 CTAs / SM
+constexpr int HR_CAP = 1 << HR_CAP_LOG2;         // 8192 slots
 constexpr int HR_SPT = HR_CAP / HR_THREADS;      // slots per thread in the table scan
+constexpr int HR_XT = 4;                         // keys per thread per slice of a long bucket tail
+constexpr int HR_MAX_TAIL_ROUNDS = 1000;         // ~2 M keys: beyond that one CTA would serialise the reduce
 constexpr u64 HR_NONE = ~0ull;                   // empty slot / no key (mixed keys have <= 56 bits)
+// Packed table word: tag(42) | count(22).  Shared-memory atomics cost ~2 cycles per lane on this part and
+// bound the kernel, so one atomic per key matters: a new key is claimed AND counted by one 64-bit CAS, a
+// repeated key by one 32-bit add on the low word.  tag = mixed key - (first bucket of the tile << rem_bits);
+// the count cannot overflow its field because a CTA never counts more than HR_TILE + (HR_MAX_TAIL_ROUNDS *
+// HR_XT + 1) * HR_THREADS keys.
+constexpr int HR_CB = 22;
+constexpr int HR_TAG_BITS = 64 - HR_CB;
+constexpr u64 HR_CMASK = (1ull << HR_CB) - 1ull;
 static_assert(2 * HR_SPT <= 32, "two flag bits per scanned slot must fit one register");
+static_assert((u64)HR_TILE + ((u64)HR_MAX_TAIL_ROUNDS * HR_XT + 1) * HR_THREADS < HR_CMASK, "count field too narrow");
 
-__device__ __forceinline__ void hr_insert(u64* s_key, u32* s_cnt, u64 h, u32* flags) {
-    u32 slot = (((u32)h ^ (u32)(h >> 32)) * 0x9E3779B1u) >> (32 - HR_CAP_LOG2);
+// PACKED: s_key[slot] = tag << 22 | count (64 KB, 3 CTAs / SM).  Otherwise (keys too wide for a 42-bit tag):
+// s_key[slot] = mixed key, s_cnt[slot] = count (96 KB, 2 CTAs / SM, two atomics for a new key).
+template <bool PACKED>
+__device__ __forceinline__ void hr_insert(u64* s_key, u32* s_cnt, u64 h, u64 base, u32 times, u32* flags) {
+    const u64 tag = h - base;
+    if (PACKED && (tag >> HR_TAG_BITS)) { atomicOr(flags, 8u); return; }     // bucket span wider than the tag
+    u32 slot = (((u32)tag ^ (u32)(tag >> 32)) * 0x9E3779B1u) >> (32 - HR_CAP_LOG2);
 #pragma unroll 1
     for (int probes = 0; probes < HR_CAP; ++probes) {
         u64 cur = *reinterpret_cast<volatile u64*>(s_key + slot);
-        if (cur == HR_NONE) {
-            cur = atomicCAS(reinterpret_cast<unsigned long long*>(s_key + slot), HR_NONE, h);
-            if (cur == HR_NONE) cur = h;                   // this thread claimed the slot
+        if (PACKED) {
+            if (cur == HR_NONE) {
+                cur = atomicCAS(reinterpret_cast<unsigned long long*>(s_key + slot), HR_NONE, (tag << HR_CB) | (u64)times);
+                if (cur == HR_NONE) return;                     // claimed and counted in one step
+            }
+            if ((cur >> HR_CB) == tag) { atomicAdd(reinterpret_cast<u32*>(s_key + slot), times); return; }
+        } else {
+            if (cur == HR_NONE) {
+                cur = atomicCAS(reinterpret_cast<unsigned long long*>(s_key + slot), HR_NONE, tag);
+                if (cur == HR_NONE) cur = tag;                  // this thread claimed the slot
+            }
+            if (cur == tag) { atomicAdd(s_cnt + slot, times); return; }
         }
-        if (cur == h) { atomicAdd(s_cnt + slot, 1u); return; }
         slot = (slot + 1) & (HR_CAP - 1);
     }
     atomicOr(flags, 1u);                                   // table full: the host falls back to the full sort
 }
 
-template <bool SYM>
-__global__ void __launch_bounds__(HR_THREADS, 2)
+// Keys past the tile end (the rest of the CTA's last bucket).  A long tail means a hot pair repeated many
+// times: when a whole warp holds one key, one lane adds 32 instead of 32 lanes queueing on one counter.
+template <bool PACKED>
+__device__ __forceinline__ void hr_insert_tail(u64* s_key, u32* s_cnt, u64 h, u64 base, bool mine, u32* flags) {
+    const u64 h0 = __shfl_sync(0xffffffffu, h, 0);
+    if (__all_sync(0xffffffffu, mine && h == h0)) {
+        if ((threadIdx.x & 31) == 0) hr_insert<PACKED>(s_key, s_cnt, h0, base, 32u, flags);
+    } else if (mine) {
+        hr_insert<PACKED>(s_key, s_cnt, h, base, 1u, flags);
+    }
+}
+
+// slot j -> (mixed key, count); false when the slot is empty
+template <bool PACKED>
+__device__ __forceinline__ bool hr_slot(const u64* s_key, const u32* s_cnt, int j, u64 base, u64* h, u32* c) {
+    const u64 w = s_key[j];
+    if (w == HR_NONE) return false;
+    if (PACKED) { *h = (w >> HR_CB) + base; *c = (u32)(w & HR_CMASK); }
+    else { *h = w; *c = s_cnt[j]; }
+    return true;
+}
+
+template <bool SYM, bool PACKED>
+__global__ void __launch_bounds__(HR_THREADS, PACKED ? 3 : 2)
 hash_reduce_kernel(const u64* __restrict__ keys, int64_t n, int rem_bits, KeyMix mix, u32 min_count, int mirror,
                    u64* __restrict__ out_keys, u32* __restrict__ out_count, unsigned long long* __restrict__ out_n,
                    u64 out_cap, u32* __restrict__ flags) {
     extern __shared__ __align__(16) unsigned char s_raw[];
-    u64* s_key = reinterpret_cast<u64*>(s_raw);            // [HR_CAP]
-    u32* s_cnt = reinterpret_cast<u32*>(s_key + HR_CAP);   // [HR_CAP]
-    u32* s_scan = s_cnt + HR_CAP;                          // [HR_THREADS / 32 + 1]
+    u64* s_key = reinterpret_cast<u64*>(s_raw);                              // [HR_CAP]
+    u32* s_cnt = reinterpret_cast<u32*>(s_key + HR_CAP);                     // [HR_CAP] (!PACKED)
+    u32* s_scan = s_cnt + (PACKED ? 0 : HR_CAP);                             // [HR_THREADS / 32 + 1]
     __shared__ unsigned long long s_base;
     __shared__ u32 s_over;
 
@@ -69,6 +115,8 @@ hash_reduce_kernel(const u64* __restrict__ keys, int64_t n, int rem_bits, KeyMix
     const u64 pb = t0 > 0 ? (keys[t0 - 1] >> rem_bits) : HR_NONE;
     const u64 lb = keys[t1 - 1] >> rem_bits;
     if (lb == pb) return;                                  // the whole tile continues an earlier CTA's bucket
+    // every key this CTA counts is >= the first key's bucket: tags are relative to it
+    const u64 base = PACKED ? ((keys[t0] >> rem_bits) << rem_bits) : 0ull;
 
     u64 k[HR_IPT];
 #pragma unroll
@@ -77,21 +125,46 @@ hash_reduce_kernel(const u64* __restrict__ keys, int64_t n, int rem_bits, KeyMix
         k[r] = (i < t1) ? __ldcs(keys + i) : HR_NONE;
     }
     u64 kx = (t1 + tid < n) ? __ldcs(keys + t1 + tid) : HR_NONE;     // first slice past the tile end
-    for (int j = tid; j < HR_CAP; j += HR_THREADS) { s_key[j] = HR_NONE; s_cnt[j] = 0; }
+    for (int j = tid; j < HR_CAP; j += HR_THREADS) {
+        s_key[j] = HR_NONE;
+        if (!PACKED) s_cnt[j] = 0;
+    }
     if (tid == 0) s_over = 0;
     __syncthreads();
 
 #pragma unroll
     for (int r = 0; r < HR_IPT; ++r)
-        if (k[r] != HR_NONE && (k[r] >> rem_bits) != pb) hr_insert(s_key, s_cnt, k[r], flags);
-    // the keys of bucket lb are a prefix of what follows the tile
-    int64_t base = t1;
-    while (true) {
+        if (k[r] != HR_NONE && (k[r] >> rem_bits) != pb) hr_insert<PACKED>(s_key, s_cnt, k[r], base, 1u, flags);
+    // the keys of bucket lb are a prefix of what follows the tile: first the slice loaded up front, then
+    // (rarely: a bucket that holds a hot pair) slices of HR_XT keys per thread until the bucket ends
+    {
         const bool more = (kx != HR_NONE) && ((kx >> rem_bits) == lb);
-        if (more) hr_insert(s_key, s_cnt, kx, flags);
-        if (!__syncthreads_and(more ? 1 : 0)) break;
-        base += HR_THREADS;
-        kx = (base + tid < n) ? __ldcs(keys + base + tid) : HR_NONE;
+        hr_insert_tail<PACKED>(s_key, s_cnt, kx, base, more, flags);
+        if (__syncthreads_and(more ? 1 : 0)) {
+            int64_t next = t1 + HR_THREADS;
+            int rounds = 0;
+            while (true) {
+                u64 kk[HR_XT];
+#pragma unroll
+                for (int q = 0; q < HR_XT; ++q) {
+                    const int64_t i = next + q * HR_THREADS + tid;
+                    kk[q] = (i < n) ? __ldcs(keys + i) : HR_NONE;
+                }
+                bool all = true;
+#pragma unroll
+                for (int q = 0; q < HR_XT; ++q) {
+                    const bool m = (kk[q] != HR_NONE) && ((kk[q] >> rem_bits) == lb);
+                    hr_insert_tail<PACKED>(s_key, s_cnt, kk[q], base, m, flags);
+                    all = all && m;
+                }
+                if (!__syncthreads_and(all ? 1 : 0)) break;
+                next += HR_XT * HR_THREADS;
+                if (++rounds >= HR_MAX_TAIL_ROUNDS) {      // block-uniform: a multi-million-key bucket is better
+                    if (tid == 0) atomicOr(flags, 4u);     // served by the sort path (host falls back)
+                    break;
+                }
+            }
+        }
     }
     __syncthreads();
 
@@ -100,12 +173,12 @@ hash_reduce_kernel(const u64* __restrict__ keys, int64_t n, int rem_bits, KeyMix
 #pragma unroll
     for (int q = 0; q < HR_SPT; ++q) {
         const int j = tid + q * HR_THREADS;
-        const u32 c = s_cnt[j];
-        if (c) {
+        u64 h; u32 c;
+        if (hr_slot<PACKED>(s_key, s_cnt, j, base, &h, &c)) {
             u64 total = c;
             bool diag = false;
-            if (SYM) {
-                const u64 plain = key_mix_inv(mix, s_key[j]);
+            if (SYM && 2ull * total >= (u64)min_count) {   // un-mix only rows that can survive
+                const u64 plain = key_mix_inv(mix, h);
                 diag = (u32)(plain >> 32) == (u32)plain;
                 if (diag) total *= 2;                      // (a, a): both orders of each event pair
             }
@@ -134,8 +207,10 @@ hash_reduce_kernel(const u64* __restrict__ keys, int64_t n, int rem_bits, KeyMix
         const u32 f = (bits >> (2 * q)) & 3u;
         if (f) {
             const int j = tid + q * HR_THREADS;
-            const u64 plain = key_mix_inv(mix, s_key[j]);
-            u64 total = s_cnt[j];
+            u64 h; u32 c;
+            hr_slot<PACKED>(s_key, s_cnt, j, base, &h, &c);
+            const u64 plain = key_mix_inv(mix, h);
+            u64 total = c;
             if (SYM && (u32)(plain >> 32) == (u32)plain) total *= 2;
             const u32 c32 = (u32)(total > 0xFFFFFFFFull ? 0xFFFFFFFFull : total);
             out_keys[o] = plain; out_count[o] = c32; ++o;
@@ -164,7 +239,7 @@ void mix_keys_inplace(ottocov_ctx* ctx, u64* keys, int64_t n, const KeyMix& mix,
 
 bool hashed_reduce_supported(int aid_bits) { return aid_bits >= 1 && 2 * aid_bits <= 56; }
 
-static size_t hr_smem_bytes() { return (size_t)HR_CAP * 8 + (size_t)HR_CAP * 4 + 32 * 4; }
+static size_t hr_smem_bytes(bool packed) { return (size_t)HR_CAP * 8 + (packed ? 0 : (size_t)HR_CAP * 4) + 32 * 4; }
 
 ottocov_table* hashed_reduce(ottocov_ctx* ctx, u64* keys, u64* alt, int64_t n, const KeyMix& mix, u32 min_count,
                              bool sym, bool mirror, int* passes_out) {
@@ -176,13 +251,15 @@ ottocov_table* hashed_reduce(ottocov_ctx* ctx, u64* keys, u64* alt, int64_t n, c
     try {
         // ---- group the keys into buckets of <= avg_target keys on average (top bits of the mixed key) ----
         static int64_t avg_target = 0;
-        static int force_fallback = 0;
+        static int force_fallback = 0, no_packed = 0;
         if (!avg_target) {
             const char* e = getenv("OTTOCOV_HR_AVG");                  // tuning knob
             avg_target = e ? atoll(e) : 512;
             if (avg_target < 16 || avg_target > 2048) avg_target = 512;
             const char* f = getenv("OTTOCOV_HR_FORCE_FALLBACK");        // test knob: exercise the overflow path
             force_fallback = (f && atoi(f)) ? 1 : 0;
+            const char* g = getenv("OTTOCOV_HR_NO_PACKED");             // test / tuning knob: wide table words
+            no_packed = (g && atoi(g)) ? 1 : 0;
         }
         int bb = 0;
         while (bb < mix.kb && (n >> bb) > avg_target) ++bb;
@@ -198,22 +275,26 @@ ottocov_table* hashed_reduce(ottocov_ctx* ctx, u64* keys, u64* alt, int64_t n, c
         DevBuf<u32> oc(ctx, cap);
         DevBuf<unsigned long long> ctr(ctx, 2);             // [0] rows written, [1] flags (low 32 bits)
         CUDA_CHECK(cudaMemsetAsync(ctr.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
-        static bool attr_done = false;
-        if (!attr_done) {
-            CUDA_CHECK(cudaFuncSetAttribute(hash_reduce_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hr_smem_bytes()));
-            CUDA_CHECK(cudaFuncSetAttribute(hash_reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hr_smem_bytes()));
-            CUDA_CHECK(cudaFuncSetAttribute(hash_reduce_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            CUDA_CHECK(cudaFuncSetAttribute(hash_reduce_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            attr_done = true;
-        }
+        // packed table words need the tag (mixed key relative to the tile's first bucket) to fit 42 bits: always
+        // true for keys of <= 42 bits; wider keys qualify when 256 consecutive buckets fit
+        const bool packed = (mix.kb <= HR_TAG_BITS || rem_bits + 8 <= HR_TAG_BITS) && !no_packed;
         const unsigned grid = (unsigned)ceil_div64(n, HR_TILE);
         u32* flags = reinterpret_cast<u32*>(ctr.p + 1);
-        if (sym)
-            COV_LAUNCH(ctx, OTTOCOV_K_RLE, 8.0 * n, hash_reduce_kernel<true>, grid, HR_THREADS, hr_smem_bytes(), k, n, rem_bits,
-                       mix, min_count, mirror ? 1 : 0, ok.p, oc.p, ctr.p, cap, flags);
-        else
-            COV_LAUNCH(ctx, OTTOCOV_K_RLE, 8.0 * n, hash_reduce_kernel<false>, grid, HR_THREADS, hr_smem_bytes(), k, n, rem_bits,
-                       mix, min_count, 0, ok.p, oc.p, ctr.p, cap, flags);
+#define HR_LAUNCH(SYM_, PACKED_)                                                                                      \
+        do {                                                                                                          \
+            auto kern = hash_reduce_kernel<SYM_, PACKED_>;                                                            \
+            static bool attr_done = false;                                                                            \
+            if (!attr_done) {                                                                                         \
+                CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hr_smem_bytes(PACKED_))); \
+                CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));          \
+                attr_done = true;                                                                                     \
+            }                                                                                                         \
+            COV_LAUNCH(ctx, OTTOCOV_K_RLE, 8.0 * n, kern, grid, HR_THREADS, hr_smem_bytes(PACKED_), k, n, rem_bits,    \
+                       mix, min_count, (SYM_ && mirror) ? 1 : 0, ok.p, oc.p, ctr.p, cap, flags);                      \
+        } while (0)
+        if (sym) { if (packed) HR_LAUNCH(true, true); else HR_LAUNCH(true, false); }
+        else { if (packed) HR_LAUNCH(false, true); else HR_LAUNCH(false, false); }
+#undef HR_LAUNCH
         unsigned long long h[2];
         cov_readback(ctx, h, ctr.p, sizeof(h));
         const int64_t rows = (int64_t)h[0];

@@ -215,16 +215,18 @@ class Engine:
     def count(self, name: Optional[str] = None, *, type_this: Optional[int] = None,
               next_types: Optional[Sequence[int]] = None, window: Optional[int] = None,
               pair_budget: Optional[int] = None, min_count: int = 1,
-              symmetric: Optional[bool] = None) -> Table:
+              symmetric: Optional[bool] = None, hashed: Optional[bool] = None) -> Table:
         """One iteration of count_co_events' loop (count_co_events.py:64-72) on the loaded events.
-        min_count > 1 fuses filter(count >= min_count) (count_co_events.py:172) into the reduce."""
-        spec = self._spec(name, type_this, next_types, window, pair_budget, min_count, symmetric)
+        min_count > 1 fuses filter(count >= min_count) (count_co_events.py:172) into the reduce.
+        hashed: force (True) or forbid (False) the bucketed hash reduce; None = auto (min_count > 1).
+        Both strategies return the same table."""
+        spec = self._spec(name, type_this, next_types, window, pair_budget, min_count, symmetric, hashed)
         h = ctypes.c_void_p()
         self._sync_stream()
         self._check(self._lib.ottocov_count(self._ctx, ctypes.byref(spec), ctypes.byref(h)))
         return Table(self, h.value)
 
-    def _spec(self, name, type_this, next_types, window, pair_budget, min_count, symmetric):
+    def _spec(self, name, type_this, next_types, window, pair_budget, min_count, symmetric, hashed=None):
         if name is not None:
             th, mask, w = self.config.spec(name)
         else:
@@ -235,6 +237,8 @@ class Engine:
             w = int(window)
         budget = self.config.PAIR_BUDGET if pair_budget is None else int(pair_budget)
         flags = 0 if symmetric is None else (2 if symmetric else 1)
+        if hashed is not None:
+            flags |= 8 if hashed else 4
         return _lib.Spec(th, mask, w, budget, max(int(min_count), 0), flags)
 
     # ---- exchange-before-reduce building blocks (multi-GPU) ---------------------------------------------
@@ -267,12 +271,14 @@ class Engine:
         self._check(self._lib.ottocov_push_keys(self._ctx, keys.data_ptr() if n else None, int(n), len(dest_ptrs), arr))
 
     def reduce_pairs(self, keys, n: int, aid_bits: int, min_count: int = 1, symmetric: bool = False,
-                     strip_dest: bool = False) -> Table:
-        """Sort + run-length count of raw keys (an int64 CUDA tensor, used as scratch)."""
+                     strip_dest: bool = False, hashed: Optional[bool] = None) -> Table:
+        """Reduce-by-key of raw keys (an int64 CUDA tensor, used as scratch): sort + run-length count, or the
+        bucketed hash reduce (auto when min_count > 1; `hashed` forces the choice)."""
         h = ctypes.c_void_p()
         self._sync_stream()
+        mode = int(bool(strip_dest)) | (0 if hashed is None else (2 if hashed else 4))
         self._check(self._lib.ottocov_reduce_pairs(self._ctx, keys.data_ptr() if n else None, int(n), int(aid_bits),
-                                                   max(int(min_count), 0), int(symmetric), int(strip_dest),
+                                                   max(int(min_count), 0), int(symmetric), mode,
                                                    ctypes.byref(h)))
         return Table(self, h.value)
 

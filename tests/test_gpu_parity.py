@@ -403,6 +403,106 @@ def test_errors_are_loud(engine):
     assert e.value.code == -2
 
 
+# ---- bucketed hash reduce (hash_reduce.cu) == full sort + run-length reduce == oracle --------------------------
+@pytest.mark.parametrize("name", NAMES)
+def test_hash_reduce_vs_oracle(engine, name):
+    s, a, t, y = small_events(41, n_sessions=900, n_aids=90, max_len=50)
+    engine.load_events(s, a, t, y)
+    oa, ob, oc, emitted, _ = c_oracle.count_name(s, a, t, y, name)
+    for mc in (1, 2, 5, 100_000):
+        ka, kb, kc = c_oracle.merge_tables([(oa, ob, oc)], min_count=mc)
+        for sym in (None, True, False):
+            for kw in ({}, {"pair_budget": 4096}):
+                got = engine.count(name, min_count=mc, symmetric=sym, hashed=True, **kw)
+                assert engine.count_info()["n_pairs"] == emitted
+                ga, gb, gc = got.fetch()
+                assert np.array_equal(ga, ka) and np.array_equal(gb, kb) and np.array_equal(gc, kc), (name, mc, sym, kw)
+                got.free()
+
+
+def test_hash_reduce_wide_keys(engine):
+    """aids of 27 bits: 54-bit keys do not fit the packed table word (42-bit tag), the wide variant runs."""
+    s, a, t, y = small_events(43, n_sessions=700, n_aids=90, max_len=40)
+    a = a * 1_000_003
+    info = engine.load_events(s, a, t, y)
+    assert info["aid_bits"] == 27
+    for name in ("click_to_click", "click_to_cart_or_buy"):
+        oa, ob, oc, emitted, _ = c_oracle.count_name(s, a, t, y, name)
+        for mc in (1, 3):
+            ka, kb, kc = c_oracle.merge_tables([(oa, ob, oc)], min_count=mc)
+            ga, gb, gc = engine.count(name, min_count=mc, hashed=True).fetch()
+            assert np.array_equal(ga, ka) and np.array_equal(gb, kb) and np.array_equal(gc, kc), (name, mc)
+
+
+def test_hash_reduce_many_buckets(engine):
+    """Enough keys for several bucket passes and thousands of reduce tiles; hashed == sorted, row for row."""
+    d = generate_numpy(SynthSpec(n_sessions=150_000, seed=11))
+    s, a, t, y = d["session"], d["aid"], d["ts"], d["type"]
+    engine.load_events(s, a, t, y)
+    oa, ob, oc, emitted, _ = c_oracle.count_name(s, a, t, y, "click_to_click")
+    for name in ("click_to_click", "click_to_cart_or_buy"):
+        for mc in (1, 2, 3):
+            want = engine.count(name, min_count=mc, hashed=False)
+            p_sort = engine.count_info()["sort_passes"]
+            got = engine.count(name, min_count=mc, hashed=True)
+            ci = engine.count_info()
+            assert 1 <= ci["sort_passes"] < p_sort            # bucket bits only: fewer distribution passes
+            for x, z in zip(got.fetch(device=True), want.fetch(device=True)):
+                assert torch.equal(x, z)
+            if name == "click_to_click":
+                ka, kb, kc = c_oracle.merge_tables([(oa, ob, oc)], min_count=mc)
+                ga, gb, gc = got.fetch()
+                assert ci["n_pairs"] == emitted
+                assert np.array_equal(ga, ka) and np.array_equal(gb, kb) and np.array_equal(gc, kc)
+            got.free(); want.free()
+
+
+def test_hash_reduce_hot_pairs(engine):
+    """A pair repeated far beyond a tile: its bucket's tail is streamed by one CTA (warp-aggregated adds);
+    a bucket of many millions of keys raises the fallback flag and the sort path takes over.  Same table."""
+    for n, expect_fallback in ((2_000, False), (9_000, True)):
+        s = np.zeros(n); a = np.where(np.arange(n) % 2 == 0, 5, 9); y = np.zeros(n)
+        t = 1_660_000_000 + np.arange(n) % 40_000
+        # plus ordinary sessions so that ordinary buckets surround the hot ones
+        s2, a2, t2, y2 = small_events(5, n_sessions=300, n_aids=50)
+        S = np.concatenate([s, s2 + 1]); A = np.concatenate([a, a2]); T = np.concatenate([t, t2]); Y = np.concatenate([y, y2])
+        engine.load_events(S, A, T, Y)
+        want = engine.count("click_to_click", min_count=3, hashed=False)
+        p_sort = engine.count_info()["sort_passes"]
+        got = engine.count("click_to_click", min_count=3, hashed=True)
+        fell_back = engine.count_info()["sort_passes"] > p_sort
+        assert fell_back == expect_fallback
+        assert got.to_dict() == want.to_dict()
+        d = got.to_dict()
+        assert d[(5, 9)] == d[(9, 5)] and d[(5, 9)] >= (n // 2) ** 2
+
+
+@pytest.mark.parametrize("mc", [1, 3])
+def test_reduce_pairs_hashed(engine, mc):
+    """ottocov_reduce_pairs (the receive side of the multi-GPU exchange) with either reduce strategy."""
+    s, a, t, y = small_events(53, n_sessions=900, n_aids=300, max_len=50)
+    info = engine.load_events(s, a, t, y)
+    for name in ("click_to_click", "click_to_cart_or_buy"):
+        for R in (1, 4):
+            tabs = {}
+            for hashed in (False, True, None):
+                n_keys, sym = engine.expand_prepare(name, min_count=mc)
+                buf_a = torch.empty(max(n_keys, 1), dtype=torch.int64, device="cuda")
+                buf_b = torch.empty(max(n_keys, 1), dtype=torch.int64, device="cuda")
+                grouped, rows = engine.expand_run(R, buf_a, buf_b)
+                off = np.concatenate([[0], np.cumsum(rows)])
+                got = {}
+                for r in range(R):
+                    keys_r = grouped[off[r]:off[r + 1]].clone()
+                    half = engine.reduce_pairs(keys_r, keys_r.numel(), info["aid_bits"], mc, symmetric=sym,
+                                               strip_dest=R > 1, hashed=hashed)
+                    ha, hb, hc = half.fetch()
+                    assert np.all(np.diff(ha.astype(np.int64) << 32 | hb) > 0)       # sorted, distinct
+                    got.update(half.to_dict())
+                tabs[hashed] = got
+            assert tabs[True] == tabs[False] == tabs[None], (name, R, mc)
+
+
 # ---- BASELINE config 1: 100k-session synthetic slice, full pair table + top-20 ----------------------------------
 def test_config1_100k_sessions(engine):
     d = generate_numpy(SynthSpec(n_sessions=100_000, seed=42))

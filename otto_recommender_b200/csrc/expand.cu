@@ -25,7 +25,7 @@
 
 constexpr int EX_THREADS = 256;
 constexpr int EX_TILE = 2048;
-constexpr int EX_ITERS = EX_TILE / (2 * EX_THREADS);
+constexpr int EX_PER = EX_TILE / EX_THREADS;          // consecutive outputs per thread
 
 // first index in [0, start] with keys[idx] >= bound, given keys[i] >= bound for all i >= start
 __device__ __forceinline__ u32 lower_bound_back(const u64* __restrict__ keys, u32 start, u64 bound) {
@@ -144,75 +144,137 @@ __device__ __forceinline__ u64 make_pair_key(u32 a, u32 b, u32 n_dest, const Key
     return k;
 }
 
+// Persistent: CTA b writes tiles b, b + gridDim.x, ...  Per tile the records that own its outputs are staged in
+// shared memory; thread t then produces the EX_PER consecutive outputs [EX_PER t, EX_PER t + EX_PER): one binary
+// search for the first, a linear walk over the record offsets for the rest.  The keys go through a swizzled
+// shared-memory transpose and leave as 128-bit stores, 512 contiguous bytes per warp instruction.
+// ghist != nullptr: the digit histograms of the distribution passes that will sort these keys (pl) are
+// accumulated here, in shared memory while the keys are still in registers, and flushed once per CTA -- the
+// sort's own histogram kernel (one more read of every key) is not needed.
 template <bool SELF, bool CANON, bool MIX>
 __global__ void __launch_bounds__(EX_THREADS)
 expand_kernel(const u32* __restrict__ rec_src, const u32* __restrict__ rec_lo,
               const u64* __restrict__ rec_off, const u32* __restrict__ tile_rec,
               const u32* __restrict__ aid_src, const u32* __restrict__ aid_tgt, u64 out_begin,
-              u64 out_end, u64* __restrict__ dst, u32 n_dest, KeyMix mix) {
-    __shared__ u32 s_off[EX_TILE + 1];
-    __shared__ u32 s_lo[EX_TILE + 1];
-    __shared__ u32 s_aid[EX_TILE + 1];
+              u64 out_end, u64* __restrict__ dst, u32 n_dest, KeyMix mix, int64_t n_tiles, PassList pl,
+              u64* __restrict__ ghist) {
+    constexpr int PITCH = EX_TILE + 2;
+    __shared__ __align__(16) u32 s_buf[3 * PITCH];
     __shared__ u32 s_src[SELF ? EX_TILE + 1 : 1];
-
-    const u64 o0 = out_begin + (u64)blockIdx.x * EX_TILE;
-    const u32 n_out = (u32)min((u64)EX_TILE, out_end - o0);
-    const u32 r0 = tile_rec[blockIdx.x];
-    const u32 r1 = tile_rec[blockIdx.x + 1];          // record of the tile's last output (clamped)
-    // records that own outputs of this tile: r0 .. r_last, r_last = record of output o0 + n_out - 1
-    u32 r_last = r1;
-    if ((u64)blockIdx.x * EX_TILE + EX_TILE + out_begin < out_end) {
-        // tile_rec[b+1] is the record of the NEXT tile's first output; it owns outputs of this
-        // tile only if it starts before that output
-        if (rec_off[r1] >= o0 + n_out) r_last = r1 - 1;
-    }
-    const u32 n_rec = r_last - r0 + 1;                // <= EX_TILE (offsets strictly increase)
-
-    for (u32 j = threadIdx.x; j < n_rec; j += EX_THREADS) {
-        const u32 r = r0 + j;
-        const u64 off = rec_off[r];
-        const u32 src = rec_src[r];
-        u32 lo = rec_lo[r];
-        u32 rel;
-        if (off <= o0) { rel = 0; lo += (u32)(o0 - off); }   // only j == 0: skip outputs of earlier tiles
-        else rel = (u32)(off - o0);
-        s_off[j] = rel;
-        s_lo[j] = lo;
-        s_aid[j] = aid_src[src];
-        if (SELF) s_src[j] = src;
-    }
-    __syncthreads();
-
+    extern __shared__ u32 s_hist[];                   // [pl.n][RS_RADIX] when ghist
+    u32* s_off = s_buf;
+    u32* s_lo = s_buf + PITCH;
+    u32* s_aid = s_buf + 2 * PITCH;
+    u64* s_out = reinterpret_cast<u64*>(s_buf);       // [EX_TILE]: re-uses s_off / s_lo once the keys sit in registers
+    const bool hist = ghist != nullptr;
+    if (hist)
+        for (int j = threadIdx.x; j < pl.n * RS_RADIX; j += EX_THREADS) s_hist[j] = 0;
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-    u64* tile_dst = dst + (size_t)blockIdx.x * EX_TILE;
-#pragma unroll
-    for (int it = 0; it < EX_ITERS; ++it) {
-        const u32 k = (u32)it * (2 * EX_THREADS) + 2 * threadIdx.x;
-        if (k >= n_out) continue;
-        // last record with s_off <= k
-        u32 lo = 0, hi = n_rec;
-        while (hi - lo > 1) {
-            const u32 mid = (lo + hi) >> 1;
-            if (s_off[mid] <= k) lo = mid; else hi = mid;
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const u64 o0 = out_begin + (u64)tile * EX_TILE;
+        const u32 n_out = (u32)min((u64)EX_TILE, out_end - o0);
+        const u32 r0 = tile_rec[tile];
+        const u32 r1 = tile_rec[tile + 1];                // record of the tile's last output (clamped)
+        // records that own outputs of this tile: r0 .. r_last, r_last = record of output o0 + n_out - 1
+        u32 r_last = r1;
+        if ((u64)tile * EX_TILE + EX_TILE + out_begin < out_end) {
+            // tile_rec[t+1] is the record of the NEXT tile's first output; it owns outputs of this
+            // tile only if it starts before that output
+            if (rec_off[r1] >= o0 + n_out) r_last = r1 - 1;
         }
-        u32 j = lo;
-        u32 tgt = s_lo[j] + (k - s_off[j]);
-        if (SELF) tgt += (tgt >= s_src[j]);
-        const u64 key0 = make_pair_key<CANON, MIX>(s_aid[j], aid_tgt[tgt], n_dest, mix);
-        if (k + 1 < n_out) {
-            if (j + 1 < n_rec && s_off[j + 1] <= k + 1) ++j;
-            u32 tgt1 = s_lo[j] + (k + 1 - s_off[j]);
-            if (SELF) tgt1 += (tgt1 >= s_src[j]);
-            const u64 key1 = make_pair_key<CANON, MIX>(s_aid[j], aid_tgt[tgt1], n_dest, mix);
-            if (vec_ok) {
-                ulonglong2 v; v.x = key0; v.y = key1;
-                __stcs(reinterpret_cast<ulonglong2*>(tile_dst + k), v);
+        const u32 n_rec = r_last - r0 + 1;                // <= EX_TILE (offsets strictly increase)
+
+        for (u32 j = threadIdx.x; j < n_rec; j += EX_THREADS) {
+            const u32 r = r0 + j;
+            const u64 off = rec_off[r];
+            const u32 src = rec_src[r];
+            u32 lo = rec_lo[r];
+            u32 rel;
+            if (off <= o0) { rel = 0; lo += (u32)(o0 - off); }   // only j == 0: skip outputs of earlier tiles
+            else rel = (u32)(off - o0);
+            s_off[j] = rel;
+            s_lo[j] = lo;
+            s_aid[j] = aid_src[src];
+            if (SELF) s_src[j] = src;
+        }
+        __syncthreads();
+
+        u64 key[EX_PER];
+        const u32 k0 = (u32)EX_PER * threadIdx.x;
+        if (k0 < n_out) {
+            u32 lo = 0, hi = n_rec;                       // last record with s_off <= k0
+            while (hi - lo > 1) {
+                const u32 mid = (lo + hi) >> 1;
+                if (s_off[mid] <= k0) lo = mid; else hi = mid;
+            }
+            u32 j = lo;
+            u32 a = s_aid[j];
+            u32 tb = s_lo[j] - s_off[j];                  // target index = tb + k (mod 2^32)
+            u32 src = SELF ? s_src[j] : 0u;
+            u32 next_off = (j + 1 < n_rec) ? s_off[j + 1] : 0xFFFFFFFFu;
+#pragma unroll
+            for (int q = 0; q < EX_PER; ++q) {
+                const u32 k = k0 + q;
+                if (k < n_out) {
+                    if (k >= next_off) {                  // offsets strictly increase: at most one step per output
+                        ++j;
+                        a = s_aid[j];
+                        tb = s_lo[j] - s_off[j];
+                        if (SELF) src = s_src[j];
+                        next_off = (j + 1 < n_rec) ? s_off[j + 1] : 0xFFFFFFFFu;
+                    }
+                    u32 tgt = tb + k;
+                    if (SELF) tgt += (tgt >= src);
+                    key[q] = make_pair_key<CANON, MIX>(a, aid_tgt[tgt], n_dest, mix);
+                }
+            }
+            if (hist) {
+#pragma unroll
+                for (int q = 0; q < EX_PER; ++q) {
+                    if (k0 + q < n_out) {
+                        for (int p = 0; p < pl.n; ++p) {
+                            const u32 d = (u32)(key[q] >> pl.shift[p]) & ((1u << pl.bits[p]) - 1u);
+                            atomicAdd(&s_hist[p * RS_RADIX + d], 1u);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();                                  // every thread is done with the staged records
+        if (k0 < n_out) {
+#pragma unroll
+            for (int q = 0; q < EX_PER; ++q)              // output o sits at o ^ ((o >> 3) & 7): conflict-free read-back
+                if (k0 + q < n_out) s_out[k0 + (u32)(q ^ (int)(threadIdx.x & 7))] = key[q];
+        }
+        __syncthreads();
+        u64* tile_dst = dst + (size_t)tile * EX_TILE;
+#pragma unroll
+        for (int it = 0; it < EX_TILE / (2 * EX_THREADS); ++it) {
+            const u32 k = (u32)it * (2 * EX_THREADS) + 2 * threadIdx.x;
+            if (k >= n_out) continue;
+            const u32 m = (k >> 3) & 7u;
+            const u64 key0 = s_out[k ^ m];
+            if (k + 1 < n_out) {
+                const u64 key1 = s_out[(k + 1) ^ m];
+                if (vec_ok) {
+                    ulonglong2 v; v.x = key0; v.y = key1;
+                    __stcs(reinterpret_cast<ulonglong2*>(tile_dst + k), v);
+                } else {
+                    __stcs(tile_dst + k, key0);
+                    __stcs(tile_dst + k + 1, key1);
+                }
             } else {
                 __stcs(tile_dst + k, key0);
-                __stcs(tile_dst + k + 1, key1);
             }
-        } else {
-            __stcs(tile_dst + k, key0);
+        }
+        __syncthreads();                                  // s_buf is re-staged by the next tile
+    }
+    if (hist) {
+        __syncthreads();
+        for (int j = threadIdx.x; j < pl.n * RS_RADIX; j += EX_THREADS) {
+            const u32 c = s_hist[j];
+            if (c) atomicAdd(&ghist[j], (u64)c);
         }
     }
 }
@@ -308,10 +370,16 @@ static ExpandPlan* make_plan(ottocov_ctx* ctx, const ottocov_spec* spec, bool di
 // keys of plan outputs [c0, c1) -> dst[0 .. c1-c0).  n_dest > 1 also stamps hash(aid of the key) % n_dest
 // into key bits [56, 64) so one radix pass on those bits groups the keys by destination rank.
 // mix != nullptr: keys are written mixed (bucketed hash reduce), n_dest must be 0.
+// hist_passes + ghist (device, [passes][RS_RADIX], zeroed by the caller): also accumulate the digit histograms
+// of those distribution passes over the emitted keys.
 static void expand_range(ottocov_ctx* ctx, const ExpandPlan* pl, u64 c0, u64 c1, u64* dst_base, u32 n_dest,
-                         const KeyMix* mix = nullptr) {
+                         const KeyMix* mix = nullptr, const PassList* hist_passes = nullptr, u64* ghist = nullptr) {
     const TypeArray& src = ctx->ta[pl->A];
     const KeyMix mx = mix ? *mix : KeyMix();
+    PassList hp;
+    hp.n = 0;
+    if (hist_passes && ghist) hp = *hist_passes; else ghist = nullptr;
+    const size_t hist_smem = (size_t)hp.n * RS_RADIX * sizeof(u32);
     u64 seg_start = 0;
     for (Segment* sg : pl->segs) {
         const u64 seg_end = seg_start + sg->n_pairs;
@@ -326,9 +394,11 @@ static void expand_range(ottocov_ctx* ctx, const ExpandPlan* pl, u64 c0, u64 c1,
             const TypeArray& tgt = ctx->ta[sg->tgt_type];
             u64* dst = dst_base + (a - c0);
             const double bytes = 8.0 * (double)(oe - ob);
+            const unsigned grid = (unsigned)imin64(n_tiles, (int64_t)ctx->num_sms * 5);     // 5 CTAs / SM at 48 registers
 #define EX_LAUNCH(SELF_, CANON_, MIX_)                                                                              \
-            COV_LAUNCH(ctx, OTTOCOV_K_EXPAND, bytes, (expand_kernel<SELF_, CANON_, MIX_>), (unsigned)n_tiles, EX_THREADS, 0, \
-                       sg->rec_src.p, sg->rec_lo.p, sg->rec_off.p, tile_rec.p, src.aid, tgt.aid, ob, oe, dst, n_dest, mx)
+            COV_LAUNCH(ctx, OTTOCOV_K_EXPAND, bytes, (expand_kernel<SELF_, CANON_, MIX_>), grid, EX_THREADS, hist_smem,  \
+                       sg->rec_src.p, sg->rec_lo.p, sg->rec_off.p, tile_rec.p, src.aid, tgt.aid, ob, oe, dst, n_dest, mx, \
+                       n_tiles, hp, ghist)
             if (mix) {
                 if (pl->sym) EX_LAUNCH(false, true, true);
                 else if (sg->self) EX_LAUNCH(true, false, true);
@@ -393,11 +463,21 @@ ottocov_table* count_impl(ottocov_ctx* ctx, const ottocov_spec* spec) {
         DevBuf<u64> keys(ctx, cn), alt(ctx, cn);
         cov_trace(ctx, "count: alloc keys");
         if (hashed) {
-            expand_range(ctx, pl, c0, c1, keys.p, 0, &mix);
+            // the expansion also builds the digit histograms of the bucket passes (no extra read of the keys)
+            const int bb = hashed_bucket_bits((int64_t)cn, mix.kb);
+            BitField bucket_field[1] = {{mix.kb - bb, mix.kb}};
+            const PassList hp = make_pass_list(bucket_field, 1);
+            DevBuf<u64> ghist;
+            if (hp.n > 0 && cn > 1) {
+                ghist.alloc(ctx, (size_t)hp.n * RS_RADIX);
+                CUDA_CHECK(cudaMemsetAsync(ghist.p, 0, (size_t)hp.n * RS_RADIX * sizeof(u64), ctx->stream));
+            }
+            expand_range(ctx, pl, c0, c1, keys.p, 0, &mix, &hp, ghist.p);
             cov_trace(ctx, "count: expand (mixed keys)");
             int passes = 0;
             mirrored = sym && single;                  // the mirrored rows come out of the same table scan
-            ottocov_table* part = hashed_reduce(ctx, keys.p, alt.p, (int64_t)cn, mix, fused_min, sym, mirrored, &passes);
+            ottocov_table* part = hashed_reduce(ctx, keys.p, alt.p, (int64_t)cn, mix, fused_min, sym, mirrored, &passes,
+                                                ghist.p);
             partials.push_back(part);
             ci.sort_passes = passes;
             cov_trace(ctx, "count: bucket passes + hash reduce");

@@ -241,8 +241,21 @@ bool hashed_reduce_supported(int aid_bits) { return aid_bits >= 1 && 2 * aid_bit
 
 static size_t hr_smem_bytes(bool packed) { return (size_t)HR_CAP * 8 + (packed ? 0 : (size_t)HR_CAP * 4) + 32 * 4; }
 
+// bucket bits for n keys of kb bits: buckets of <= OTTOCOV_HR_AVG (default 512) keys on average
+int hashed_bucket_bits(int64_t n, int kb) {
+    static int64_t avg_target = 0;
+    if (!avg_target) {
+        const char* e = getenv("OTTOCOV_HR_AVG");                      // tuning knob
+        avg_target = e ? atoll(e) : 512;
+        if (avg_target < 16 || avg_target > 2048) avg_target = 512;
+    }
+    int bb = 0;
+    while (bb < kb && (n >> bb) > avg_target) ++bb;
+    return bb;
+}
+
 ottocov_table* hashed_reduce(ottocov_ctx* ctx, u64* keys, u64* alt, int64_t n, const KeyMix& mix, u32 min_count,
-                             bool sym, bool mirror, int* passes_out) {
+                             bool sym, bool mirror, int* passes_out, u64* pre_hist) {
     ottocov_table* out = new ottocov_table();
     out->aid_bits = mix.ab;
     if (passes_out) *passes_out = 0;
@@ -250,23 +263,18 @@ ottocov_table* hashed_reduce(ottocov_ctx* ctx, u64* keys, u64* alt, int64_t n, c
     if (min_count < 1) min_count = 1;
     try {
         // ---- group the keys into buckets of <= avg_target keys on average (top bits of the mixed key) ----
-        static int64_t avg_target = 0;
-        static int force_fallback = 0, no_packed = 0;
-        if (!avg_target) {
-            const char* e = getenv("OTTOCOV_HR_AVG");                  // tuning knob
-            avg_target = e ? atoll(e) : 512;
-            if (avg_target < 16 || avg_target > 2048) avg_target = 512;
+        static int force_fallback = -1, no_packed = 0;
+        if (force_fallback < 0) {
             const char* f = getenv("OTTOCOV_HR_FORCE_FALLBACK");        // test knob: exercise the overflow path
             force_fallback = (f && atoi(f)) ? 1 : 0;
             const char* g = getenv("OTTOCOV_HR_NO_PACKED");             // test / tuning knob: wide table words
             no_packed = (g && atoi(g)) ? 1 : 0;
         }
-        int bb = 0;
-        while (bb < mix.kb && (n >> bb) > avg_target) ++bb;
+        const int bb = hashed_bucket_bits(n, mix.kb);
         const int rem_bits = mix.kb - bb;
         BitField bucket_field[1] = {{rem_bits, mix.kb}};
         u64* k = keys; u64* ka = alt; u32* v = nullptr; u32* va = nullptr;
-        const int passes = radix_sort_pairs(ctx, k, ka, v, va, n, bucket_field, 1);
+        const int passes = radix_sort_pairs(ctx, k, ka, v, va, n, bucket_field, 1, pre_hist);
         if (passes_out) *passes_out = passes;
 
         // ---- count inside the buckets ------------------------------------------------------------------------

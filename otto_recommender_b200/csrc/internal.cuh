@@ -202,11 +202,21 @@ COV_HD u64 key_mix_inv(const KeyMix& m, u64 h) {     // -> plain key aid << 32 |
 // ---- device building blocks (implemented in the .cu files) -------------------------------------
 // radix_sort.cu
 struct BitField { int lo, hi; };   // sort on key bits [lo, hi)
+constexpr int RS_MAX_BITS = 8;
+constexpr int RS_RADIX = 1 << RS_MAX_BITS;
+constexpr int RS_MAX_PASSES = 16;
+struct PassList {                  // the distribution passes a field list expands to (<= 8 bits each)
+    int n;
+    int shift[RS_MAX_PASSES];
+    int bits[RS_MAX_PASSES];
+};
+PassList make_pass_list(const BitField* fields, int n_fields);
 // Sorts n keys (+ optional payload) on the given fields, least significant field first.
 // keys/alt (and vals/valt) are a double buffer; on return `keys`/`vals` point at the sorted data.
-// Returns the number of radix passes it ran.
+// Returns the number of radix passes it ran.  pre_hist: optional device array [passes][RS_RADIX] of raw
+// digit counts of these keys (accumulated by whoever wrote them); saves the histogram read.
 int radix_sort_pairs(ottocov_ctx* ctx, u64*& keys, u64*& alt, u32*& vals, u32*& valt, int64_t n,
-                     const BitField* fields, int n_fields);
+                     const BitField* fields, int n_fields, u64* pre_hist = nullptr);
 
 void radix_partition_push(ottocov_ctx* ctx, const u64* keys, int64_t n, int shift, int bits,
                           const u64* ptr_base_host, int n_digits);
@@ -253,9 +263,12 @@ void partition_table_impl(ottocov_ctx* ctx, const ottocov_table* t, int n_ranks,
 // double buffer of n keys each and are used as scratch.  Returns the table of plain keys whose count is
 // >= min_count, sorted by key.  sym: keys are canonical half pairs (diagonal totals doubled); mirror
 // (sym only): also emit the transposed off-diagonal rows, i.e. return the full symmetric table.
+// The keys are first sorted on their top hashed_bucket_bits(n, mix.kb) bits, i.e. on the field
+// [mix.kb - bb, mix.kb); pre_hist (optional) = raw digit counts of exactly those passes (see radix_sort_pairs).
 bool hashed_reduce_supported(int aid_bits);
+int hashed_bucket_bits(int64_t n, int kb);
 ottocov_table* hashed_reduce(ottocov_ctx* ctx, u64* keys, u64* alt, int64_t n, const KeyMix& mix, u32 min_count,
-                             bool sym, bool mirror, int* passes_out);
+                             bool sym, bool mirror, int* passes_out, u64* pre_hist = nullptr);
 // plain keys (optionally with a destination stamp in bits 56..63) -> mixed keys, in place
 void mix_keys_inplace(ottocov_ctx* ctx, u64* keys, int64_t n, const KeyMix& mix, bool strip_dest);
 

@@ -23,19 +23,11 @@ constexpr int RS_THREADS = 256;
 constexpr int RS_IPT = 16;
 constexpr int RS_TILE = RS_THREADS * RS_IPT;   // 4096 keys = 32 KB
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_MAX_BITS = 8;
-constexpr int RS_RADIX = 1 << RS_MAX_BITS;
-constexpr int RS_MAX_PASSES = 16;
 
 constexpr u64 ST_VALUE_MASK = (1ull << 56) - 1;
 constexpr u64 ST_FLAG_AGG = 1ull << 62;
 constexpr u64 ST_FLAG_PREFIX = 2ull << 62;
 
-struct PassList {
-    int n;
-    int shift[RS_MAX_PASSES];
-    int bits[RS_MAX_PASSES];
-};
 
 // ---- histograms of every pass in one read ----------------------------------------------------------
 __global__ void __launch_bounds__(256) rs_histogram_kernel(const u64* __restrict__ keys, int64_t n,
@@ -353,8 +345,7 @@ static u32 next_epoch(ottocov_ctx* ctx) {
     return ++ctx->sweep_epoch;
 }
 
-int radix_sort_pairs(ottocov_ctx* ctx, u64*& keys, u64*& alt, u32*& vals, u32*& valt, int64_t n,
-                     const BitField* fields, int n_fields) {
+PassList make_pass_list(const BitField* fields, int n_fields) {
     PassList pl;
     pl.n = 0;
     for (int f = 0; f < n_fields; ++f) {
@@ -371,17 +362,29 @@ int radix_sort_pairs(ottocov_ctx* ctx, u64*& keys, u64*& alt, u32*& vals, u32*& 
             lo += b;
         }
     }
+    return pl;
+}
+
+// pre_hist (optional): device array [passes][RS_RADIX] of raw digit counts of exactly these keys and fields
+// (make_pass_list order), e.g. accumulated by the kernel that wrote the keys; it is scanned in place and
+// the histogram read of the keys is skipped.
+int radix_sort_pairs(ottocov_ctx* ctx, u64*& keys, u64*& alt, u32*& vals, u32*& valt, int64_t n,
+                     const BitField* fields, int n_fields, u64* pre_hist) {
+    const PassList pl = make_pass_list(fields, n_fields);
     if (n <= 1 || pl.n == 0) return 0;
     const bool has_vals = vals != nullptr;
 
-    DevBuf<u64> ghist(ctx, (size_t)pl.n * RS_RADIX);
-    CUDA_CHECK(cudaMemsetAsync(ghist.p, 0, (size_t)pl.n * RS_RADIX * sizeof(u64), ctx->stream));
-    {
+    DevBuf<u64> ghist;
+    u64* gh = pre_hist;
+    if (!gh) {
+        ghist.alloc(ctx, (size_t)pl.n * RS_RADIX);
+        gh = ghist.p;
+        CUDA_CHECK(cudaMemsetAsync(gh, 0, (size_t)pl.n * RS_RADIX * sizeof(u64), ctx->stream));
         int grid = (int)imin64(ceil_div64(n, 256 * 8), (int64_t)ctx->num_sms * 8);
         COV_LAUNCH(ctx, OTTOCOV_K_HIST, 8.0 * n, rs_histogram_kernel, grid, 256,
-                   (size_t)pl.n * RS_RADIX * sizeof(u32), keys, n, pl, ghist.p);
-        COV_LAUNCH(ctx, OTTOCOV_K_MISC, 0, rs_scan_hist_kernel, pl.n, RS_RADIX, 0, ghist.p);
+                   (size_t)pl.n * RS_RADIX * sizeof(u32), keys, n, pl, gh);
     }
+    COV_LAUNCH(ctx, OTTOCOV_K_MISC, 0, rs_scan_hist_kernel, pl.n, RS_RADIX, 0, gh);
 
     const int64_t n_tiles = ceil_div64(n, RS_TILE);
     ensure_sweep_state(ctx, (size_t)n_tiles * RS_RADIX);
@@ -408,7 +411,7 @@ int radix_sort_pairs(ottocov_ctx* ctx, u64*& keys, u64*& alt, u32*& vals, u32*& 
                 attr_done = true;                                                                           \
             }                                                                                               \
             COV_LAUNCH(ctx, OTTOCOV_K_SORT_PASS, pass_bytes, kern, (unsigned)n_tiles, RS_THREADS, smem, keys, alt, \
-                       (const u32*)vals, valt, n, pl.shift[p], bits, ghist.p + (size_t)p * RS_RADIX,        \
+                       (const u32*)vals, valt, n, pl.shift[p], bits, gh + (size_t)p * RS_RADIX,        \
                        (const u64*)nullptr, ctx->sweep_status, ctx->sweep_ticket + p, epoch);                                    \
         } while (0)
 #define RS_DISPATCH(HV)                                                                                     \

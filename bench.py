@@ -8,7 +8,9 @@ OTTO shape -- 12.9 M sessions, ~220 M events, 1.8 M aids (generator: otto_recomm
 SURVEY.md App. C).  One "step" = one pass of the hot path over that batch:
 
     raw event columns in HBM -> loader (order check / sort, dedup, split by type) -> window ranges ->
-    pair expansion -> radix sort -> run-length reduce -> threshold (count >= 10) -> segmented top-20
+    pair expansion (keys written through a bijective mix, bucket histograms fused in) -> 3 radix
+    distribution passes on the top hash bits -> bucketed hash reduce in shared memory with the threshold
+    (count >= 10) and the symmetric mirror fused in -> key sort of the survivors -> segmented top-20
 
 `value`  = emitted co-event pairs / device time, inputs resident in HBM (CUDA events, max over ranks).
 `e2e`    = same metric through the public Python API with HOST (pinned) event columns in and the
@@ -327,7 +329,7 @@ def run_ours(args):
     # ---- roofline of the dominant kernel (radix distribution pass) -------------------------------------
     peak, peak_src = _peaks()
     # achieved = algorithmic bytes of every distribution pass in the timed region / their CUDA-event time.
-    # The per-launch figures are those of the dominant launches (the 6 passes over this rank's keys:
+    # The per-launch figures are those of the dominant launches (the bucket passes over this rank's keys:
     # 16 B per key per pass), the same launch shape `traffic` was captured on with ncu.
     sp = stats["sort_pass"]
     achieved = sp["algo_bytes"] / (sp["ms"] * 1e-3) / 1e9 if sp["ms"] > 0 else 0.0

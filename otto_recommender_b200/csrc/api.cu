@@ -6,7 +6,7 @@
 static thread_local std::string g_create_error;
 
 static const char* k_family_names[OTTOCOV_K_FAMILIES] = {
-    "load", "window", "expand", "histogram", "sort_pass", "rle", "filter", "topk", "order", "partition", "misc"};
+    "load", "window", "expand", "histogram", "sort_pass", "reduce", "filter", "topk", "order", "partition", "misc"};
 
 void ottocov_ctx::begin(int family) {
     stats[family].launches += 1;

@@ -230,14 +230,13 @@ expand_kernel(const u32* __restrict__ rec_src, const u32* __restrict__ rec_lo,
                 }
             }
             if (hist) {
+                for (int p = 0; p < pl.n; ++p) {          // pass parameters are read once per pass, not per key
+                    const int sh = pl.shift[p];
+                    const u32 msk = (1u << pl.bits[p]) - 1u;
+                    u32* hrow = s_hist + p * RS_RADIX;
 #pragma unroll
-                for (int q = 0; q < EX_PER; ++q) {
-                    if (k0 + q < n_out) {
-                        for (int p = 0; p < pl.n; ++p) {
-                            const u32 d = (u32)(key[q] >> pl.shift[p]) & ((1u << pl.bits[p]) - 1u);
-                            atomicAdd(&s_hist[p * RS_RADIX + d], 1u);
-                        }
-                    }
+                    for (int q = 0; q < EX_PER; ++q)
+                        if (k0 + q < n_out) atomicAdd(&hrow[(u32)(key[q] >> sh) & msk], 1u);
                 }
             }
         }
@@ -530,18 +529,6 @@ void expand_prepare_impl(ottocov_ctx* ctx, const ottocov_spec* spec, int64_t* n_
     *symmetric = pl->sym ? 1 : 0;
 }
 
-__global__ void __launch_bounds__(256) dest_count_kernel(const u64* __restrict__ keys, int64_t n, u32 n_dest,
-                                                         unsigned long long* __restrict__ counts) {
-    __shared__ unsigned int s_c[256];
-    s_c[threadIdx.x] = 0;
-    __syncthreads();
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        atomicAdd(&s_c[(u32)(keys[i] >> 56)], 1u);
-    __syncthreads();
-    if (threadIdx.x < n_dest && s_c[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)s_c[threadIdx.x]);
-}
-
 void expand_run_impl(ottocov_ctx* ctx, int n_ranks, u64* buf_a, u64* buf_b, int* result_in_b, int64_t* rows_per_dest) {
     ExpandPlan* pl = static_cast<ExpandPlan*>(ctx->plan);
     if (!pl) COV_THROW(OTTOCOV_ERR_STATE, "ottocov_expand_run before ottocov_expand_prepare");
@@ -552,25 +539,28 @@ void expand_run_impl(ottocov_ctx* ctx, int n_ranks, u64* buf_a, u64* buf_b, int*
     for (int r = 0; r < n_ranks; ++r) rows_per_dest[r] = 0;
     const int64_t n = (int64_t)pl->P;
     if (n == 0) return;
-    expand_range(ctx, pl, 0, pl->P, buf_a, n_ranks > 1 ? (u32)n_ranks : 0u);
-    if (n_ranks == 1) { rows_per_dest[0] = n; return; }
-    // rows per destination, then ONE stable radix pass on the destination bits
-    DevBuf<unsigned long long> cnt(ctx, 256);
-    CUDA_CHECK(cudaMemsetAsync(cnt.p, 0, 256 * sizeof(unsigned long long), ctx->stream));
-    COV_LAUNCH(ctx, OTTOCOV_K_PARTITION, 8.0 * n, dest_count_kernel, (int)imin64(ceil_div64(n, 2048), (int64_t)ctx->num_sms * 8),
-               256, 0, buf_a, n, (u32)n_ranks, cnt.p);
-    unsigned long long h[256];
-    cov_readback(ctx, h, cnt.p, 256 * sizeof(unsigned long long));
+    if (n_ranks == 1) {
+        expand_range(ctx, pl, 0, pl->P, buf_a, 0u);
+        rows_per_dest[0] = n;
+        return;
+    }
+    // rows per destination = histogram of the stamp bits, accumulated by the expansion itself
+    int bits = 1;
+    while ((1 << bits) < n_ranks) ++bits;
+    BitField dest_field[1] = {{56, 56 + bits}};
+    const PassList dp = make_pass_list(dest_field, 1);
+    DevBuf<u64> cnt(ctx, RS_RADIX);
+    CUDA_CHECK(cudaMemsetAsync(cnt.p, 0, RS_RADIX * sizeof(u64), ctx->stream));
+    expand_range(ctx, pl, 0, pl->P, buf_a, (u32)n_ranks, nullptr, &dp, cnt.p);
+    unsigned long long h[RS_RADIX];
+    cov_readback(ctx, h, cnt.p, RS_RADIX * sizeof(u64));
     if (!buf_b) {                    // caller will push the keys itself (ottocov_push_keys): no local grouping
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
         for (int r = 0; r < n_ranks; ++r) rows_per_dest[r] = (int64_t)h[r];
         return;
     }
-    int bits = 1;
-    while ((1 << bits) < n_ranks) ++bits;
-    BitField f[1] = {{56, 56 + bits}};
     u64* k = buf_a; u64* ka = buf_b; u32* v = nullptr; u32* va = nullptr;
-    radix_sort_pairs(ctx, k, ka, v, va, n, f, 1);
+    radix_sort_pairs(ctx, k, ka, v, va, n, dest_field, 1, cnt.p);      // the counts double as the pass histogram
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     for (int r = 0; r < n_ranks; ++r) rows_per_dest[r] = (int64_t)h[r];
     *result_in_b = (k == buf_b) ? 1 : 0;
@@ -599,10 +589,15 @@ ottocov_table* reduce_pairs_impl(ottocov_ctx* ctx, u64* keys, int64_t n, int aid
     if (hashed) {
         delete out;
         const KeyMix mix = make_key_mix(aid_bits);
-        mix_keys_inplace(ctx, keys, n, mix, strip);     // the strip pass, now also mixing
+        const int bb = hashed_bucket_bits(n, mix.kb);
+        BitField bucket_field[1] = {{mix.kb - bb, mix.kb}};
+        const PassList hp = make_pass_list(bucket_field, 1);
+        DevBuf<u64> ghist(ctx, (size_t)(hp.n > 0 ? hp.n : 1) * RS_RADIX);
+        mix_keys_inplace(ctx, keys, n, mix, strip, hp, ghist.p);     // the strip pass, now also mixing + histograms
         DevBuf<u64> alt(ctx, n);
         int passes = 0;
-        out = hashed_reduce(ctx, keys, alt.p, n, mix, min_count > 1 ? min_count : 1, sym != 0, false, &passes);
+        out = hashed_reduce(ctx, keys, alt.p, n, mix, min_count > 1 ? min_count : 1, sym != 0, false, &passes,
+                            (hp.n > 0 && n > 1) ? ghist.p : nullptr);
         ctx->last_count.sort_passes = passes;
         ctx->last_count.n_chunks = 1;
         ctx->last_count.n_unique = out->n;

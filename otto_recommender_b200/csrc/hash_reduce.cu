@@ -125,9 +125,17 @@ hash_reduce_kernel(const u64* __restrict__ keys, int64_t n, int rem_bits, KeyMix
         k[r] = (i < t1) ? __ldcs(keys + i) : HR_NONE;
     }
     u64 kx = (t1 + tid < n) ? __ldcs(keys + t1 + tid) : HR_NONE;     // first slice past the tile end
-    for (int j = tid; j < HR_CAP; j += HR_THREADS) {
-        s_key[j] = HR_NONE;
-        if (!PACKED) s_cnt[j] = 0;
+    {
+        uint4* kv = reinterpret_cast<uint4*>(s_key);           // two slots per 128-bit store
+        const uint4 ones = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+#pragma unroll
+        for (int q = 0; q < HR_CAP / 2 / HR_THREADS; ++q) kv[tid + q * HR_THREADS] = ones;
+        if (!PACKED) {
+            uint4* cv = reinterpret_cast<uint4*>(s_cnt);
+            const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int q = 0; q < HR_CAP / 4 / HR_THREADS; ++q) cv[tid + q * HR_THREADS] = zero;
+        }
     }
     if (tid == 0) s_over = 0;
     __syncthreads();
@@ -168,16 +176,23 @@ hash_reduce_kernel(const u64* __restrict__ keys, int64_t n, int rem_bits, KeyMix
     }
     __syncthreads();
 
-    // table scan: two flag bits per slot (bit 0 keep, bit 1 also emit the mirrored row)
+    // table scan.  The kernel is bound by issued instructions, and at a threshold of 10 only a slot in a
+    // hundred survives: the first look at a slot is one 32-bit load of its count (an empty packed slot reads
+    // as the all-ones count, which no real count reaches) and a compare with the lowest count that could
+    // survive (half the threshold for a symmetric kind: a diagonal row counts twice); only candidates are
+    // decoded and un-mixed.  Two flag bits per slot: bit 0 keep, bit 1 also emit the mirrored row.
+    const u32 cand = SYM ? (min_count + 1u) / 2u : min_count;
     u32 bits = 0, emit = 0;
 #pragma unroll
     for (int q = 0; q < HR_SPT; ++q) {
         const int j = tid + q * HR_THREADS;
-        u64 h; u32 c;
-        if (hr_slot<PACKED>(s_key, s_cnt, j, base, &h, &c)) {
+        const u32 c = PACKED ? (reinterpret_cast<const u32*>(s_key + j)[0] & (u32)HR_CMASK) : s_cnt[j];
+        if (c >= cand && (!PACKED || c != (u32)HR_CMASK) && c != 0u) {
             u64 total = c;
             bool diag = false;
-            if (SYM && 2ull * total >= (u64)min_count) {   // un-mix only rows that can survive
+            if (SYM) {
+                u64 h; u32 c2;
+                hr_slot<PACKED>(s_key, s_cnt, j, base, &h, &c2);
                 const u64 plain = key_mix_inv(mix, h);
                 diag = (u32)(plain >> 32) == (u32)plain;
                 if (diag) total *= 2;                      // (a, a): both orders of each event pair
@@ -202,20 +217,19 @@ hash_reduce_kernel(const u64* __restrict__ keys, int64_t n, int rem_bits, KeyMix
     __syncthreads();
     if (s_over || blk_total == 0) return;
     u64 o = s_base + ex;
-#pragma unroll
-    for (int q = 0; q < HR_SPT; ++q) {
+    while (bits) {                                         // survivors only
+        const int q = (__ffs(bits) - 1) >> 1;
         const u32 f = (bits >> (2 * q)) & 3u;
-        if (f) {
-            const int j = tid + q * HR_THREADS;
-            u64 h; u32 c;
-            hr_slot<PACKED>(s_key, s_cnt, j, base, &h, &c);
-            const u64 plain = key_mix_inv(mix, h);
-            u64 total = c;
-            if (SYM && (u32)(plain >> 32) == (u32)plain) total *= 2;
-            const u32 c32 = (u32)(total > 0xFFFFFFFFull ? 0xFFFFFFFFull : total);
-            out_keys[o] = plain; out_count[o] = c32; ++o;
-            if (f & 2u) { out_keys[o] = (plain << 32) | (plain >> 32); out_count[o] = c32; ++o; }
-        }
+        bits &= ~(3u << (2 * q));
+        const int j = tid + q * HR_THREADS;
+        u64 h; u32 c;
+        hr_slot<PACKED>(s_key, s_cnt, j, base, &h, &c);
+        const u64 plain = key_mix_inv(mix, h);
+        u64 total = c;
+        if (SYM && (u32)(plain >> 32) == (u32)plain) total *= 2;
+        const u32 c32 = (u32)(total > 0xFFFFFFFFull ? 0xFFFFFFFFull : total);
+        out_keys[o] = plain; out_count[o] = c32; ++o;
+        if (f & 2u) { out_keys[o] = (plain << 32) | (plain >> 32); out_count[o] = c32; ++o; }
     }
 }
 
@@ -224,17 +238,36 @@ __global__ void __launch_bounds__(256) unmix_kernel(u64* __restrict__ keys, int6
     if (i < n) keys[i] = key_mix_inv(mix, keys[i]);
 }
 
-__global__ void __launch_bounds__(256) mix_kernel(u64* __restrict__ keys, int64_t n, KeyMix mix, u64 keep_mask) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const u64 k = keys[i] & keep_mask;
-    keys[i] = key_mix_fwd(mix, (u32)(k >> 32), (u32)k);
+// plain keys (optionally with a destination stamp) -> mixed keys in place; the digit histograms of the bucket
+// passes (pl) are accumulated in the same read, so the sort needs no histogram pass of its own
+__global__ void __launch_bounds__(256) mix_hist_kernel(u64* __restrict__ keys, int64_t n, KeyMix mix, u64 keep_mask,
+                                                       PassList pl, u64* __restrict__ ghist) {
+    extern __shared__ u32 s_hist[];                   // [pl.n][RS_RADIX]
+    for (int j = threadIdx.x; j < pl.n * RS_RADIX; j += blockDim.x) s_hist[j] = 0;
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const u64 k = keys[i] & keep_mask;
+        const u64 h = key_mix_fwd(mix, (u32)(k >> 32), (u32)k);
+        keys[i] = h;
+        for (int p = 0; p < pl.n; ++p)
+            atomicAdd(&s_hist[p * RS_RADIX + ((u32)(h >> pl.shift[p]) & ((1u << pl.bits[p]) - 1u))], 1u);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < pl.n * RS_RADIX; j += blockDim.x) {
+        const u32 c = s_hist[j];
+        if (c) atomicAdd(&ghist[j], (u64)c);
+    }
 }
 
-void mix_keys_inplace(ottocov_ctx* ctx, u64* keys, int64_t n, const KeyMix& mix, bool strip_dest) {
+// ghist: device [pl.n][RS_RADIX], zeroed here; pass it to hashed_reduce as pre_hist
+void mix_keys_inplace(ottocov_ctx* ctx, u64* keys, int64_t n, const KeyMix& mix, bool strip_dest, const PassList& pl,
+                      u64* ghist) {
     if (n <= 0) return;
-    COV_LAUNCH(ctx, OTTOCOV_K_PARTITION, 16.0 * n, mix_kernel, (unsigned)ceil_div64(n, 256), 256, 0, keys, n, mix,
-               strip_dest ? 0x00FFFFFFFFFFFFFFull : ~0ull);
+    if (pl.n > 0) CUDA_CHECK(cudaMemsetAsync(ghist, 0, (size_t)pl.n * RS_RADIX * sizeof(u64), ctx->stream));
+    const int grid = (int)imin64(ceil_div64(n, 256 * 8), (int64_t)ctx->num_sms * 8);
+    COV_LAUNCH(ctx, OTTOCOV_K_PARTITION, 16.0 * n, mix_hist_kernel, grid, 256, (size_t)pl.n * RS_RADIX * sizeof(u32), keys, n,
+               mix, strip_dest ? 0x00FFFFFFFFFFFFFFull : ~0ull, pl, ghist);
 }
 
 bool hashed_reduce_supported(int aid_bits) { return aid_bits >= 1 && 2 * aid_bits <= 56; }

@@ -269,8 +269,10 @@ bool hashed_reduce_supported(int aid_bits);
 int hashed_bucket_bits(int64_t n, int kb);
 ottocov_table* hashed_reduce(ottocov_ctx* ctx, u64* keys, u64* alt, int64_t n, const KeyMix& mix, u32 min_count,
                              bool sym, bool mirror, int* passes_out, u64* pre_hist = nullptr);
-// plain keys (optionally with a destination stamp in bits 56..63) -> mixed keys, in place
-void mix_keys_inplace(ottocov_ctx* ctx, u64* keys, int64_t n, const KeyMix& mix, bool strip_dest);
+// plain keys (optionally with a destination stamp in bits 56..63) -> mixed keys, in place; also fills ghist
+// (device, [pl.n][RS_RADIX]) with the digit counts of the passes in pl (hashed_reduce's pre_hist)
+void mix_keys_inplace(ottocov_ctx* ctx, u64* keys, int64_t n, const KeyMix& mix, bool strip_dest, const PassList& pl,
+                      u64* ghist);
 
 // topk.cu
 void topk_impl(ottocov_ctx* ctx, const ottocov_table* t, int k);

@@ -173,6 +173,20 @@ int ottocov_topk_fetch(ottocov_ctx* ctx, int32_t* aid_x, int32_t* n_valid, int32
 int ottocov_topk_lookup(ottocov_ctx* ctx, const int32_t* aids, int64_t n, int where, int32_t* n_valid,
                         int32_t* aid_y /*[n*k]*/, int32_t* cnt /*[n*k]*/);
 
+/* ---- popularity of aids inside session clusters: replaces, for ONE clustering, the body of
+ * model/count_popularity.py:56-85 -- groupby([cluster, aid]) with six counts (clicks, carts, orders; all time and
+ * ts > ts_recent, the reference's 7-day horizon :54), rank('ordinal', reverse=True).over(cluster) clipped to 999
+ * for each count (:73-75), filter(min(ranks) <= keep_top_k) (:81).  `cluster` is the per-EVENT cluster id
+ * (-1 = session without a cluster, the fill_null(-1) of :51); events are not de-duplicated (the reference does
+ * not either).  Ties: count descending, then aid ascending (the reference's tie order is unspecified).
+ * Rows come back ordered by (cluster, aid); ranks is [6][cap_rows] int16 in the reference's column order
+ * rank_clicks, rank_carts, rank_orders, rank_clicks_7d, rank_carts_7d, rank_orders_7d. */
+int ottocov_count_popularity(ottocov_ctx* ctx, const int32_t* cluster, const int32_t* aid, const int32_t* ts,
+                             const int8_t* type, int64_t n, int where, int32_t ts_recent, int keep_top_k,
+                             int64_t* n_rows);
+int ottocov_popularity_fetch(ottocov_ctx* ctx, int32_t* aid, int32_t* cluster, int16_t* ranks /*[6][cap_rows]*/,
+                             int64_t cap_rows, int where);
+
 /* ---- multi-GPU exchange support: stable partition of a table's rows by
  * dest = ottocov_hash_dest(aid, n_ranks) into caller-owned DEVICE buffers (the send buffers of
  * the all-to-all); rows_per_dest is a HOST array [n_ranks].  No reference counterpart (the

@@ -202,6 +202,7 @@ int ottocov_destroy(ottocov_ctx* ctx) {
     cudaSetDevice(ctx->device);
     free_events(ctx);
     free_topk(ctx);
+    free_popularity(ctx);
     free_plan(ctx);
     if (ctx->sweep_status) cudaFreeAsync(ctx->sweep_status, ctx->stream);
     for (auto& kv : ctx->live) cudaFreeAsync(kv.first, ctx->stream);    // tables the caller never freed
@@ -442,6 +443,24 @@ int ottocov_topk_lookup(ottocov_ctx* ctx, const int32_t* aids, int64_t n, int wh
     API_BEGIN(ctx)
     if (n < 0 || (n > 0 && (!aids || !n_valid || !aid_y || !cnt))) COV_THROW(OTTOCOV_ERR_ARG, "bad argument");
     topk_lookup_impl(ctx, aids, n, where, n_valid, aid_y, cnt);
+    API_END(ctx)
+}
+
+int ottocov_count_popularity(ottocov_ctx* ctx, const int32_t* cluster, const int32_t* aid, const int32_t* ts,
+                             const int8_t* type, int64_t n, int where, int32_t ts_recent, int keep_top_k, int64_t* n_rows) {
+    API_BEGIN(ctx)
+    if (n < 0 || keep_top_k < 1) COV_THROW(OTTOCOV_ERR_ARG, "bad argument");
+    if (n > 0 && (!cluster || !aid || !ts || !type)) COV_THROW(OTTOCOV_ERR_ARG, "NULL column");
+    if (where != OTTOCOV_HOST && where != OTTOCOV_DEVICE) COV_THROW(OTTOCOV_ERR_ARG, "bad `where`");
+    if (n >= (int64_t)0xFFFFFFFFll) COV_THROW(OTTOCOV_ERR_ARG, "at most 2^32-2 rows per call");
+    count_popularity_impl(ctx, cluster, aid, ts, type, n, where, ts_recent, keep_top_k);
+    if (n_rows) *n_rows = ctx->pop_n;
+    API_END(ctx)
+}
+
+int ottocov_popularity_fetch(ottocov_ctx* ctx, int32_t* aid, int32_t* cluster, int16_t* ranks, int64_t cap_rows, int where) {
+    API_BEGIN(ctx)
+    popularity_fetch_impl(ctx, aid, cluster, ranks, cap_rows, where);
     API_END(ctx)
 }
 

@@ -100,6 +100,12 @@ struct ottocov_ctx {
     int32_t* topk_nvalid = nullptr;
     int32_t* topk_aid_y = nullptr;
     int32_t* topk_cnt = nullptr;
+    // popularity result (popularity.cu): rows kept by the last ottocov_count_popularity
+    bool pop_valid = false;
+    int64_t pop_n = 0, pop_stride = 0;
+    int32_t* pop_aid = nullptr;
+    int32_t* pop_cl = nullptr;
+    int16_t* pop_rank = nullptr;       // [6][pop_stride]
 
     void begin(int family);
     void end(int family, double algo_bytes);
@@ -279,6 +285,12 @@ void topk_impl(ottocov_ctx* ctx, const ottocov_table* t, int k);
 void free_topk(ottocov_ctx* ctx);
 void topk_lookup_impl(ottocov_ctx* ctx, const int32_t* aids, int64_t n, int where, int32_t* n_valid, int32_t* aid_y,
                       int32_t* cnt);
+
+// popularity.cu
+void count_popularity_impl(ottocov_ctx* ctx, const int32_t* cluster, const int32_t* aid, const int32_t* ts,
+                           const int8_t* type, int64_t n, int where, int32_t ts_recent, int keep_top_k);
+void popularity_fetch_impl(ottocov_ctx* ctx, int32_t* aid, int32_t* cluster, int16_t* ranks, int64_t cap_rows, int where);
+void free_popularity(ottocov_ctx* ctx);
 
 // ---- small device helpers -------------------------------------------------------------------------
 #ifdef __CUDACC__

@@ -380,6 +380,35 @@ class Engine:
                                                   ac.ctypes.data))
         return nv, ay, ac
 
+    # ---- popularity inside session clusters (model/count_popularity.py:56-85) ---------------------------------
+    POPULARITY_RANK_COLUMNS = ("rank_clicks", "rank_carts", "rank_orders", "rank_clicks_7d", "rank_carts_7d",
+                               "rank_orders_7d")
+
+    def count_popularity(self, cluster, aid, ts, type_, ts_recent: int, keep_top_k: int = 20) -> Dict[str, np.ndarray]:
+        """groupby([cluster, aid]) with six counts (type x {all time, ts > ts_recent}), ordinal rank per cluster
+        (count desc, aid asc; clipped to 999) for each count, rows whose best rank is <= keep_top_k.
+        `cluster` is the per-event cluster id (-1 = none).  -> {'aid', 'cluster', rank_* (int16)}, rows ordered
+        by (cluster, aid)."""
+        pc, wc, kc = _as_col(cluster, np.int32, "int32")
+        pa, wa, ka = _as_col(aid, np.int32, "int32")
+        pt, wt, kt = _as_col(ts, np.int32, "int32")
+        py, wy, ky = _as_col(type_, np.int8, "int8")
+        if len({wc, wa, wt, wy}) != 1:
+            raise ValueError("all four columns must live on the same side (host or device)")
+        n = int(kc.shape[0])
+        rows = ctypes.c_int64()
+        self._sync_stream()
+        self._check(self._lib.ottocov_count_popularity(self._ctx, pc, pa, pt, py, n, wc, int(ts_recent), int(keep_top_k),
+                                                       ctypes.byref(rows)))
+        m = int(rows.value)
+        o_aid = np.empty(m, np.int32); o_cl = np.empty(m, np.int32); o_rank = np.empty((6, m), np.int16)
+        self._check(self._lib.ottocov_popularity_fetch(self._ctx, o_aid.ctypes.data, o_cl.ctypes.data, o_rank.ctypes.data,
+                                                       m, _lib.HOST))
+        out = {"aid": o_aid, "cluster": o_cl}
+        for i, name in enumerate(self.POPULARITY_RANK_COLUMNS):
+            out[name] = o_rank[i]
+        return out
+
     # ---- multi-GPU support ----------------------------------------------------------------------------------
     def partition(self, table: Table, n_ranks: int, keys_out_ptr: int, count_out_ptr: int) -> List[int]:
         rows = (ctypes.c_int64 * n_ranks)()

@@ -114,7 +114,71 @@ class ClockSampler:
                     reasons.add(nm)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
+
+
+class NvmlSampler:
+    """The same clocks + throttle reasons read in-process through NVML (what nvidia-smi itself calls), every
+    100 ms while the timed region runs.  A separate `nvidia-smi -lms` process queries a dozen fields per sample
+    and was measured to stall kernel launches and stream synchronisations on some hosts (a 32 ms step became
+    43-54 ms while it ran); three light NVML calls per sample do not."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, gpu_index: int = 0):
+        self.gpu = gpu_index
+        self.rows = []
+        self.t0 = self.t1 = None
+        self.ok = False
+        self._stop = threading.Event()
+
+    def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else self.gpu
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nv = pynvml
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.ok = False
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                self.rows.append((time.perf_counter(), sm, rs))
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
+
+    def stop(self):
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"], "source": "nvml"}
+        self._stop.set()
+        self.thread.join(timeout=1)
+        rows = [r for r in self.rows if self.t0 is None or (self.t0 - 0.05 <= r[0] <= (self.t1 or r[0]) + 0.05)]
+        if not rows:
+            rows = self.rows[-3:]
+        sm = sorted(r[1] for r in rows)
+        reasons = set()
+        for r in rows:
+            for bit, name in self.REASONS.items():
+                if r[2] & bit:
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.mx, "reasons": sorted(reasons),
+                "samples": len(sm), "source": "nvml (pynvml, 100 ms)"}
 
 
 # =====================================================================================================
@@ -240,9 +304,12 @@ def run_ours(args):
 
     # nvidia-smi is started BEFORE the warm-up (its NVML start-up stalls the driver for tens of ms) and
     # keeps sampling every 100 ms; only samples that arrive inside the timed region are reported.
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank) if args.clock_sampler == "smi" else NvmlSampler(local_rank)
     if rank == 0 and not args.no_clock_sampler:
         sampler.start()
+        if isinstance(sampler, NvmlSampler) and not sampler.ok:        # no pynvml: fall back to nvidia-smi
+            sampler = ClockSampler(local_rank)
+            sampler.start()
     for _ in range(args.warmup):
         ci, rows_f = step_device()
     barrier()
@@ -398,7 +465,9 @@ def main():
     ap.add_argument("--breakdown", action="store_true", help="per-API-call wall times on stderr")
     ap.add_argument("--exchange", default="push", choices=["push", "nccl"],
                     help="N > 1: fused partition + peer-store kernel over NVLink (push) or NCCL all-to-all (nccl)")
-    ap.add_argument("--no-clock-sampler", action="store_true", help="do not run nvidia-smi during the timed region")
+    ap.add_argument("--no-clock-sampler", action="store_true", help="do not sample clocks during the timed region")
+    ap.add_argument("--clock-sampler", default="nvml", choices=["nvml", "smi"],
+                    help="clocks + throttle reasons during the timed region: in-process NVML (default) or an nvidia-smi -lms process")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -101,6 +101,7 @@ void cov_free(ottocov_ctx* ctx, void* p) {
 }
 
 void cov_trim(ottocov_ctx* ctx) {
+    ctx->budget_cache = 0;
     for (CacheBlock& c : ctx->cache) cudaFreeAsync(c.p, ctx->stream);
     ctx->cache.clear();
     ctx->cached_bytes = 0;

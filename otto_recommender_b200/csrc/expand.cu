@@ -413,13 +413,17 @@ static void expand_range(ottocov_ctx* ctx, const ExpandPlan* pl, u64 c0, u64 c1,
     }
 }
 
-static u64 auto_budget(ottocov_ctx* ctx) {
+// cudaMemGetInfo is a driver round trip (it serialises with whatever else talks to the driver), and free + parked
+// bytes barely move between steps: the figure is cached per context and refreshed when a count would not fit it.
+static u64 auto_budget(ottocov_ctx* ctx, bool refresh) {
+    if (ctx->budget_cache && !refresh) return ctx->budget_cache;
     size_t free_b = 0, total_b = 0;
     CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
     // blocks parked in our cache count as free; 16 B per pair for the double buffer plus <= 12 B per
     // pair for the reduced table
     u64 budget = (u64)((double)(free_b + ctx->cached_bytes) * 0.6 / 28.0);
-    return budget < (1u << 20) ? (1u << 20) : budget;
+    ctx->budget_cache = budget < (1u << 20) ? (1u << 20) : budget;
+    return ctx->budget_cache;
 }
 
 ottocov_table* count_impl(ottocov_ctx* ctx, const ottocov_spec* spec) {
@@ -436,7 +440,8 @@ ottocov_table* count_impl(ottocov_ctx* ctx, const ottocov_spec* spec) {
     if (P == 0) { ci.n_chunks = 0; return make_empty_table(aid_bits); }
 
     // ---- chunking by pair budget ----------------------------------------------------------------------
-    u64 budget = spec->pair_budget > 0 ? (u64)spec->pair_budget : auto_budget(ctx);
+    u64 budget = spec->pair_budget > 0 ? (u64)spec->pair_budget : auto_budget(ctx, false);
+    if (spec->pair_budget <= 0 && P > budget) budget = auto_budget(ctx, true);      // before chunking, look again
     cov_trace(ctx, "count: budget");
     budget = (budget / EX_TILE) * EX_TILE;
     if (budget == 0) budget = EX_TILE;

@@ -95,6 +95,86 @@ __device__ __forceinline__ bool hr_slot(const u64* s_key, const u32* s_cnt, int 
     return true;
 }
 
+// Table scan + emit, called by every thread of the CTA (contains barriers).  The kernel is bound by issued
+// instructions, and at a threshold of 10 only a slot in a hundred survives: the first look at a slot is one
+// 32-bit load of its count (an empty packed slot reads as the all-ones count, which no real count reaches) and a
+// compare with the lowest count that could survive (half the threshold for a symmetric kind: a diagonal row
+// counts twice); only candidates are decoded and un-mixed.  Survivors are appended to the output with one global
+// atomic per CTA.  Returns false when the output buffer overflowed (flag raised; the caller gives up).
+template <bool SYM, bool PACKED>
+__device__ __forceinline__ bool hr_emit(const u64* s_key, const u32* s_cnt, u32* s_scan, unsigned long long* s_base, u32* s_over,
+                                        u64 base, const KeyMix& mix, u32 min_count, int mirror, u64* __restrict__ out_keys,
+                                        u32* __restrict__ out_count, unsigned long long* __restrict__ out_n, u64 out_cap,
+                                        u32* __restrict__ flags) {
+    const int tid = threadIdx.x;
+    const u32 cand = SYM ? (min_count + 1u) / 2u : min_count;
+    u32 bits = 0, emit = 0;                                // two flag bits per slot: keep, also emit the mirrored row
+#pragma unroll
+    for (int q = 0; q < HR_SPT; ++q) {
+        const int j = tid + q * HR_THREADS;
+        const u32 c = PACKED ? (reinterpret_cast<const u32*>(s_key + j)[0] & (u32)HR_CMASK) : s_cnt[j];
+        if (c >= cand && (!PACKED || c != (u32)HR_CMASK) && c != 0u) {
+            u64 total = c;
+            bool diag = false;
+            if (SYM) {
+                u64 h; u32 c2;
+                hr_slot<PACKED>(s_key, s_cnt, j, base, &h, &c2);
+                const u64 plain = key_mix_inv(mix, h);
+                diag = (u32)(plain >> 32) == (u32)plain;
+                if (diag) total *= 2;                      // (a, a): both orders of each event pair
+            }
+            if (total >= (u64)min_count) {
+                const bool two = SYM && mirror && !diag;
+                bits |= (two ? 3u : 1u) << (2 * q);
+                emit += two ? 2u : 1u;
+            }
+        }
+    }
+    u32 blk_total;
+    const u32 ex = block_exclusive_scan<u32, HR_THREADS>(emit, s_scan, &blk_total);
+    if (tid == 0) {
+        unsigned long long b = 0;
+        if (blk_total) {
+            b = atomicAdd(out_n, (unsigned long long)blk_total);
+            if (b + blk_total > out_cap) { atomicOr(flags, 2u); *s_over = 1; }
+        }
+        *s_base = b;
+    }
+    __syncthreads();
+    if (*s_over) return false;
+    u64 o = *s_base + ex;
+    while (bits) {                                         // survivors only
+        const int q = (__ffs(bits) - 1) >> 1;
+        const u32 f = (bits >> (2 * q)) & 3u;
+        bits &= ~(3u << (2 * q));
+        const int j = tid + q * HR_THREADS;
+        u64 h; u32 c;
+        hr_slot<PACKED>(s_key, s_cnt, j, base, &h, &c);
+        const u64 plain = key_mix_inv(mix, h);
+        u64 total = c;
+        if (SYM && (u32)(plain >> 32) == (u32)plain) total *= 2;
+        const u32 c32 = (u32)(total > 0xFFFFFFFFull ? 0xFFFFFFFFull : total);
+        out_keys[o] = plain; out_count[o] = c32; ++o;
+        if (f & 2u) { out_keys[o] = (plain << 32) | (plain >> 32); out_count[o] = c32; ++o; }
+    }
+    return true;
+}
+
+template <bool PACKED>
+__device__ __forceinline__ void hr_clear(u64* s_key, u32* s_cnt) {
+    const int tid = threadIdx.x;
+    uint4* kv = reinterpret_cast<uint4*>(s_key);           // two slots per 128-bit store
+    const uint4 ones = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+#pragma unroll
+    for (int q = 0; q < HR_CAP / 2 / HR_THREADS; ++q) kv[tid + q * HR_THREADS] = ones;
+    if (!PACKED) {
+        uint4* cv = reinterpret_cast<uint4*>(s_cnt);
+        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int q = 0; q < HR_CAP / 4 / HR_THREADS; ++q) cv[tid + q * HR_THREADS] = zero;
+    }
+}
+
 template <bool SYM, bool PACKED>
 __global__ void __launch_bounds__(HR_THREADS, PACKED ? 3 : 2)
 hash_reduce_kernel(const u64* __restrict__ keys, int64_t n, int rem_bits, KeyMix mix, u32 min_count, int mirror,
@@ -125,18 +205,7 @@ hash_reduce_kernel(const u64* __restrict__ keys, int64_t n, int rem_bits, KeyMix
         k[r] = (i < t1) ? __ldcs(keys + i) : HR_NONE;
     }
     u64 kx = (t1 + tid < n) ? __ldcs(keys + t1 + tid) : HR_NONE;     // first slice past the tile end
-    {
-        uint4* kv = reinterpret_cast<uint4*>(s_key);           // two slots per 128-bit store
-        const uint4 ones = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-#pragma unroll
-        for (int q = 0; q < HR_CAP / 2 / HR_THREADS; ++q) kv[tid + q * HR_THREADS] = ones;
-        if (!PACKED) {
-            uint4* cv = reinterpret_cast<uint4*>(s_cnt);
-            const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-            for (int q = 0; q < HR_CAP / 4 / HR_THREADS; ++q) cv[tid + q * HR_THREADS] = zero;
-        }
-    }
+    hr_clear<PACKED>(s_key, s_cnt);
     if (tid == 0) s_over = 0;
     __syncthreads();
 
@@ -176,60 +245,72 @@ hash_reduce_kernel(const u64* __restrict__ keys, int64_t n, int rem_bits, KeyMix
     }
     __syncthreads();
 
-    // table scan.  The kernel is bound by issued instructions, and at a threshold of 10 only a slot in a
-    // hundred survives: the first look at a slot is one 32-bit load of its count (an empty packed slot reads
-    // as the all-ones count, which no real count reaches) and a compare with the lowest count that could
-    // survive (half the threshold for a symmetric kind: a diagonal row counts twice); only candidates are
-    // decoded and un-mixed.  Two flag bits per slot: bit 0 keep, bit 1 also emit the mirrored row.
-    const u32 cand = SYM ? (min_count + 1u) / 2u : min_count;
-    u32 bits = 0, emit = 0;
+    hr_emit<SYM, PACKED>(s_key, s_cnt, s_scan, &s_base, &s_over, base, mix, min_count, mirror, out_keys, out_count, out_n,
+                         out_cap, flags);
+}
+
+// ---- big-bucket variant ---------------------------------------------------------------------------------------
+// One distribution pass costs as much as this whole kernel, so when TWO passes can already bring the buckets
+// down to ~12 K keys the third pass is dropped and the bucket is finished here instead: one CTA per bucket
+// (boundaries from a binary search per bucket), the bucket is walked 2^sub_bits times and round r counts only the
+// keys whose next sub_bits hash bits equal r -- each round's keys fit the same 8192-slot table.  The repeated
+// reads come from L2 (a bucket is ~90 KB); the number of shared-memory atomics, which bounds the kernel, is the
+// same one per key.
+constexpr int64_t HB_MAX_BUCKET = 4000000;       // keys; beyond that (a hot pair) the sort path serves the call
+static_assert(HB_MAX_BUCKET < (int64_t)HR_CMASK, "count field too narrow for a big bucket");
+
+__global__ void __launch_bounds__(256) bucket_bounds_kernel(const u64* __restrict__ keys, int64_t n, int rem_bits, int64_t nb,
+                                                            u32* __restrict__ bounds) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > nb) return;
+    if (b == nb) { bounds[b] = (u32)n; return; }
+    const u64 target = (u64)b << rem_bits;
+    int64_t lo = 0, hi = n;                                // first index with keys >= target
+    while (lo < hi) {
+        const int64_t mid = lo + ((hi - lo) >> 1);
+        if (keys[mid] >= target) hi = mid; else lo = mid + 1;
+    }
+    bounds[b] = (u32)lo;
+}
+
+template <bool SYM>
+__global__ void __launch_bounds__(HR_THREADS, 3)
+hash_reduce_big_kernel(const u64* __restrict__ keys, const u32* __restrict__ bounds, int rem_bits, int sub_bits, KeyMix mix,
+                       u32 min_count, int mirror, u64* __restrict__ out_keys, u32* __restrict__ out_count,
+                       unsigned long long* __restrict__ out_n, u64 out_cap, u32* __restrict__ flags) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    u64* s_key = reinterpret_cast<u64*>(s_raw);                              // [HR_CAP] packed words
+    u32* s_scan = reinterpret_cast<u32*>(s_key + HR_CAP);                    // [HR_THREADS / 32 + 1]
+    __shared__ unsigned long long s_base;
+    __shared__ u32 s_over;
+    const int tid = threadIdx.x;
+    const int64_t s0 = bounds[blockIdx.x], e0 = bounds[blockIdx.x + 1];
+    if (s0 == e0) return;
+    if (e0 - s0 > HB_MAX_BUCKET) { if (tid == 0) atomicOr(flags, 4u); return; }
+    const u64 base = (u64)blockIdx.x << rem_bits;
+    const int rounds = 1 << sub_bits;
+    const int sub_shift = rem_bits - sub_bits;
+    if (tid == 0) s_over = 0;
+    for (int round = 0; round < rounds; ++round) {
+        hr_clear<true>(s_key, nullptr);
+        __syncthreads();
+        for (int64_t c0 = s0; c0 < e0; c0 += HR_TILE) {
+            u64 k[HR_IPT];
 #pragma unroll
-    for (int q = 0; q < HR_SPT; ++q) {
-        const int j = tid + q * HR_THREADS;
-        const u32 c = PACKED ? (reinterpret_cast<const u32*>(s_key + j)[0] & (u32)HR_CMASK) : s_cnt[j];
-        if (c >= cand && (!PACKED || c != (u32)HR_CMASK) && c != 0u) {
-            u64 total = c;
-            bool diag = false;
-            if (SYM) {
-                u64 h; u32 c2;
-                hr_slot<PACKED>(s_key, s_cnt, j, base, &h, &c2);
-                const u64 plain = key_mix_inv(mix, h);
-                diag = (u32)(plain >> 32) == (u32)plain;
-                if (diag) total *= 2;                      // (a, a): both orders of each event pair
+            for (int r = 0; r < HR_IPT; ++r) {
+                const int64_t i = c0 + r * HR_THREADS + tid;
+                k[r] = (i < e0) ? __ldg(keys + i) : HR_NONE;       // re-read every round: keep the lines in L2
             }
-            if (total >= (u64)min_count) {
-                const bool two = SYM && mirror && !diag;
-                bits |= (two ? 3u : 1u) << (2 * q);
-                emit += two ? 2u : 1u;
-            }
+#pragma unroll
+            for (int r = 0; r < HR_IPT; ++r)
+                if (k[r] != HR_NONE && (int)((k[r] >> sub_shift) & (u64)(rounds - 1)) == round)
+                    hr_insert<true>(s_key, nullptr, k[r], base, 1u, flags);
         }
-    }
-    u32 blk_total;
-    const u32 ex = block_exclusive_scan<u32, HR_THREADS>(emit, s_scan, &blk_total);
-    if (tid == 0) {
-        unsigned long long b = 0;
-        if (blk_total) {
-            b = atomicAdd(out_n, (unsigned long long)blk_total);
-            if (b + blk_total > out_cap) { atomicOr(flags, 2u); s_over = 1; }
-        }
-        s_base = b;
-    }
-    __syncthreads();
-    if (s_over || blk_total == 0) return;
-    u64 o = s_base + ex;
-    while (bits) {                                         // survivors only
-        const int q = (__ffs(bits) - 1) >> 1;
-        const u32 f = (bits >> (2 * q)) & 3u;
-        bits &= ~(3u << (2 * q));
-        const int j = tid + q * HR_THREADS;
-        u64 h; u32 c;
-        hr_slot<PACKED>(s_key, s_cnt, j, base, &h, &c);
-        const u64 plain = key_mix_inv(mix, h);
-        u64 total = c;
-        if (SYM && (u32)(plain >> 32) == (u32)plain) total *= 2;
-        const u32 c32 = (u32)(total > 0xFFFFFFFFull ? 0xFFFFFFFFull : total);
-        out_keys[o] = plain; out_count[o] = c32; ++o;
-        if (f & 2u) { out_keys[o] = (plain << 32) | (plain >> 32); out_count[o] = c32; ++o; }
+        __syncthreads();
+        if (!hr_emit<SYM, true>(s_key, nullptr, s_scan, &s_base, &s_over, base, mix, min_count, mirror, out_keys, out_count,
+                                out_n, out_cap, flags))
+            return;
+        __syncthreads();                                   // the table is cleared again by the next round
     }
 }
 
@@ -274,18 +355,43 @@ bool hashed_reduce_supported(int aid_bits) { return aid_bits >= 1 && 2 * aid_bit
 
 static size_t hr_smem_bytes(bool packed) { return (size_t)HR_CAP * 8 + (packed ? 0 : (size_t)HR_CAP * 4) + 32 * 4; }
 
-// bucket bits for n keys of kb bits: buckets of <= OTTOCOV_HR_AVG (default 512) keys on average
-int hashed_bucket_bits(int64_t n, int kb) {
+// How n mixed keys of kb bits are bucketed.
+//   small buckets (hash_reduce_kernel): <= OTTOCOV_HR_AVG (default 512) keys on average, tile-owned;
+//   big buckets (hash_reduce_big_kernel): <= 12288 keys on average, one CTA per bucket, 2^sub_bits rounds: it
+//   can save a distribution pass (742 M keys: 16 bucket bits = 2 passes instead of 21 = 3), but measured on the
+//   headline run the reduce then takes 10.7 ms instead of 5.4 (every key is looked at in each of the four rounds,
+//   four table scans per bucket) and the two 8-bit passes 4.9 ms each instead of 4.46: 21.1 ms against 19.3 ms.
+//   So it is opt-in: OTTOCOV_HR_MODE=2 takes big buckets whenever they are possible (the parity tests run
+//   with it in a child process), the default is small buckets.
+struct HashPlan { int bb; bool big; int sub_bits; };
+constexpr int64_t HB_AVG_BUCKET = 12288;
+constexpr int HB_SUB_BITS = 2;
+
+static HashPlan hashed_plan(int64_t n, int kb) {
     static int64_t avg_target = 0;
+    static int mode = 0;
     if (!avg_target) {
         const char* e = getenv("OTTOCOV_HR_AVG");                      // tuning knob
         avg_target = e ? atoll(e) : 512;
         if (avg_target < 16 || avg_target > 2048) avg_target = 512;
+        const char* m = getenv("OTTOCOV_HR_MODE");
+        mode = m ? atoi(m) : 0;
     }
-    int bb = 0;
-    while (bb < kb && (n >> bb) > avg_target) ++bb;
-    return bb;
+    HashPlan p;
+    p.big = false; p.sub_bits = 0; p.bb = 0;
+    while (p.bb < kb && (n >> p.bb) > avg_target) ++p.bb;
+    int bbig = 0;
+    while (bbig < kb && (n >> bbig) > HB_AVG_BUCKET) ++bbig;
+    const int passes_small = (p.bb + RS_MAX_BITS - 1) / RS_MAX_BITS, passes_big = (bbig + RS_MAX_BITS - 1) / RS_MAX_BITS;
+    const bool possible = kb <= HR_TAG_BITS && kb - bbig >= HB_SUB_BITS && n < (int64_t)0xFFFFFFFFll && bbig <= 20;
+    (void)passes_small; (void)passes_big;
+    if (mode == 2 && possible) {
+        p.bb = bbig; p.big = true; p.sub_bits = HB_SUB_BITS;
+    }
+    return p;
 }
+
+int hashed_bucket_bits(int64_t n, int kb) { return hashed_plan(n, kb).bb; }
 
 ottocov_table* hashed_reduce(ottocov_ctx* ctx, u64* keys, u64* alt, int64_t n, const KeyMix& mix, u32 min_count,
                              bool sym, bool mirror, int* passes_out, u64* pre_hist) {
@@ -303,7 +409,8 @@ ottocov_table* hashed_reduce(ottocov_ctx* ctx, u64* keys, u64* alt, int64_t n, c
             const char* g = getenv("OTTOCOV_HR_NO_PACKED");             // test / tuning knob: wide table words
             no_packed = (g && atoi(g)) ? 1 : 0;
         }
-        const int bb = hashed_bucket_bits(n, mix.kb);
+        const HashPlan plan = hashed_plan(n, mix.kb);
+        const int bb = plan.bb;
         const int rem_bits = mix.kb - bb;
         BitField bucket_field[1] = {{rem_bits, mix.kb}};
         u64* k = keys; u64* ka = alt; u32* v = nullptr; u32* va = nullptr;
@@ -333,8 +440,30 @@ ottocov_table* hashed_reduce(ottocov_ctx* ctx, u64* keys, u64* alt, int64_t n, c
             COV_LAUNCH(ctx, OTTOCOV_K_RLE, 8.0 * n, kern, grid, HR_THREADS, hr_smem_bytes(PACKED_), k, n, rem_bits,    \
                        mix, min_count, (SYM_ && mirror) ? 1 : 0, ok.p, oc.p, ctr.p, cap, flags);                      \
         } while (0)
-        if (sym) { if (packed) HR_LAUNCH(true, true); else HR_LAUNCH(true, false); }
-        else { if (packed) HR_LAUNCH(false, true); else HR_LAUNCH(false, false); }
+        if (plan.big) {
+            const int64_t nb = (int64_t)1 << bb;
+            DevBuf<u32> bounds(ctx, (size_t)nb + 1);
+            COV_LAUNCH(ctx, OTTOCOV_K_MISC, 0, bucket_bounds_kernel, (unsigned)ceil_div64(nb + 1, 256), 256, 0, k, n, rem_bits, nb,
+                       bounds.p);
+            static bool big_attr = false;
+            if (!big_attr) {
+                CUDA_CHECK(cudaFuncSetAttribute(hash_reduce_big_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hr_smem_bytes(true)));
+                CUDA_CHECK(cudaFuncSetAttribute(hash_reduce_big_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hr_smem_bytes(true)));
+                CUDA_CHECK(cudaFuncSetAttribute(hash_reduce_big_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+                CUDA_CHECK(cudaFuncSetAttribute(hash_reduce_big_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+                big_attr = true;
+            }
+            if (sym)
+                COV_LAUNCH(ctx, OTTOCOV_K_RLE, 8.0 * n, hash_reduce_big_kernel<true>, (unsigned)nb, HR_THREADS, hr_smem_bytes(true), k,
+                           bounds.p, rem_bits, plan.sub_bits, mix, min_count, mirror ? 1 : 0, ok.p, oc.p, ctr.p, cap, flags);
+            else
+                COV_LAUNCH(ctx, OTTOCOV_K_RLE, 8.0 * n, hash_reduce_big_kernel<false>, (unsigned)nb, HR_THREADS, hr_smem_bytes(true), k,
+                           bounds.p, rem_bits, plan.sub_bits, mix, min_count, 0, ok.p, oc.p, ctr.p, cap, flags);
+        } else if (sym) {
+            if (packed) HR_LAUNCH(true, true); else HR_LAUNCH(true, false);
+        } else {
+            if (packed) HR_LAUNCH(false, true); else HR_LAUNCH(false, false);
+        }
 #undef HR_LAUNCH
         unsigned long long h[2];
         cov_readback(ctx, h, ctr.p, sizeof(h));

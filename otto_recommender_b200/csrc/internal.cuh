@@ -92,6 +92,7 @@ struct ottocov_ctx {
     u32* scan_ticket = nullptr;
     u64* scan_totals = nullptr;        // [8] grand totals of the last scan launch
     void* pinned = nullptr;            // 4 KB page-locked landing pad for small device -> host read-backs
+    u64 budget_cache = 0;              // pair budget derived from free HBM (expand.cu::auto_budget); 0 = not computed
     void* plan = nullptr;              // ExpandPlan between ottocov_expand_prepare and ottocov_expand_run
     // top-k result
     int topk_k = 0;

@@ -19,9 +19,24 @@
 // 1.8 M aids -> 6 passes of 7 bits), not 64.
 #include "internal.cuh"
 
-constexpr int RS_THREADS = 256;
-constexpr int RS_IPT = 16;
-constexpr int RS_TILE = RS_THREADS * RS_IPT;   // 4096 keys = 32 KB
+#ifndef OTTOCOV_RS_THREADS
+#define OTTOCOV_RS_THREADS 256
+#endif
+constexpr int RS_THREADS = OTTOCOV_RS_THREADS;
+// Keys per thread = tile size / 256.  Measured on 742 M-key passes (experiments/README.md): 2.0 TB/s at 8, 2.66 at
+// 16, 2.92 at 32, 2.97 at 40 -- the per-tile costs (look-back round trip, scans over the warp histograms, five CTA
+// barriers) are amortised over more keys, and that outweighs the lower occupancy (128 registers, 2 CTAs/SM).
+// A (key, value) tile carries half again as many registers per item, so it stays smaller.
+#ifndef OTTOCOV_RS_IPT
+#define OTTOCOV_RS_IPT 40
+#endif
+#ifndef OTTOCOV_RS_IPT_PAIRS
+#define OTTOCOV_RS_IPT_PAIRS 16
+#endif
+constexpr int RS_IPT_KEYS = OTTOCOV_RS_IPT;
+constexpr int RS_IPT_PAIRS = OTTOCOV_RS_IPT_PAIRS;
+constexpr int rs_ipt(bool has_vals) { return has_vals ? RS_IPT_PAIRS : RS_IPT_KEYS; }
+constexpr int rs_tile(bool has_vals) { return RS_THREADS * rs_ipt(has_vals); }
 constexpr int RS_WARPS = RS_THREADS / 32;
 
 constexpr u64 ST_VALUE_MASK = (1ull << 56) - 1;
@@ -100,13 +115,13 @@ __device__ __forceinline__ u32 match_digit_ballot(u32 d) {
     return peers;
 }
 
-// Stable rank of each of the lane's RS_IPT keys inside the warp's 512-key segment (rows of 32 keys);
+// Stable rank of each of the lane's IPT keys inside the warp's 32 x IPT-key segment (rows of 32 keys);
 // bumps the warp's running digit counters.  FULL = every row is valid (all tiles but the last).
-template <int ALGO, int NB, bool FULL>
-__device__ __forceinline__ void rank_rows(const u64 (&key)[RS_IPT], int shift, u32 mask, u32 radix, int my_n, int lane,
-                                          u32 lt, u32* my_whist, u32* mm, u32 (&rnk2)[RS_IPT / 2]) {
+template <int ALGO, int NB, bool FULL, int IPT>
+__device__ __forceinline__ void rank_rows(const u64 (&key)[IPT], int shift, u32 mask, u32 radix, int my_n, int lane,
+                                          u32 lt, u32* my_whist, u32* mm, u32 (&rnk2)[IPT / 2]) {
 #pragma unroll
-    for (int i = 0; i < RS_IPT; ++i) {
+    for (int i = 0; i < IPT; ++i) {
         const bool valid = FULL || i < my_n;
         const u32 d = (u32)(key[i] >> shift) & mask;
         u32 peers;
@@ -142,22 +157,22 @@ __device__ __forceinline__ void rank_rows(const u64 (&key)[RS_IPT], int shift, u
 // experiments/README.md; 1 is the default):
 //   0  match.any            1  NB ballots (one per digit bit)            2  atomicOr on a per-warp mask table
 // phases A, D and F for one tile; FULL = all 4096 slots valid (every tile but the last): no predicates
-template <bool HAS_VALS, bool FULL>
+template <bool HAS_VALS, bool FULL, int IPT>
 __device__ __forceinline__ void load_rows(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in, int64_t lbase,
-                                          int my_n, u64 (&key)[RS_IPT], u32 (&val)[RS_IPT]) {
+                                          int my_n, u64 (&key)[IPT], u32 (&val)[IPT]) {
 #pragma unroll
-    for (int i = 0; i < RS_IPT; ++i) {
+    for (int i = 0; i < IPT; ++i) {
         const bool valid = FULL || i < my_n;
         key[i] = valid ? ld_stream_u64(keys_in + lbase + i * 32) : ~0ull;
         if (HAS_VALS) val[i] = valid ? __ldcs(vals_in + lbase + i * 32) : 0u;
     }
 }
 
-template <bool HAS_VALS, bool FULL>
-__device__ __forceinline__ void stage_rows(const u64 (&key)[RS_IPT], const u32 (&val)[RS_IPT], const u32 (&rnk2)[RS_IPT / 2],
+template <bool HAS_VALS, bool FULL, int IPT>
+__device__ __forceinline__ void stage_rows(const u64 (&key)[IPT], const u32 (&val)[IPT], const u32 (&rnk2)[IPT / 2],
                                            int shift, u32 mask, int my_n, const u32* my_whist, u64* s_keys, u32* s_vals) {
 #pragma unroll
-    for (int i = 0; i < RS_IPT; ++i) {
+    for (int i = 0; i < IPT; ++i) {
         if (FULL || i < my_n) {
             const u32 d = (u32)(key[i] >> shift) & mask;
             const u32 r = (i & 1) ? (rnk2[i >> 1] >> 16) : (rnk2[i >> 1] & 0xFFFFu);
@@ -170,12 +185,12 @@ __device__ __forceinline__ void stage_rows(const u64 (&key)[RS_IPT], const u32 (
 
 // s_gptr[d] = byte address of keys_out[global slot of the tile's first key of digit d] - 8 * (slot of that key in
 // the staging buffer), so the key staged at slot j goes to s_gptr[d] + 8 j: one 64-bit add per key.
-template <bool HAS_VALS, bool FULL>
+template <bool HAS_VALS, bool FULL, int IPT>
 __device__ __forceinline__ void write_rows(const u64* s_keys, const u32* s_vals, const u64* s_gptr, int shift, u32 mask,
                                            int tid, int tile_n, const u64* keys_out, u32* vals_out) {
     const u64 toff = (u64)tid * 8u;
 #pragma unroll
-    for (int i = 0; i < RS_IPT; ++i) {
+    for (int i = 0; i < IPT; ++i) {
         const int j = tid + i * RS_THREADS;
         if (FULL || j < tile_n) {
             const u64 k = s_keys[j];
@@ -191,21 +206,26 @@ __device__ __forceinline__ void write_rows(const u64* s_keys, const u32* s_vals,
 }
 
 #ifndef OTTOCOV_RS_MINB
-#define OTTOCOV_RS_MINB 4
+#define OTTOCOV_RS_MINB 2          // keys only: 40 keys per thread need the 128-register budget of 2 CTAs/SM
+#endif
+#ifndef OTTOCOV_RS_MINB_PAIRS
+#define OTTOCOV_RS_MINB_PAIRS 4    // (key, value) tiles of 4096: 64 registers, 4 CTAs/SM
 #endif
 template <bool HAS_VALS, int ALGO, int NB>
-__global__ void __launch_bounds__(RS_THREADS, OTTOCOV_RS_MINB)
+__global__ void __launch_bounds__(RS_THREADS, HAS_VALS ? OTTOCOV_RS_MINB_PAIRS : OTTOCOV_RS_MINB)
 rs_onesweep_kernel(const u64* __restrict__ keys_in, u64* __restrict__ keys_out,
                    const u32* __restrict__ vals_in, u32* __restrict__ vals_out, int64_t n, int shift,
                    int bits, const u64* __restrict__ digit_base, const u64* __restrict__ ptr_base, u64* status,
                    u32* ticket, u32 epoch) {
+    constexpr int IPT = HAS_VALS ? RS_IPT_PAIRS : RS_IPT_KEYS;
+    constexpr int RS_TILE = RS_THREADS * IPT;
     extern __shared__ __align__(16) unsigned char s_raw[];
     u64* s_keys = reinterpret_cast<u64*>(s_raw);                              // [RS_TILE]
     u32* s_whist = reinterpret_cast<u32*>(s_keys + RS_TILE);                  // [RS_WARPS][RS_RADIX]
     u32* s_dstart = s_whist + RS_WARPS * RS_RADIX;                            // [RS_RADIX]
     u64* s_gptr = reinterpret_cast<u64*>(s_dstart + RS_RADIX);                // [RS_RADIX]
-    u32* s_scan = reinterpret_cast<u32*>(s_gptr + RS_RADIX);                  // [RS_WARPS + 1] (+pad)
-    u32* s_tile = s_scan + 16;                                                // [1] (+pad to 16)
+    u32* s_scan = reinterpret_cast<u32*>(s_gptr + RS_RADIX);                  // [RS_WARPS + 1] (+pad to 48)
+    u32* s_tile = s_scan + 48;                                                // [1] (+pad to 16)
     u32* s_match = s_tile + 16;                                               // [RS_WARPS][RS_RADIX] if ALGO == 2
     u32* s_vals = s_match + (ALGO == 2 ? RS_WARPS * RS_RADIX : 0);            // [RS_TILE] if HAS_VALS
 
@@ -224,10 +244,10 @@ rs_onesweep_kernel(const u64* __restrict__ keys_in, u64* __restrict__ keys_out,
     const bool full = tile_n == RS_TILE;
 
     // -- A: load (warp-striped: every access is a coalesced 256 B row) ------------------------------
-    u64 key[RS_IPT];
-    u32 val[RS_IPT];
-    const int64_t lbase = tile_base + (int64_t)warp * 32 * RS_IPT + lane;
-    const int my_n = (int)min((int64_t)RS_IPT, (n - lbase + 31) / 32);        // valid items of this lane (may be <= 0)
+    u64 key[IPT];
+    u32 val[IPT];
+    const int64_t lbase = tile_base + (int64_t)warp * 32 * IPT + lane;
+    const int my_n = (int)min((int64_t)IPT, (n - lbase + 31) / 32);        // valid items of this lane (may be <= 0)
     if (full) load_rows<HAS_VALS, true>(keys_in, vals_in, lbase, my_n, key, val);
     else load_rows<HAS_VALS, false>(keys_in, vals_in, lbase, my_n, key, val);
 
@@ -237,7 +257,7 @@ rs_onesweep_kernel(const u64* __restrict__ keys_in, u64* __restrict__ keys_out,
     //       bumps the warp's running counter for the digit, no atomics needed.
     u32* my_whist = s_whist + warp * RS_RADIX;
     const u32 lt = lanemask_lt();
-    u32 rnk2[RS_IPT / 2];                       // two 16-bit ranks per register
+    u32 rnk2[IPT / 2];                       // two 16-bit ranks per register
     u32* mm = (ALGO == 2) ? s_match + warp * RS_RADIX : nullptr;
     if (full) rank_rows<ALGO, NB, true>(key, shift, mask, radix, my_n, lane, lt, my_whist, mm, rnk2);
     else rank_rows<ALGO, NB, false>(key, shift, mask, radix, my_n, lane, lt, my_whist, mm, rnk2);
@@ -307,15 +327,15 @@ rs_onesweep_kernel(const u64* __restrict__ keys_in, u64* __restrict__ keys_out,
     __syncthreads();
 
     // -- F: coalesced per-digit runs out --------------------------------------------------------------------
-    if (full) write_rows<HAS_VALS, true>(s_keys, s_vals, s_gptr, shift, mask, tid, tile_n, keys_out, vals_out);
-    else write_rows<HAS_VALS, false>(s_keys, s_vals, s_gptr, shift, mask, tid, tile_n, keys_out, vals_out);
+    if (full) write_rows<HAS_VALS, true, IPT>(s_keys, s_vals, s_gptr, shift, mask, tid, tile_n, keys_out, vals_out);
+    else write_rows<HAS_VALS, false, IPT>(s_keys, s_vals, s_gptr, shift, mask, tid, tile_n, keys_out, vals_out);
 }
 
 static size_t rs_smem_bytes(bool has_vals, int algo) {
-    size_t b = (size_t)RS_TILE * 8 + (size_t)RS_WARPS * RS_RADIX * 4 + RS_RADIX * 4 + RS_RADIX * 8 +
-               16 * 4 + 16 * 4;
+    size_t b = (size_t)rs_tile(has_vals) * 8 + (size_t)RS_WARPS * RS_RADIX * 4 + RS_RADIX * 4 + RS_RADIX * 8 +
+               48 * 4 + 16 * 4;
     if (algo == 2) b += (size_t)RS_WARPS * RS_RADIX * 4;
-    if (has_vals) b += (size_t)RS_TILE * 4;
+    if (has_vals) b += (size_t)rs_tile(true) * 4;
     return b;
 }
 
@@ -386,7 +406,7 @@ int radix_sort_pairs(ottocov_ctx* ctx, u64*& keys, u64*& alt, u32*& vals, u32*& 
     }
     COV_LAUNCH(ctx, OTTOCOV_K_MISC, 0, rs_scan_hist_kernel, pl.n, RS_RADIX, 0, gh);
 
-    const int64_t n_tiles = ceil_div64(n, RS_TILE);
+    const int64_t n_tiles = ceil_div64(n, rs_tile(has_vals));
     ensure_sweep_state(ctx, (size_t)n_tiles * RS_RADIX);
     CUDA_CHECK(cudaMemsetAsync(ctx->sweep_ticket, 0, RS_MAX_PASSES * sizeof(u32), ctx->stream));
 
@@ -406,7 +426,7 @@ int radix_sort_pairs(ottocov_ctx* ctx, u64*& keys, u64*& alt, u32*& vals, u32*& 
             auto kern = rs_onesweep_kernel<HV, AL, NBITS>;                                                  \
             static bool attr_done = false;                                                                  \
             if (!attr_done) {                                                                               \
-                CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(true, 2))); \
+                CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(HV, 2))); \
                 CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); \
                 attr_done = true;                                                                           \
             }                                                                                               \
@@ -441,16 +461,16 @@ void radix_partition_push(ottocov_ctx* ctx, const u64* keys, int64_t n, int shif
     u64 h[RS_RADIX];
     for (int d = 0; d < RS_RADIX; ++d) h[d] = d < n_digits ? ptr_base_host[d] : 0;
     CUDA_CHECK(cudaMemcpyAsync(pb.p, h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
-    const int64_t n_tiles = ceil_div64(n, RS_TILE);
+    const int64_t n_tiles = ceil_div64(n, rs_tile(false));
     ensure_sweep_state(ctx, (size_t)n_tiles * RS_RADIX);
     CUDA_CHECK(cudaMemsetAsync(ctx->sweep_ticket, 0, RS_MAX_PASSES * sizeof(u32), ctx->stream));
     const u32 epoch = next_epoch(ctx);
     auto kern = (bits <= 4) ? rs_onesweep_kernel<false, 1, 4> : rs_onesweep_kernel<false, 1, 8>;
     static bool attr_done = false;
     if (!attr_done) {
-        CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<false, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(true, 2)));
+        CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<false, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(false, 2)));
         CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<false, 1, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<false, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(true, 2)));
+        CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<false, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(false, 2)));
         CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<false, 1, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr_done = true;
     }

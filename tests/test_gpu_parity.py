@@ -503,6 +503,25 @@ def test_reduce_pairs_hashed(engine, mc):
             assert tabs[True] == tabs[False] == tabs[None], (name, R, mc)
 
 
+def test_hash_reduce_big_bucket_mode():
+    """The big-bucket variant (one CTA per ~12 K-key bucket, four rounds over the same shared-memory table) is
+    chosen automatically only at sizes where it saves a distribution pass (hundreds of millions of keys).
+    OTTOCOV_HR_MODE=2 prefers it whenever it is possible; the library reads the knob once per process, so the
+    hash-reduce, threshold, symmetric and exchange tests are re-run in a child process with it set."""
+    import subprocess
+    import sys
+    if os.environ.get("OTTOCOV_HR_MODE"):
+        pytest.skip("already inside the child run")
+    env = dict(os.environ, OTTOCOV_HR_MODE="2")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_parity.py"), "-q", "-x", "-m", "gpu",
+                        "-p", "no:cacheprovider", "-k",
+                        "hash_reduce_vs_oracle or hash_reduce_many or hash_reduce_hot or fused_threshold or symmetric_shortcut "
+                        "or exchange_first or reduce_pairs_hashed or arbitrary_specs"],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 # ---- BASELINE config 1: 100k-session synthetic slice, full pair table + top-20 ----------------------------------
 def test_config1_100k_sessions(engine):
     d = generate_numpy(SynthSpec(n_sessions=100_000, seed=42))

@@ -54,13 +54,14 @@ __device__ __forceinline__ u64 warp_bitonic_merge_desc(u64 v, int lane) {
 }
 
 __global__ void __launch_bounds__(256) topk_kernel(const u64* __restrict__ keys, const u32* __restrict__ count,
-                                                   const u64* __restrict__ seg_start, int64_t n_seg, int64_t n_rows,
-                                                   int k, int32_t* __restrict__ out_aid_x,
+                                                   const u64* __restrict__ seg_start, const u64* __restrict__ n_seg_dev,
+                                                   int64_t n_rows, int k, int32_t* __restrict__ out_aid_x,
                                                    int32_t* __restrict__ out_nvalid, int32_t* __restrict__ out_aid_y,
                                                    int32_t* __restrict__ out_cnt) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t n_seg = (int64_t)*n_seg_dev;          // written by the segment-head scan just before this launch
     for (int64_t s = warp0; s < n_seg; s += n_warps) {
         const int64_t a = (int64_t)seg_start[s];
         const int64_t b = (s + 1 < n_seg) ? (int64_t)seg_start[s + 1] : n_rows;
@@ -107,15 +108,16 @@ void topk_impl(ottocov_ctx* ctx, const ottocov_table* t, int k) {
     DevBuf<u64> seg_start(ctx, cap);
     SegmentHeads f;
     f.keys = t->keys; f.seg_start = seg_start.p;
-    u64 tot[1];
-    scan_apply(ctx, OTTOCOV_K_TOPK, f, t->n, tot, 8.0 * t->n);
-    const u64 n_seg = tot[0];
-    ctx->stats[OTTOCOV_K_TOPK].algo_bytes += 8.0 * (double)n_seg;
-    DevBuf<int32_t> ax(ctx, n_seg), nv(ctx, n_seg), ay(ctx, n_seg * k), ac(ctx, n_seg * k);
-    const int64_t warps_needed = (int64_t)n_seg;
-    int grid = (int)imin64(ceil_div64(warps_needed, 8), (int64_t)ctx->num_sms * 32);
-    COV_LAUNCH(ctx, OTTOCOV_K_TOPK, 12.0 * t->n + 8.0 * n_seg + 8.0 * k * n_seg, topk_kernel, grid, 256, 0,
-               t->keys, t->count, seg_start.p, (int64_t)n_seg, t->n, k, ax.p, nv.p, ay.p, ac.p);
+    // The number of segments stays on the device: the top-K kernel is enqueued right behind the scan with a grid
+    // and output buffers sized for the bound, and reads the count itself -- one host round trip less per call.
+    scan_apply(ctx, OTTOCOV_K_TOPK, f, t->n, nullptr, 8.0 * t->n);
+    DevBuf<int32_t> ax(ctx, cap), nv(ctx, cap), ay(ctx, cap * k), ac(ctx, cap * k);
+    int grid = (int)imin64(ceil_div64(cap, 8), (int64_t)ctx->num_sms * 32);
+    COV_LAUNCH(ctx, OTTOCOV_K_TOPK, 12.0 * t->n, topk_kernel, grid, 256, 0,
+               t->keys, t->count, seg_start.p, (const u64*)ctx->scan_totals, t->n, k, ax.p, nv.p, ay.p, ac.p);
+    u64 n_seg = 0;
+    cov_readback(ctx, &n_seg, ctx->scan_totals, sizeof(u64));
+    ctx->stats[OTTOCOV_K_TOPK].algo_bytes += 16.0 * (double)n_seg + 8.0 * k * (double)n_seg;
     ctx->topk_aid_x = ax.take(); ctx->topk_nvalid = nv.take();
     ctx->topk_aid_y = ay.take(); ctx->topk_cnt = ac.take();
     ctx->topk_n = (int64_t)n_seg;

@@ -214,6 +214,8 @@ int ottocov_destroy(ottocov_ctx* ctx) {
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (ProfEvent& pe : ctx->prof_pending) { if (pe.a) cudaEventDestroy(pe.a); if (pe.b) cudaEventDestroy(pe.b); }
     for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->sync_events) cudaEventDestroy(e);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     (void)cudaGetLastError();
     delete ctx;
     return OTTOCOV_OK;

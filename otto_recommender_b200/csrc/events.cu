@@ -146,6 +146,182 @@ static int bit_width_u64(u64 v) {
     return b;
 }
 
+// rows [base, base + n) of a functor defined on global row indices (one launch of a chained scan)
+template <class F>
+struct RowOffset {
+    static constexpr int NC = F::NC;
+    F f;
+    int64_t base;
+    __device__ u64 value(int64_t i) const { return f.value(i + base); }
+    __device__ void apply(int64_t i, u64 v, const u64* pre) const { f.apply(i + base, v, pre); }
+};
+
+// out[0..2] += rows of type 0..2, out[3] |= some type outside 0..2
+__global__ void __launch_bounds__(256) ev_type_count_kernel(const int8_t* __restrict__ type, int64_t n,
+                                                            unsigned long long* __restrict__ out) {
+    unsigned c0 = 0, c1 = 0, c2 = 0, bad = 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int y = type[i];
+        c0 += (y == 0); c1 += (y == 1); c2 += (y == 2);
+        if (y < 0 || y > 2) bad = 1;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+        c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+        c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+        bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (c0) atomicAdd(&out[0], (unsigned long long)c0);
+        if (c1) atomicAdd(&out[1], (unsigned long long)c1);
+        if (c2) atomicAdd(&out[2], (unsigned long long)c2);
+        if (bad) atomicOr(&out[3], 1ull);
+    }
+}
+
+
+// ---- host columns: copy and load overlapped ----------------------------------------------------------------
+// A 220 M-row load is 2.9 GB over PCIe (~52 ms) followed by ~4.5 ms of kernels.  The kernels only need rows
+// that have arrived, so for host input the copy is cut into chunks on a second stream and each chunk is
+// validated and split as soon as it lands:
+//   * the type column goes first (1 B/row) and is counted at once: that validates every type and gives the
+//     capacities of the per-type outputs before any other column has arrived;
+//   * chunk c of (session, aid, ts) is copied; behind an event, the main stream runs the statistics kernel and
+//     one launch of the dedup + split scan on its rows.  The scan is chained over the launches (scan.cuh
+//     carry_in), so output positions and cross-type ranks are exactly those of a single scan;
+//   * search keys use the fixed offset INT32_MIN for session and ts (the minima are not known yet; only
+//     differences of keys matter to the window search).
+// The split is optimistic: it assumes rows ordered by (session, ts).  If the statistics say otherwise (or the
+// data is invalid) its outputs are dropped and the caller continues with the general path on the device copies.
+constexpr int64_t EV_PIPE_MIN_ROWS = 4 << 20;
+constexpr int EV_PIPE_CHUNKS = 12;
+
+static bool load_events_pipelined(ottocov_ctx* ctx, const int32_t* h_session, const int32_t* h_aid, const int32_t* h_ts,
+                                  const int8_t* h_type, int64_t n, int32_t* d_session, int32_t* d_aid, int32_t* d_ts,
+                                  int8_t* d_type) {
+    if (!ctx->copy_stream) CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    cudaStream_t cs = ctx->copy_stream;
+    auto new_event = [&]() {
+        cudaEvent_t e;
+        if (!ctx->sync_events.empty()) { e = ctx->sync_events.back(); ctx->sync_events.pop_back(); }
+        else CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        return e;
+    };
+    std::vector<cudaEvent_t> used;
+    struct EventReturn {
+        ottocov_ctx* c; std::vector<cudaEvent_t>& v;
+        ~EventReturn() { for (cudaEvent_t e : v) c->sync_events.push_back(e); }
+    } event_return{ctx, used};
+
+    // the destination blocks may have been handed over by earlier work of the main stream: order the copies behind it
+    cudaEvent_t e0 = new_event(); used.push_back(e0);
+    CUDA_CHECK(cudaEventRecord(e0, ctx->stream));
+    CUDA_CHECK(cudaStreamWaitEvent(cs, e0, 0));
+
+    ctx->begin(OTTOCOV_K_LOAD);
+    CUDA_CHECK(cudaMemcpyAsync(d_type, h_type, n, cudaMemcpyHostToDevice, cs));
+    cudaEvent_t et = new_event(); used.push_back(et);
+    CUDA_CHECK(cudaEventRecord(et, cs));
+    int64_t b[EV_PIPE_CHUNKS + 1];
+    cudaEvent_t ec[EV_PIPE_CHUNKS];
+    for (int c = 0; c <= EV_PIPE_CHUNKS; ++c) b[c] = (n * c / EV_PIPE_CHUNKS) & ~(int64_t)31;
+    b[EV_PIPE_CHUNKS] = n;
+    for (int c = 0; c < EV_PIPE_CHUNKS; ++c) {
+        const int64_t m = b[c + 1] - b[c];
+        if (m > 0) {
+            CUDA_CHECK(cudaMemcpyAsync(d_session + b[c], h_session + b[c], m * 4, cudaMemcpyHostToDevice, cs));
+            CUDA_CHECK(cudaMemcpyAsync(d_aid + b[c], h_aid + b[c], m * 4, cudaMemcpyHostToDevice, cs));
+            CUDA_CHECK(cudaMemcpyAsync(d_ts + b[c], h_ts + b[c], m * 4, cudaMemcpyHostToDevice, cs));
+        }
+        ec[c] = new_event(); used.push_back(ec[c]);
+        CUDA_CHECK(cudaEventRecord(ec[c], cs));
+    }
+    ctx->end(OTTOCOV_K_LOAD, 13.0 * n);
+    ctx->stats[OTTOCOV_K_LOAD].launches -= 1;   // copies, not kernels
+    // From here on every exit path must leave the main stream behind the last copy (the caller goes on to use
+    // or free the device columns on it); an exception must not return to the caller while a copy still reads its
+    // host buffers.
+    struct JoinCopies {
+        ottocov_ctx* c; cudaEvent_t last; bool done = false;
+        ~JoinCopies() {
+            cudaStreamWaitEvent(c->stream, last, 0);
+            if (!done) cudaStreamSynchronize(c->copy_stream);
+        }
+    } join_copies{ctx, ec[EV_PIPE_CHUNKS - 1]};
+
+    // -- types: validity and per-type capacities -------------------------------------------------------------------
+    CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, et, 0));
+    DevBuf<unsigned long long> d_tc(ctx, 4);
+    CUDA_CHECK(cudaMemsetAsync(d_tc.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    COV_LAUNCH(ctx, OTTOCOV_K_LOAD, 1.0 * n, ev_type_count_kernel, (int)imin64(ceil_div64(n, 1024), (int64_t)ctx->num_sms * 8), 256, 0,
+               d_type, n, d_tc.p);
+    unsigned long long tc[4];
+    cov_readback(ctx, tc, d_tc.p, sizeof(tc));
+    if (tc[3]) { join_copies.done = true; return false; }       // the general path reports the error
+
+    DevBuf<u64> o_skey[3];
+    DevBuf<u32> o_aid[3], o_x0[3], o_x1[3];
+    SplitByType<true> f;
+    f.skey = nullptr; f.session = d_session; f.ts = d_ts; f.smin = INT32_MIN; f.tmin = INT32_MIN;
+    f.aid = reinterpret_cast<const u32*>(d_aid); f.type = d_type;
+    for (int t = 0; t < 3; ++t) {
+        const size_t cap = (size_t)tc[t];
+        o_skey[t].alloc(ctx, cap); o_aid[t].alloc(ctx, cap); o_x0[t].alloc(ctx, cap); o_x1[t].alloc(ctx, cap);
+        f.out[t].skey = o_skey[t].p; f.out[t].aid = o_aid[t].p;
+        f.out[t].xrank[0] = o_x0[t].p; f.out[t].xrank[1] = o_x1[t].p;
+        f.out[t].n = 0;
+    }
+    DevBuf<EvStats> d_st(ctx, 1);
+    DevBuf<u64> chain(ctx, 8);                  // two sets of 3 running totals, used alternately
+    COV_LAUNCH(ctx, OTTOCOV_K_MISC, 0, ev_stats_init_kernel, 1, 1, 0, d_st.p);
+    const u64* carry = nullptr;
+    int last = -1;
+    for (int c = 0; c < EV_PIPE_CHUNKS; ++c) {
+        const int64_t m = b[c + 1] - b[c];
+        CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ec[c], 0));
+        if (m <= 0) continue;
+        const int grid = (int)imin64(ceil_div64(m, 256), (int64_t)ctx->num_sms * 16);
+        // one row of overlap with the previous chunk: the order check compares every row with its predecessor
+        // (the extra row only repeats values the minima / maxima have already seen)
+        const int64_t o = b[c] > 0 ? b[c] - 1 : 0;
+        COV_LAUNCH(ctx, OTTOCOV_K_LOAD, 13.0 * m, ev_stats_kernel, grid, 256, 0, d_session + o, d_aid + o, d_ts + o, d_type + o,
+                   b[c + 1] - o, d_st.p);
+        RowOffset<SplitByType<true>> fo;
+        fo.f = f; fo.base = b[c];
+        u64* tout = chain.p + 4 * (c & 1);
+        scan_apply(ctx, OTTOCOV_K_LOAD, fo, m, nullptr, 13.0 * m + 20.0 * m, carry, tout);
+        carry = tout;
+        last = c;
+    }
+    EvStats st;
+    cov_readback(ctx, &st, d_st.p, sizeof(st));
+    join_copies.done = true;                                       // every copy was waited for and has completed
+    if (st.unsorted || st.amin < 0 || last < 0) return false;      // general path: sort first / report the error
+    u64 totals[3];
+    cov_readback(ctx, totals, chain.p + 4 * (last & 1), sizeof(totals));
+
+    ottocov_events_info& info = ctx->info;
+    info.session_min = st.smin; info.session_max = st.smax;
+    info.ts_min = st.tmin; info.ts_max = st.tmax;
+    info.aid_max = st.amax;
+    info.aid_bits = bit_width_u64((u64)st.amax);
+    if (info.aid_bits == 0) info.aid_bits = 1;
+    info.was_sorted = 1;
+    for (int t = 0; t < 3; ++t) {
+        ctx->ta[t].skey = o_skey[t].take();
+        ctx->ta[t].aid = o_aid[t].take();
+        ctx->ta[t].xrank[0] = o_x0[t].take();
+        ctx->ta[t].xrank[1] = o_x1[t].take();
+        ctx->ta[t].n = (int64_t)totals[t];
+        info.n_by_type[t] = (int64_t)totals[t];
+    }
+    info.n_events = (int64_t)(totals[0] + totals[1] + totals[2]);
+    ctx->loaded = true;
+    return true;
+}
+
 void free_events(ottocov_ctx* ctx) {
     for (int t = 0; t < 3; ++t) {
         dev_free(ctx, ctx->ta[t].skey);
@@ -173,7 +349,13 @@ void load_events_impl(ottocov_ctx* ctx, const int32_t* session, const int32_t* a
     // -- columns onto the device -----------------------------------------------------------------
     DevBuf<int32_t> d_session, d_aid, d_ts;
     DevBuf<int8_t> d_type;
-    if (where == OTTOCOV_HOST) {
+    static int no_pipeline = -1;
+    if (no_pipeline < 0) { const char* e = getenv("OTTOCOV_NO_LOAD_PIPELINE"); no_pipeline = (e && atoi(e)) ? 1 : 0; }
+    if (where == OTTOCOV_HOST && n >= EV_PIPE_MIN_ROWS && !no_pipeline) {
+        d_session.alloc(ctx, n); d_aid.alloc(ctx, n); d_ts.alloc(ctx, n); d_type.alloc(ctx, n);
+        if (load_events_pipelined(ctx, session, aid, ts, type, n, d_session.p, d_aid.p, d_ts.p, d_type.p)) return;
+        session = d_session.p; aid = d_aid.p; ts = d_ts.p; type = d_type.p;     // all four columns have arrived
+    } else if (where == OTTOCOV_HOST) {
         d_session.alloc(ctx, n); d_aid.alloc(ctx, n); d_ts.alloc(ctx, n); d_type.alloc(ctx, n);
         ctx->begin(OTTOCOV_K_LOAD);
         CUDA_CHECK(cudaMemcpyAsync(d_session.p, session, n * 4, cudaMemcpyHostToDevice, ctx->stream));

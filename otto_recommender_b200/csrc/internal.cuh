@@ -92,6 +92,8 @@ struct ottocov_ctx {
     u32* scan_ticket = nullptr;
     u64* scan_totals = nullptr;        // [8] grand totals of the last scan launch
     void* pinned = nullptr;            // 4 KB page-locked landing pad for small device -> host read-backs
+    cudaStream_t copy_stream = nullptr;        // host -> device column copies overlapped with the loader (events.cu)
+    std::vector<cudaEvent_t> sync_events;      // pool of timing-less events for cross-stream ordering
     u64 budget_cache = 0;              // pair budget derived from free HBM (expand.cu::auto_budget); 0 = not computed
     void* plan = nullptr;              // ExpandPlan between ottocov_expand_prepare and ottocov_expand_run
     // top-k result

@@ -93,10 +93,13 @@ __device__ __forceinline__ u64 warp_lookback_sum(u64* word, int64_t stride, int6
     return excl;
 }
 
-template <class F>
+// CHAINED: one logical scan cut into several launches (carry_in = inclusive totals of the earlier launches); a
+// separate instantiation so that the single-launch kernels compile exactly as before.
+template <class F, bool CHAINED>
 __global__ void __launch_bounds__(SCAN_THREADS, OTTOCOV_SCAN_MINB) scan_onepass_kernel(F f, int64_t n, int64_t n_tiles, u64* status,
                                                                      u32* ticket, u32 epoch,
-                                                                     u64* __restrict__ totals) {
+                                                                     u64* __restrict__ totals,
+                                                                     const u64* __restrict__ carry_in) {
     __shared__ u64 s_warp_tot[SCAN_THREADS / 32];
     __shared__ u64 s_tile_pref[SCAN_MAX_NC];
     __shared__ u32 s_tile;
@@ -133,7 +136,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, OTTOCOV_SCAN_MINB) scan_onepass_
         u64 mine = c[0];
 #pragma unroll
         for (int k = 1; k < F::NC; ++k) mine = (warp == k) ? c[k] : mine;
-        const u64 pre = warp_lookback_sum(status + tile * F::NC + warp, F::NC, tile, mine, epoch);
+        u64 pre = warp_lookback_sum(status + tile * F::NC + warp, F::NC, tile, mine, epoch);
+        if (CHAINED) pre += carry_in[warp];
         if (lane == 0) {
             s_tile_pref[warp] = pre;
             if (tile == n_tiles - 1) totals[warp] = pre + mine;
@@ -159,18 +163,25 @@ __global__ void __launch_bounds__(SCAN_THREADS, OTTOCOV_SCAN_MINB) scan_onepass_
 void scan_state_prepare(ottocov_ctx* ctx, size_t status_words, u32* epoch_out);     // reduce.cu
 
 // Host driver.  totals_host (may be nullptr) receives the NC grand totals and forces a stream sync.
+// carry_in / totals_out (device, [NC]): chain one logical scan over several launches -- a launch adds carry_in to
+// every prefix and writes its inclusive totals (carry included) to totals_out (default: ctx->scan_totals).
 template <class F>
 static void scan_apply(ottocov_ctx* ctx, int family, const F& f, int64_t n, u64* totals_host,
-                       double algo_bytes) {
+                       double algo_bytes, const u64* carry_in = nullptr, u64* totals_out = nullptr) {
     if (totals_host)
         for (int k = 0; k < F::NC; ++k) totals_host[k] = 0;
     if (n <= 0) return;
     const int64_t n_tiles = ceil_div64(n, SCAN_TILE);
     u32 epoch;
     scan_state_prepare(ctx, (size_t)n_tiles * F::NC, &epoch);
-    COV_LAUNCH(ctx, family, algo_bytes, (scan_onepass_kernel<F>), (unsigned)n_tiles, SCAN_THREADS, 0, f, n, n_tiles,
-               ctx->scan_status, ctx->scan_ticket, epoch, ctx->scan_totals);
+    u64* tout = totals_out ? totals_out : ctx->scan_totals;
+    if (carry_in)
+        COV_LAUNCH(ctx, family, algo_bytes, (scan_onepass_kernel<F, true>), (unsigned)n_tiles, SCAN_THREADS, 0, f, n, n_tiles,
+                   ctx->scan_status, ctx->scan_ticket, epoch, tout, carry_in);
+    else
+        COV_LAUNCH(ctx, family, algo_bytes, (scan_onepass_kernel<F, false>), (unsigned)n_tiles, SCAN_THREADS, 0, f, n, n_tiles,
+                   ctx->scan_status, ctx->scan_ticket, epoch, tout, (const u64*)nullptr);
     if (totals_host) {
-        cov_readback(ctx, totals_host, ctx->scan_totals, sizeof(u64) * F::NC);
+        cov_readback(ctx, totals_host, tout, sizeof(u64) * F::NC);
     }
 }

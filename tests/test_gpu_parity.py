@@ -522,6 +522,43 @@ def test_hash_reduce_big_bucket_mode():
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
+def test_pipelined_host_load(engine):
+    """Host columns of >= 4 M rows are copied in chunks on a second stream and validated / de-duplicated / split
+    chunk by chunk behind the copies (one scan chained over the launches).  Same arrays, same info and same
+    tables as the single-shot load of device-resident columns; unsorted or invalid input falls back."""
+    d = generate_numpy(SynthSpec(n_sessions=300_000, seed=21))
+    s, a, t, y = d["session"], d["aid"], d["ts"], d["type"]
+    assert len(s) >= 4 << 20
+    # sprinkle exact duplicates (also across chunk boundaries: every 1/12 of the rows) and keep (session, ts) order
+    rng = np.random.default_rng(3)
+    dup = np.sort(np.concatenate([rng.integers(0, len(s), 50_000), (len(s) * np.arange(1, 12) // 12) & ~31]))
+    idx = np.sort(np.concatenate([np.arange(len(s)), dup]))
+    s, a, t, y = s[idx], a[idx], t[idx], y[idx]
+    dev = [torch.from_numpy(x).cuda() for x in (s, a, t, y)]
+    info_d = engine.load_events(*dev)
+    want = {n: engine.count(n, min_count=2, hashed=False).fetch() for n in ("click_to_click", "click_to_cart_or_buy", "cart_to_buy")}
+    info_h = engine.load_events(s, a, t, y)                         # host arrays: the pipelined path
+    assert info_h == info_d and info_h["was_sorted"] == 1 and info_h["n_events"] < info_h["n_rows_in"]
+    for n, w in want.items():
+        for x, z in zip(engine.count(n, min_count=2, hashed=False).fetch(), w):
+            assert np.array_equal(x, z), n
+    # unsorted host input: the optimistic split is dropped, the general path sorts first
+    p = rng.permutation(len(s))
+    info_u = engine.load_events(s[p], a[p], t[p], y[p])
+    assert info_u["was_sorted"] == 0 and info_u["n_events"] == info_d["n_events"] and info_u["n_by_type"] == info_d["n_by_type"]
+    for x, z in zip(engine.count("click_to_cart_or_buy", min_count=2).fetch(), want["click_to_cart_or_buy"]):
+        assert np.array_equal(x, z)
+    # invalid input is still reported
+    bad = y.copy(); bad[len(bad) // 2] = 7
+    with pytest.raises(OttocovError) as e:
+        engine.load_events(s, a, t, bad)
+    assert e.value.code == -3
+    neg = a.copy(); neg[-5] = -1
+    with pytest.raises(OttocovError) as e:
+        engine.load_events(s, neg, t, y)
+    assert e.value.code == -3
+
+
 # ---- BASELINE config 1: 100k-session synthetic slice, full pair table + top-20 ----------------------------------
 def test_config1_100k_sessions(engine):
     d = generate_numpy(SynthSpec(n_sessions=100_000, seed=42))

@@ -132,11 +132,13 @@ struct SplitByType {
     __device__ void apply(int64_t i, u64 v, const u64* pre) const {
         if (!v) return;
         const int t = type[i];
-        const u64 pos = pre[t];
+        // selects instead of pre[(t + k) % 3]: a dynamically indexed array would live in local memory
+        const u64 p0 = pre[0], p1 = pre[1], p2 = pre[2];
+        const u64 pos = t == 0 ? p0 : (t == 1 ? p1 : p2);
         out[t].skey[pos] = key_at(i);
         out[t].aid[pos] = aid[i];
-        out[t].xrank[0][pos] = (u32)pre[(t + 1) % 3];
-        out[t].xrank[1][pos] = (u32)pre[(t + 2) % 3];
+        out[t].xrank[0][pos] = (u32)(t == 0 ? p1 : (t == 1 ? p2 : p0));
+        out[t].xrank[1][pos] = (u32)(t == 0 ? p2 : (t == 1 ? p0 : p1));
     }
 };
 

@@ -1,10 +1,8 @@
-# N=1 evidence run: GPU tests, default bench, reference arm, ncu launch list, ncu --set full of the two top kernels
+# N=1 evidence run: GPU tests, smoke, default bench, reference arm, ncu launch list (the --set full capture: _run_gpu_ncu.sh)
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -q -x --timeout 900 > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
 timeout 600 python bench.py > gpurun_out/bench_default.log 2> gpurun_out/bench_default.err; echo "bench exit $?"; python tools/show_bench.py gpurun_out/bench_default.log
-OTTOCOV_RS_ALGO=2 timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_algo2.log 2>/dev/null; echo "== algo2"; python tools/show_bench.py gpurun_out/bench_algo2.log | grep -E "ms/step|sort_pass"
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.log 2>&1; tail -c 300 gpurun_out/bench_reference.log
 CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-clock-sampler"
 timeout 300 $CMD > gpurun_out/plain_ll.log 2>&1 && timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_r01_final.csv $CMD > gpurun_out/ncu_ll.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'rs_onesweep_kernel|hash_reduce_kernel' -s 4 -c 4 -o gpurun_out/r01_final_top $CMD > gpurun_out/ncu_full.log 2>&1
-tail -2 gpurun_out/ncu_full.log

@@ -23,6 +23,9 @@
 #include "internal.cuh"
 #include "scan.cuh"
 
+#ifndef OTTOCOV_EX_DIRECT
+#define OTTOCOV_EX_DIRECT 0
+#endif
 constexpr int EX_THREADS = 256;
 constexpr int EX_TILE = 2048;
 constexpr int EX_PER = EX_TILE / EX_THREADS;          // consecutive outputs per thread
@@ -240,6 +243,25 @@ expand_kernel(const u32* __restrict__ rec_src, const u32* __restrict__ rec_lo,
                 }
             }
         }
+#if OTTOCOV_EX_DIRECT
+        // measured variant (experiments/README.md): 8 consecutive keys leave straight from the registers as four
+        // 128-bit stores per thread (64 B per thread, sectors half-filled per instruction, merged in L2)
+        {
+            u64* tile_dst = dst + (size_t)tile * EX_TILE;
+            if (k0 < n_out) {
+#pragma unroll
+                for (int q = 0; q < EX_PER; q += 2) {
+                    if (k0 + q + 1 < n_out && vec_ok) {
+                        ulonglong2 v; v.x = key[q]; v.y = key[q + 1];
+                        __stcs(reinterpret_cast<ulonglong2*>(tile_dst + k0 + q), v);
+                    } else {
+                        if (k0 + q < n_out) __stcs(tile_dst + k0 + q, key[q]);
+                        if (k0 + q + 1 < n_out) __stcs(tile_dst + k0 + q + 1, key[q + 1]);
+                    }
+                }
+            }
+        }
+#else
         __syncthreads();                                  // every thread is done with the staged records
         if (k0 < n_out) {
 #pragma unroll
@@ -267,6 +289,7 @@ expand_kernel(const u32* __restrict__ rec_src, const u32* __restrict__ rec_lo,
                 __stcs(tile_dst + k, key0);
             }
         }
+#endif
         __syncthreads();                                  // s_buf is re-staged by the next tile
     }
     if (hist) {

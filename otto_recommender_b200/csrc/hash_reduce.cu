@@ -11,17 +11,22 @@
 //      every copy of a key lies in one bucket;
 //   3. hash_reduce_kernel: a CTA owns the buckets that START inside its 4096-key tile (it skips the
 //      head of the tile that continues the previous CTA's bucket and reads past the tile end to finish
-//      its last bucket), counts their keys in a shared-memory open-addressing table (64-bit CAS on the
-//      key slot, 32-bit add on the count), then scans the table: rows with count >= min_count are
-//      un-mixed and appended to the output (one global atomic per CTA); for symmetric kinds the
-//      diagonal doubling and the mirrored row (b, a, c) are emitted in the same step;
+//      its last bucket), counts their keys in a shared-memory open-addressing table of packed words
+//      tag(42) | count(22) -- one 64-bit CAS claims AND counts a new key, one 32-bit add counts a
+//      repeated one -- then scans the table count-first: rows with count >= min_count are un-mixed and
+//      appended to the output (one global atomic per CTA); for symmetric kinds the diagonal doubling
+//      and the mirrored row (b, a, c) are emitted in the same step;
 //   4. the few surviving rows are sorted by plain key (they arrive in bucket order).
-// HBM traffic after the expansion: 8 P (histogram) + passes x 16 P + 8 P, against 8 P + 6 x 16 P + 8 P.
+// HBM traffic after the expansion: passes x 16 P + 8 P (the pass histograms come from the expansion),
+// against 8 P + 6 x 16 P + 8 P.  The kernel is bound by shared-memory atomics: one per key.
 //
 // The table holds DISTINCT keys only, so hot pairs (one key repeated millions of times) cost nothing
 // but the streaming read.  If a CTA ever meets more distinct keys than its table holds (needs an
-// adversarial input: buckets are balanced by the hash), it raises a flag and the host re-does the
-// reduce with the full sort (the mixed keys are un-mixed in place first).
+// adversarial input: buckets are balanced by the hash), a bucket tail runs past 2 M keys, or a tag
+// does not fit its field, a flag is raised and the host re-does the reduce with the full sort (the
+// mixed keys are un-mixed in place first).  Keys too wide for the packed word use an unpacked table
+// (64-bit key + 32-bit count); hash_reduce_big_kernel (one CTA per ~12 K-key bucket after one pass
+// less) is a measured, opt-in variant.
 #include "internal.cuh"
 #include "scan.cuh"
 

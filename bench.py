@@ -17,6 +17,7 @@ SURVEY.md App. C).  One "step" = one pass of the hot path over that batch:
            top-20 + thresholded pair table copied back to host inside the timed region.
 N > 1    = strong scaling: the same 220 M events, sessions range-sharded over the ranks, counts
            re-sharded by hash(aid) with an NCCL all-to-all (otto_recommender_b200/dist.py).
+--workload popularity = the popularity stage instead, one GPU, its own JSON line.
 --impl reference = the reference's CPU algorithm (pyarrow restatement of model/count_co_events.py,
            oracle/ref_restatement.py -- polars itself is not installable here) on all host cores, one
            100k-session part of the same workload per step.
@@ -456,6 +457,68 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# =====================================================================================================
+# --workload popularity: the popularity stage, same conventions, its own JSON line
+# =====================================================================================================
+def run_popularity(args):
+    """events/s through ottocov_count_popularity on the synthetic OTTO shape with the event columns resident in
+    HBM: general popularity (one cluster) and `--clusters` pseudo-clusters; the CPU restatement
+    (oracle/popularity_oracle.py, pandas, one core) timed on a bounded sample of the same events."""
+    import numpy as np
+    import torch
+    from otto_recommender_b200 import Engine
+    from otto_recommender_b200.synth import SynthSpec, generate
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    d = generate(SynthSpec(n_sessions=args.sessions, n_aids=N_AIDS, seed=42), dev)
+    s, a, t, y = d["session"], d["aid"], d["ts"], d["type"]
+    n = int(s.numel())
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+    cl_of_session = torch.randint(-1, args.clusters, (args.sessions,), generator=g, device=dev, dtype=torch.int32)
+    cols = {1: torch.zeros(n, dtype=torch.int32, device=dev), args.clusters: cl_of_session[s.long()].contiguous()}
+    ts_recent = int(t.max().item()) - 7 * 86400
+    eng = Engine(0)
+    runs = {}
+    for ncl, cl in cols.items():
+        for _ in range(max(args.warmup, 1)):
+            r = eng.count_popularity(cl, a, t, y, ts_recent=ts_recent, keep_top_k=TOP_K)
+        eng.kernel_stats(reset=True)
+        eng.set_profiling(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(args.steps):
+            r = eng.count_popularity(cl, a, t, y, ts_recent=ts_recent, keep_top_k=TOP_K)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        st = eng.kernel_stats(reset=True)
+        eng.set_profiling(False)
+        sp = st["sort_pass"]
+        runs[f"cl{ncl}"] = {"ms_per_step": ms, "events_per_s": n / (ms * 1e-3), "rows_kept": int(len(r["aid"])),
+                            "kernels_ms_per_step": {k: v["ms"] / args.steps for k, v in st.items() if v["launches"]},
+                            "sort_pass_algo_GBps": (sp["algo_bytes"] / (sp["ms"] * 1e-3) / 1e9) if sp["ms"] > 0 else None}
+    out = {"metric": "events/s (popularity counts + 6 ordinal ranks per cluster, top-20 kept)", "unit": "events/s",
+           "value": runs[f"cl{args.clusters}"]["events_per_s"], "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": runs[f"cl{args.clusters}"]["ms_per_step"], "higher_is_better": True, "dtype": "u64",
+           "data": "synthetic", "vs_baseline": None,
+           "config": {"workload": f"count_popularity: {args.sessions:,} sessions / {n:,} events / {N_AIDS:,} aids, "
+                                  f"{args.clusters} pseudo-clusters (and one cluster), keep_top_k {TOP_K}"},
+           "runs": runs}
+    if not args.no_cpu_baseline:
+        from oracle import popularity_oracle as po
+        m = min(n, args.cpu_sample_events)
+        hc = [x[:m].cpu().numpy() for x in (cols[args.clusters], a, t, y)]
+        t0 = time.perf_counter()
+        po.popularity_ranks_frame(*hc, keep_top_k=TOP_K, ts_recent=ts_recent)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": m / dt, "unit": "events/s", "cores": 1, "kind": "port",
+                               "sample": f"first {m:,} events, {args.clusters} clusters, oracle/popularity_oracle.py "
+                                         f"(pandas), {dt:.1f} s"}
+    print(json.dumps(out))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -471,8 +534,14 @@ def main():
     ap.add_argument("--no-clock-sampler", action="store_true", help="do not sample clocks during the timed region")
     ap.add_argument("--clock-sampler", default="nvml", choices=["nvml", "smi"],
                     help="clocks + throttle reasons during the timed region: in-process NVML (default) or an nvidia-smi -lms process")
+    ap.add_argument("--workload", default="cooc", choices=["cooc", "popularity"],
+                    help="cooc = the BASELINE.json metric (default); popularity = the popularity stage, N=1, its own JSON line")
+    ap.add_argument("--clusters", type=int, default=50, help="--workload popularity: pseudo-clusters")
+    ap.add_argument("--cpu-sample-events", type=int, default=10_000_000, help="--workload popularity: events of the CPU sample")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "popularity":
+        run_popularity(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -11,7 +11,7 @@ PARITY UNPINNED by the reference (it runs inside polars, ships no tests or fixtu
 instead by the hand-verified vector tests/golden/pop_events.json and by the agreement of the two restatements.
 The reference's ``rank('ordinal')`` breaks ties by the row order its hash group-by happened to leave; the
 canonical rule used by both restatements and by the engine is count descending, then aid ascending.
-Only tests/ (and tools/bench_popularity.py's CPU leg) may import this module.
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg (--workload popularity) may import this module.
 """
 from __future__ import annotations
 

@@ -223,6 +223,10 @@ int ottocov_reduce_pairs(ottocov_ctx* ctx, uint64_t* keys_dev, int64_t n, int ai
 int ottocov_table_mirror(ottocov_ctx* ctx, const ottocov_table* t, int transpose_only, ottocov_table** out);
 
 /* ---- building blocks exposed for tests and micro-benchmarks ---------------------------------- */
+/* The bijective key mix of the bucketed hash reduce (host code, needs no GPU): a pair (aid, aid_next), both below
+ * 2^aid_bits, <-> a 2*aid_bits-bit mixed key.  ottocov_key_unmix returns aid << 32 | aid_next.  1 <= aid_bits <= 28. */
+uint64_t ottocov_key_mix(int aid_bits, uint32_t aid, uint32_t aid_next);
+uint64_t ottocov_key_unmix(int aid_bits, uint64_t mixed);
 /* LSD radix sort of device-resident 64-bit keys on bits [lo_bit, hi_bit), optional 32-bit
  * payload (vals may be NULL).  Sorted data ends in keys/vals (in place from the caller's view). */
 int ottocov_sort_u64(ottocov_ctx* ctx, uint64_t* keys_dev, uint32_t* vals_dev, int64_t n,

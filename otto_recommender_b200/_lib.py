@@ -78,6 +78,8 @@ SYMBOLS = {
     "ottocov_table_partition": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, POINTER(c_int64)]),
     "ottocov_hash_dest": (c_uint32, [c_uint32, c_uint32]),
     "ottocov_sort_u64": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int]),
+    "ottocov_key_mix": (c_uint64, [c_int, c_uint32, c_uint32]),
+    "ottocov_key_unmix": (c_uint64, [c_int, c_uint64]),
     "ottocov_count_popularity": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int32, c_int,
                                          POINTER(c_int64)]),
     "ottocov_popularity_fetch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int]),

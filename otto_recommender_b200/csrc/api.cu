@@ -483,6 +483,18 @@ uint32_t ottocov_hash_dest(uint32_t aid, uint32_t n_ranks) {
     return n_ranks ? h % n_ranks : 0;
 }
 
+uint64_t ottocov_key_mix(int aid_bits, uint32_t aid, uint32_t aid_next) {
+    if (aid_bits < 1 || aid_bits > 28) return ~0ull;
+    const KeyMix m = make_key_mix(aid_bits);
+    return key_mix_fwd(m, aid, aid_next);
+}
+
+uint64_t ottocov_key_unmix(int aid_bits, uint64_t mixed) {
+    if (aid_bits < 1 || aid_bits > 28) return ~0ull;
+    const KeyMix m = make_key_mix(aid_bits);
+    return key_mix_inv(m, mixed);
+}
+
 int ottocov_sort_u64(ottocov_ctx* ctx, uint64_t* keys_dev, uint32_t* vals_dev, int64_t n, int lo_bit, int hi_bit) {
     API_BEGIN(ctx)
     if (n < 0 || lo_bit < 0 || hi_bit > 64 || lo_bit > hi_bit) COV_THROW(OTTOCOV_ERR_ARG, "bad argument");

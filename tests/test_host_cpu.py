@@ -112,3 +112,36 @@ def test_shard_bounds_balanced():
         w = lens * np.minimum(lens, 32)
         per = np.array([w[b[i]:b[i + 1]].sum() for i in range(r)])
         assert per.max() / per.mean() < 1.02
+
+
+def test_key_mix_is_a_bijection():
+    """The hash path of the reduce-by-key rests on the key mix being invertible (equal keys stay equal, distinct
+    keys stay distinct, the plain key comes back exactly).  Host code of the library: no GPU needed."""
+    from otto_recommender_b200 import _lib
+    lib = _lib.load_library()
+    rng = np.random.default_rng(0)
+    for ab in (1, 2, 3, 7, 11, 16, 21, 23, 24, 28):
+        lim = 1 << ab
+        if ab <= 3:                                    # exhaustive: every key of 2 ab bits maps to a distinct mixed key
+            seen = set()
+            for x in range(lim):
+                for y in range(lim):
+                    h = lib.ottocov_key_mix(ab, x, y)
+                    assert h < (1 << (2 * ab)) and lib.ottocov_key_unmix(ab, h) == (x << 32 | y)
+                    seen.add(h)
+            assert len(seen) == lim * lim
+        xs = rng.integers(0, lim, 2000); ys = rng.integers(0, lim, 2000)
+        edge = [(0, 0), (lim - 1, lim - 1), (0, lim - 1), (lim - 1, 0)]
+        for x, y in list(zip(xs.tolist(), ys.tolist())) + edge:
+            h = lib.ottocov_key_mix(ab, x, y)
+            assert h < (1 << (2 * ab))
+            assert lib.ottocov_key_unmix(ab, h) == (x << 32 | y)
+    # the top bits of the mixed key spread a skewed key set evenly: 2^8 buckets of a 100 k-key Zipf-like set
+    ab = 21
+    a = np.minimum((rng.pareto(1.1, 100_000) * 50).astype(np.int64), (1 << ab) - 1)
+    b = np.minimum((rng.pareto(1.1, 100_000) * 50).astype(np.int64), (1 << ab) - 1)
+    keys = np.unique(a << 32 | b)
+    top = np.array([lib.ottocov_key_mix(ab, int(k >> 32), int(k & 0xFFFFFFFF)) >> (2 * ab - 8) for k in keys])
+    counts = np.bincount(top, minlength=256)
+    assert counts.max() < 2.0 * len(keys) / 256 and counts.min() > 0.4 * len(keys) / 256
+    assert lib.ottocov_key_mix(29, 0, 0) == 2 ** 64 - 1      # out of range is loud

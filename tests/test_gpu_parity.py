@@ -559,6 +559,43 @@ def test_pipelined_host_load(engine):
     assert e.value.code == -3
 
 
+def test_hash_reduce_packed_relative_tags():
+    """Keys of more than 42 bits (the 4x-scale config: 23-bit aids, 46-bit keys) use the packed table word with
+    tags RELATIVE to the tile's first bucket, which needs >= 2^(kb - 34) buckets -- hundreds of millions of keys at
+    the default bucket size.  With OTTOCOV_HR_AVG=16 (16 keys per bucket) a million keys are enough; the knob is
+    read once per process, so the check runs in a child process."""
+    import subprocess
+    import sys
+    if os.environ.get("OTTOCOV_HR_AVG"):
+        pytest.skip("already inside the child run")
+    env = dict(os.environ, OTTOCOV_HR_AVG="16")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
+                        "-k", "wide_keys_small_buckets_child or hash_reduce_vs_oracle"],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_wide_keys_small_buckets_child(engine):
+    if os.environ.get("OTTOCOV_HR_AVG") != "16":
+        pytest.skip("runs inside test_hash_reduce_packed_relative_tags")
+    s, a, t, y = small_events(47, n_sessions=4000, n_aids=3000, max_len=50)
+    a = a * 2500                                   # 23-bit aids -> 46-bit keys
+    info = engine.load_events(s, a, t, y)
+    assert info["aid_bits"] == 23
+    for name in ("click_to_click", "click_to_cart_or_buy"):
+        oa, ob, oc, emitted, _ = c_oracle.count_name(s, a, t, y, name)
+        for mc in (1, 2):
+            ka, kb, kc = c_oracle.merge_tables([(oa, ob, oc)], min_count=mc)
+            for sym in (True, False):
+                tab = engine.count(name, min_count=mc, symmetric=sym, hashed=True)
+                ci = engine.count_info()
+                ga, gb, gc = tab.fetch()
+                assert np.array_equal(ga, ka) and np.array_equal(gb, kb) and np.array_equal(gc, kc), (name, mc, sym)
+                # bucket passes only (no fall-back to the full 46-bit sort) when there are enough keys for >= 2^12 buckets
+                if ci["n_pairs"] >= 400_000:
+                    assert ci["sort_passes"] <= 3, ci
+
+
 # ---- BASELINE config 1: 100k-session synthetic slice, full pair table + top-20 ----------------------------------
 def test_config1_100k_sessions(engine):
     d = generate_numpy(SynthSpec(n_sessions=100_000, seed=42))

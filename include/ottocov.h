@@ -32,7 +32,7 @@ extern "C" {
 #pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
 #endif
 
-#define OTTOCOV_VERSION 100
+#define OTTOCOV_VERSION 200
 
 typedef enum {
     OTTOCOV_OK = 0,
@@ -54,15 +54,16 @@ typedef struct ottocov_table ottocov_table;
 /* One co-event kind = one entry of config.MAP_NAME_COUNT_TYPE + MAP_MAX_TIME_TO_NEXT
  * (reference config.py:43-49, 81-88). */
 enum { OTTOCOV_SYM_OFF = 1, OTTOCOV_SYM_ON = 2,
-       OTTOCOV_HASH_OFF = 4, OTTOCOV_HASH_ON = 8 };   /* see ottocov_spec.flags */
+       OTTOCOV_HASH_OFF = 4, OTTOCOV_HASH_ON = 8,     /* see ottocov_spec.flags */
+       OTTOCOV_DT_RANGE = 16 };                       /* dt_min / dt_max of the spec are set */
 /* bits of ottocov_reduce_pairs' strip_dest argument above bit 0 */
 enum { OTTOCOV_REDUCE_HASH_ON = 2, OTTOCOV_REDUCE_HASH_OFF = 4 };
 
 typedef struct {
     int32_t type_this;       /* source event type: 0 click, 1 cart, 2 order                       */
     uint32_t next_mask;      /* bit t set <=> events of type t are "next" events                  */
-    int64_t window;          /* |ts_next - ts| <= window, seconds, inclusive; clamped to 86400     */
-                             /* (the +-24 h pre-filter of count_co_events.py:33-36)                */
+    int64_t window;          /* |ts_next - ts| <= window, seconds, inclusive (config.MAP_MAX_TIME_TO_NEXT); */
+                             /* intersected with the pre-filter dt_min <= ts_next - ts <= dt_max     */
     int64_t pair_budget;     /* max co-event pairs expanded at once (HBM footprint); 0 = auto     */
     uint32_t min_count;      /* keep only pairs with count >= min_count (0 or 1 = keep all); fused */
                              /* into the run-length reduce: filter(count >= ...) of :131-132, :172  */
@@ -76,6 +77,11 @@ typedef struct {
                              /* takes the hash reduce when min_count > 1 (few rows left to bring     */
                              /* back into key order); OTTOCOV_HASH_OFF / OTTOCOV_HASH_ON force it.    */
                              /* Both produce the same table bit for bit.                              */
+    int64_t dt_min, dt_max;  /* the pre-filter of self_merge (count_co_events.py:33-36):               */
+                             /* config.MIN_TIME_TO_NEXT <= ts_next - ts <= config.MAX_TIME_TO_NEXT.     */
+                             /* Read only when flags has OTTOCOV_DT_RANGE; otherwise -86400 / +86400    */
+                             /* (config.py:41-42).  An asymmetric range switches the symmetric shortcut */
+                             /* off (count(a,b) != count(b,a) then).                                     */
 } ottocov_spec;
 
 typedef struct {
@@ -91,7 +97,9 @@ typedef struct {
     int64_t n_pairs;         /* co-event pairs emitted by the last ottocov_count (sum of counts)   */
     int64_t n_unique;        /* rows of the table it produced                                      */
     int32_t n_chunks;        /* pair-budget chunks it ran                                          */
-    int32_t sort_passes;     /* radix passes per chunk                                             */
+    int32_t sort_passes;     /* distribution passes per chunk (a pass fused into the expansion counts) */
+    int32_t fused;           /* 1 = the first pass of the bucketed hash reduce ran inside the expansion     */
+    int32_t reserved;
 } ottocov_count_info;
 
 /* Per-kernel-family accounting for roofline reports (bench.py). */
@@ -221,6 +229,46 @@ int ottocov_push_keys(ottocov_ctx* ctx, const uint64_t* keys_dev, int64_t n, int
 int ottocov_reduce_pairs(ottocov_ctx* ctx, uint64_t* keys_dev, int64_t n, int aid_bits, uint32_t min_count,
                          int symmetric, int strip_dest, ottocov_table** out);
 int ottocov_table_mirror(ottocov_ctx* ctx, const ottocov_table* t, int transpose_only, ottocov_table** out);
+
+/* ---- fused expansion + exchange (default multi-GPU path, round 2) --------------------------------------------
+ * The first distribution pass of the bucketed hash reduce needs no stability, so it runs INSIDE the pair expansion
+ * (see ottocov_count); with n_ranks > 1 its digit is (owner rank of the key, low hash-bucket bits) and every digit's
+ * region is a stripe of the OWNER's receive area, mapped into this process (CUDA IPC / torch symmetric memory): the
+ * keys cross NVLink as the stores of the expansion kernel and land already partitioned for the owner's remaining
+ * passes.  No key is written to local HBM first, no NCCL data collective, no per-destination counts on the host.
+ *
+ *   ottocov_xplan_make      pure host arithmetic, identical on every rank given the same arguments: stripe
+ *                           capacities and the byte layout of a rank's receive area
+ *                             counts [src][sub] u64 | status [src][4] u64 | hist [src][passes][256] u64 |
+ *                             key stripes [src][sub][stripe_cap] u64 | mirrored rows [src]: count, keys, counts
+ *                           max_local_keys / total_keys: largest per-rank and summed key count of
+ *                           ottocov_expand_prepare over the ranks; mirror_rows_hint: expected thresholded half-table
+ *                           rows per rank (0 = derive from total_keys)
+ *   ottocov_expand_scatter  after ottocov_expand_prepare: expands this rank's keys into the peers' stripes
+ *                           (peer_base[r] = device address of rank r's receive area as seen from this process) and
+ *                           publishes per-stripe counts, pass histograms and its status (overflow flag + the
+ *                           capacity it would have needed) to EVERY rank.  Only enqueues work.
+ *   ottocov_reduce_received after the ranks synchronised: reads the published status; *need_cap > 0 (and no table)
+ *                           when some rank overflowed a stripe -- every rank sees the same value, grows the plan
+ *                           and repeats -- else the remaining passes + hash reduce over this rank's stripes.
+ *                           symmetric: keys are canonical half pairs; the table then holds rows a <= b only.
+ *   ottocov_mirror_push     half table -> its transposed off-diagonal rows (b, a, c) stored into the stripes of
+ *                           their owners hash(b) (+ status as above); ottocov_mirror_collect merges what this rank
+ *                           received with its own half rows into the full sorted table (*need_rows > 0: grow). */
+typedef struct {
+    int32_t n_ranks, aid_bits, bucket_bits, sub_bits, rest_passes, reserved;
+    int64_t stripe_cap, mirror_cap;
+    int64_t off_counts, off_status, off_hist, off_keys, off_mstatus, off_mkeys, off_mcnt, total_bytes;
+} ottocov_xplan;
+int ottocov_xplan_make(int n_ranks, int aid_bits, int64_t max_local_keys, int64_t total_keys, int64_t stripe_cap,
+                       int64_t mirror_cap, ottocov_xplan* out);     /* stripe_cap / mirror_cap: 0 = derive */
+int ottocov_expand_scatter(ottocov_ctx* ctx, const ottocov_xplan* plan, int rank, const uint64_t* peer_base /*HOST [n_ranks]*/);
+int ottocov_reduce_received(ottocov_ctx* ctx, const ottocov_xplan* plan, uint64_t recv_area_dev, uint32_t min_count,
+                            int symmetric, ottocov_table** out, int64_t* need_cap);
+int ottocov_mirror_push(ottocov_ctx* ctx, const ottocov_xplan* plan, int rank, const ottocov_table* half,
+                        const uint64_t* peer_base /*HOST [n_ranks]*/);
+int ottocov_mirror_collect(ottocov_ctx* ctx, const ottocov_xplan* plan, int rank, const ottocov_table* half,
+                           uint64_t recv_area_dev, ottocov_table** out, int64_t* need_rows);
 
 /* ---- building blocks exposed for tests and micro-benchmarks ---------------------------------- */
 /* The bijective key mix of the bucketed hash reduce (host code, needs no GPU): a pair (aid, aid_next), both below

@@ -46,15 +46,22 @@ def _load():
             ctypes.c_int, ctypes.c_int, ctypes.c_int64,
             P(ctypes.c_void_p), P(ctypes.c_void_p), P(ctypes.c_void_p),
             P(ctypes.c_int64), P(ctypes.c_int64)]
+        lib.cov_oracle_count_range.restype = ctypes.c_int64
+        lib.cov_oracle_count_range.argtypes = [
+            ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+            ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+            P(ctypes.c_void_p), P(ctypes.c_void_p), P(ctypes.c_void_p),
+            P(ctypes.c_int64), P(ctypes.c_int64)]
         lib.cov_oracle_free.argtypes = [ctypes.c_void_p]
         lib.cov_oracle_free.restype = None
         _lib = lib
     return _lib
 
 
-def count(session, aid, ts, type_, type_this: int, next_mask: int, window: int
-          ) -> Tuple[np.ndarray, np.ndarray, np.ndarray, int, int]:
-    """-> (aid, aid_next, count) sorted by (aid, aid_next), n_emitted_pairs, n_events_after_dedup."""
+def count(session, aid, ts, type_, type_this: int, next_mask: int, window: int,
+          dt_min: int = -86400, dt_max: int = 86400) -> Tuple[np.ndarray, np.ndarray, np.ndarray, int, int]:
+    """-> (aid, aid_next, count) sorted by (aid, aid_next), n_emitted_pairs, n_events_after_dedup.
+    dt_min / dt_max: config.MIN_TIME_TO_NEXT / MAX_TIME_TO_NEXT (the pre-filter of count_co_events.py:33-36)."""
     lib = _load()
     s = np.ascontiguousarray(session, np.int32)
     a = np.ascontiguousarray(aid, np.int32)
@@ -63,10 +70,10 @@ def count(session, aid, ts, type_, type_this: int, next_mask: int, window: int
     n = len(s)
     pa_, pb_, pc_ = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
     emitted, nded = ctypes.c_int64(), ctypes.c_int64()
-    u = lib.cov_oracle_count(n, s.ctypes.data, a.ctypes.data, t.ctypes.data, y.ctypes.data,
-                             type_this, next_mask, window,
-                             ctypes.byref(pa_), ctypes.byref(pb_), ctypes.byref(pc_),
-                             ctypes.byref(emitted), ctypes.byref(nded))
+    u = lib.cov_oracle_count_range(n, s.ctypes.data, a.ctypes.data, t.ctypes.data, y.ctypes.data,
+                                   type_this, next_mask, window, dt_min, dt_max,
+                                   ctypes.byref(pa_), ctypes.byref(pb_), ctypes.byref(pc_),
+                                   ctypes.byref(emitted), ctypes.byref(nded))
     if u < 0:
         raise MemoryError("cov_oracle_count failed")
     try:

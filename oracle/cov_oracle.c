@@ -75,10 +75,28 @@ void cov_oracle_free(void* p) { free(p); }
  * (aid, aid_next); *n_emitted = total ordered co-event pairs (sum of counts).  Returns -1 on
  * allocation failure.  Free the arrays with cov_oracle_free.
  */
+int64_t cov_oracle_count_range(int64_t n, const int32_t* session, const int32_t* aid, const int32_t* ts,
+                               const int8_t* type, int type_this, int next_mask, int64_t window,
+                               int64_t dt_min, int64_t dt_max,
+                               int32_t** out_aid, int32_t** out_aid_next, uint32_t** out_count,
+                               int64_t* n_emitted, int64_t* n_events_after_dedup);
+
 int64_t cov_oracle_count(int64_t n, const int32_t* session, const int32_t* aid, const int32_t* ts,
                          const int8_t* type, int type_this, int next_mask, int64_t window,
                          int32_t** out_aid, int32_t** out_aid_next, uint32_t** out_count,
                          int64_t* n_emitted, int64_t* n_events_after_dedup) {
+    /* config.py:41-42: MIN_TIME_TO_NEXT = -24 h, MAX_TIME_TO_NEXT = +24 h */
+    return cov_oracle_count_range(n, session, aid, ts, type, type_this, next_mask, window, -86400, 86400,
+                                  out_aid, out_aid_next, out_count, n_emitted, n_events_after_dedup);
+}
+
+/* The same with the pre-filter bounds of self_merge (count_co_events.py:33-36) as parameters:
+ * dt_min <= ts_j - ts_i <= dt_max (config.MIN_TIME_TO_NEXT / MAX_TIME_TO_NEXT). */
+int64_t cov_oracle_count_range(int64_t n, const int32_t* session, const int32_t* aid, const int32_t* ts,
+                               const int8_t* type, int type_this, int next_mask, int64_t window,
+                               int64_t dt_min, int64_t dt_max,
+                               int32_t** out_aid, int32_t** out_aid_next, uint32_t** out_count,
+                               int64_t* n_emitted, int64_t* n_events_after_dedup) {
     *out_aid = NULL; *out_aid_next = NULL; *out_count = NULL; *n_emitted = 0;
     ev_t* ev = (ev_t*)malloc((size_t)(n > 0 ? n : 1) * sizeof(ev_t));
     if (!ev) return -1;
@@ -101,7 +119,7 @@ int64_t cov_oracle_count(int64_t n, const int32_t* session, const int32_t* aid, 
                 if (j == i) continue;                /* the event joined with itself */
                 if (!((next_mask >> ev[j].type) & 1)) continue;
                 int64_t dt = (int64_t)ev[j].ts - (int64_t)ev[i].ts;
-                if (dt < -86400 || dt > 86400) continue;
+                if (dt < dt_min || dt > dt_max) continue;
                 int64_t adt = dt < 0 ? -dt : dt;
                 if (adt > window) continue;
                 uint64_t k = ((uint64_t)(uint32_t)ev[i].aid << 32) | (uint32_t)ev[j].aid;

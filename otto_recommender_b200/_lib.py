@@ -23,7 +23,7 @@ class OttocovError(RuntimeError):
 
 class Spec(Structure):
     _fields_ = [("type_this", c_int32), ("next_mask", c_uint32), ("window", c_int64), ("pair_budget", c_int64),
-                ("min_count", c_uint32), ("flags", c_uint32)]
+                ("min_count", c_uint32), ("flags", c_uint32), ("dt_min", c_int64), ("dt_max", c_int64)]
 
 
 class EventsInfo(Structure):
@@ -33,7 +33,16 @@ class EventsInfo(Structure):
 
 
 class CountInfo(Structure):
-    _fields_ = [("n_pairs", c_int64), ("n_unique", c_int64), ("n_chunks", c_int32), ("sort_passes", c_int32)]
+    _fields_ = [("n_pairs", c_int64), ("n_unique", c_int64), ("n_chunks", c_int32), ("sort_passes", c_int32),
+                ("fused", c_int32), ("reserved", c_int32)]
+
+
+class XPlan(Structure):
+    """ottocov_xplan: stripe capacities + byte layout of a rank's receive area (fused expansion + exchange)."""
+    _fields_ = [("n_ranks", c_int32), ("aid_bits", c_int32), ("bucket_bits", c_int32), ("sub_bits", c_int32),
+                ("rest_passes", c_int32), ("reserved", c_int32), ("stripe_cap", c_int64), ("mirror_cap", c_int64),
+                ("off_counts", c_int64), ("off_status", c_int64), ("off_hist", c_int64), ("off_keys", c_int64),
+                ("off_mstatus", c_int64), ("off_mkeys", c_int64), ("off_mcnt", c_int64), ("total_bytes", c_int64)]
 
 
 class KernelStat(Structure):
@@ -59,6 +68,11 @@ SYMBOLS = {
     "ottocov_expand_prepare": (c_int, [c_void_p, POINTER(Spec), POINTER(c_int64), POINTER(c_int)]),
     "ottocov_expand_run": (c_int, [c_void_p, c_int, c_void_p, c_void_p, POINTER(c_int), POINTER(c_int64)]),
     "ottocov_push_keys": (c_int, [c_void_p, c_void_p, c_int64, c_int, POINTER(c_uint64)]),
+    "ottocov_xplan_make": (c_int, [c_int, c_int, c_int64, c_int64, c_int64, c_int64, POINTER(XPlan)]),
+    "ottocov_expand_scatter": (c_int, [c_void_p, POINTER(XPlan), c_int, POINTER(c_uint64)]),
+    "ottocov_reduce_received": (c_int, [c_void_p, POINTER(XPlan), c_uint64, c_uint32, c_int, POINTER(c_void_p), POINTER(c_int64)]),
+    "ottocov_mirror_push": (c_int, [c_void_p, POINTER(XPlan), c_int, c_void_p, POINTER(c_uint64)]),
+    "ottocov_mirror_collect": (c_int, [c_void_p, POINTER(XPlan), c_int, c_void_p, c_uint64, POINTER(c_void_p), POINTER(c_int64)]),
     "ottocov_reduce_pairs": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_uint32, c_int, c_int, POINTER(c_void_p)]),
     "ottocov_table_mirror": (c_int, [c_void_p, c_void_p, c_int, POINTER(c_void_p)]),
     "ottocov_get_count_info": (c_int, [c_void_p, POINTER(CountInfo)]),

@@ -206,11 +206,14 @@ int ottocov_destroy(ottocov_ctx* ctx) {
     free_popularity(ctx);
     free_plan(ctx);
     if (ctx->sweep_status) cudaFreeAsync(ctx->sweep_status, ctx->stream);
+    if (ctx->scan_status) cudaFreeAsync(ctx->scan_status, ctx->stream);
     for (auto& kv : ctx->live) cudaFreeAsync(kv.first, ctx->stream);    // tables the caller never freed
     ctx->live.clear();
     cov_trim(ctx);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->sweep_ticket) cudaFree(ctx->sweep_ticket);
+    if (ctx->scan_ticket) cudaFree(ctx->scan_ticket);
+    if (ctx->scan_totals) cudaFree(ctx->scan_totals);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (ProfEvent& pe : ctx->prof_pending) { if (pe.a) cudaEventDestroy(pe.a); if (pe.b) cudaEventDestroy(pe.b); }
     for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
@@ -314,6 +317,54 @@ int ottocov_push_keys(ottocov_ctx* ctx, const uint64_t* keys_dev, int64_t n, int
     API_BEGIN(ctx)
     if (n < 0 || !dest_ptrs || (n > 0 && !keys_dev)) COV_THROW(OTTOCOV_ERR_ARG, "bad argument");
     push_keys_impl(ctx, (const u64*)keys_dev, n, n_ranks, (const u64*)dest_ptrs);
+    API_END(ctx)
+}
+
+int ottocov_xplan_make(int n_ranks, int aid_bits, int64_t max_local_keys, int64_t total_keys, int64_t stripe_cap,
+                       int64_t mirror_cap, ottocov_xplan* out) {
+    if (!out) return OTTOCOV_ERR_ARG;
+    try {
+        xplan_make_impl(n_ranks, aid_bits, max_local_keys, total_keys, stripe_cap, mirror_cap, out);
+        return OTTOCOV_OK;
+    } catch (const CovError& e) {
+        g_create_error = e.msg;
+        return e.code;
+    }
+}
+
+int ottocov_expand_scatter(ottocov_ctx* ctx, const ottocov_xplan* plan, int rank, const uint64_t* peer_base) {
+    API_BEGIN(ctx)
+    if (!plan || !peer_base) COV_THROW(OTTOCOV_ERR_ARG, "NULL argument");
+    expand_scatter_impl(ctx, plan, rank, (const u64*)peer_base);
+    API_END(ctx)
+}
+
+int ottocov_reduce_received(ottocov_ctx* ctx, const ottocov_xplan* plan, uint64_t recv_area_dev, uint32_t min_count,
+                            int symmetric, ottocov_table** out, int64_t* need_cap) {
+    API_BEGIN(ctx)
+    if (!plan || !out || !need_cap || !recv_area_dev) COV_THROW(OTTOCOV_ERR_ARG, "NULL argument");
+    *out = nullptr;
+    const int64_t n_pairs = ctx->last_count.n_pairs;
+    *out = reduce_received_impl(ctx, plan, (u64)recv_area_dev, min_count, symmetric, need_cap);
+    ctx->last_count.n_pairs = n_pairs;
+    API_END(ctx)
+}
+
+int ottocov_mirror_push(ottocov_ctx* ctx, const ottocov_xplan* plan, int rank, const ottocov_table* half,
+                        const uint64_t* peer_base) {
+    API_BEGIN(ctx)
+    if (!plan || !half || !peer_base) COV_THROW(OTTOCOV_ERR_ARG, "NULL argument");
+    mirror_push_impl(ctx, plan, rank, half, (const u64*)peer_base);
+    API_END(ctx)
+}
+
+int ottocov_mirror_collect(ottocov_ctx* ctx, const ottocov_xplan* plan, int rank, const ottocov_table* half,
+                           uint64_t recv_area_dev, ottocov_table** out, int64_t* need_rows) {
+    API_BEGIN(ctx)
+    if (!plan || !half || !out || !need_rows || !recv_area_dev) COV_THROW(OTTOCOV_ERR_ARG, "NULL argument");
+    *out = nullptr;
+    *out = mirror_collect_impl(ctx, plan, rank, half, (u64)recv_area_dev, need_rows);
+    ctx->last_count.n_unique = *out ? (*out)->n : 0;
     API_END(ctx)
 }
 

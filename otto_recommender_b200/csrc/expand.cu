@@ -23,9 +23,6 @@
 #include "internal.cuh"
 #include "scan.cuh"
 
-#ifndef OTTOCOV_EX_DIRECT
-#define OTTOCOV_EX_DIRECT 0
-#endif
 constexpr int EX_THREADS = 256;
 constexpr int EX_TILE = 2048;
 constexpr int EX_PER = EX_TILE / EX_THREADS;          // consecutive outputs per thread
@@ -98,6 +95,34 @@ __global__ void __launch_bounds__(256) window_fwd_kernel(const u64* __restrict__
     cnt_out[j] = hi - (u32)j - 1u;
 }
 
+// General time range dt_lo <= ts_tgt - ts_src <= dt_hi (a config whose MIN/MAX_TIME_TO_NEXT pre-filter is not the
+// reference's symmetric +-24 h, count_co_events.py:33-36): plain binary searches over the whole target array.
+// self_in: source and target type agree and 0 lies in the range, so the event itself is inside and is excluded.
+__global__ void __launch_bounds__(256) window_range_kernel(const u64* __restrict__ src_key, int64_t n_src,
+                                                           const u64* __restrict__ tgt_key, u32 n_tgt, int64_t dt_lo,
+                                                           int64_t dt_hi, int self_in, u32* __restrict__ lo_out,
+                                                           u32* __restrict__ cnt_out) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_src) return;
+    const u64 k = src_key[j];
+    const int64_t t = (int64_t)(u32)k;
+    const u64 s = k & 0xFFFFFFFF00000000ull;
+    const int64_t a = t + dt_lo, b = t + dt_hi;
+    u32 lo = 0, cnt = 0;
+    if (b >= 0 && a <= 0xFFFFFFFFll && a <= b) {
+        const u64 lower = s | (u64)(a < 0 ? 0 : a);
+        const u64 upper = s | (u64)(b > 0xFFFFFFFFll ? 0xFFFFFFFFll : b);
+        u32 l = 0, h = n_tgt;                       // first index with key >= lower
+        while (l < h) { const u32 m = l + ((h - l) >> 1); if (tgt_key[m] >= lower) h = m; else l = m + 1; }
+        lo = l;
+        h = n_tgt;                                  // first index with key > upper
+        while (l < h) { const u32 m = l + ((h - l) >> 1); if (tgt_key[m] > upper) h = m; else l = m + 1; }
+        cnt = l - lo - (self_in ? 1u : 0u);
+    }
+    lo_out[j] = lo;
+    cnt_out[j] = cnt;
+}
+
 // compaction of the non-empty sources into records (src, lo, output offset)
 struct WindowRecords {
     static constexpr int NC = 2;
@@ -147,10 +172,86 @@ __device__ __forceinline__ u64 make_pair_key(u32 a, u32 b, u32 n_dest, const Key
     return k;
 }
 
+// ---- the two halves of a tile that both expansion kernels share ------------------------------------------------
+constexpr int EX_PITCH = EX_TILE + 2;
+
+// Stage the records that own outputs of tile `tile` in shared memory (s_off: first output of the record relative to
+// the tile, s_lo: target index of that output, s_aid: source aid, s_src: source index).  Returns the record count;
+// *n_out_p = outputs of the tile.  Ends with a barrier.
+template <bool SELF>
+__device__ __forceinline__ u32 stage_tile_records(const u32* __restrict__ rec_src, const u32* __restrict__ rec_lo,
+                                                  const u64* __restrict__ rec_off, const u32* __restrict__ tile_rec,
+                                                  const u32* __restrict__ aid_src, u64 out_begin, u64 out_end, int64_t tile,
+                                                  u32* s_off, u32* s_lo, u32* s_aid, u32* s_src, u32* n_out_p) {
+    const u64 o0 = out_begin + (u64)tile * EX_TILE;
+    const u32 n_out = (u32)min((u64)EX_TILE, out_end - o0);
+    const u32 r0 = tile_rec[tile];
+    const u32 r1 = tile_rec[tile + 1];                // record of the tile's last output (clamped)
+    // records that own outputs of this tile: r0 .. r_last, r_last = record of output o0 + n_out - 1
+    u32 r_last = r1;
+    if ((u64)tile * EX_TILE + EX_TILE + out_begin < out_end) {
+        // tile_rec[t+1] is the record of the NEXT tile's first output; it owns outputs of this
+        // tile only if it starts before that output
+        if (rec_off[r1] >= o0 + n_out) r_last = r1 - 1;
+    }
+    const u32 n_rec = r_last - r0 + 1;                // <= EX_TILE (offsets strictly increase)
+    for (u32 j = threadIdx.x; j < n_rec; j += EX_THREADS) {
+        const u32 r = r0 + j;
+        const u64 off = rec_off[r];
+        const u32 src = rec_src[r];
+        u32 lo = rec_lo[r];
+        u32 rel;
+        if (off <= o0) { rel = 0; lo += (u32)(o0 - off); }   // only j == 0: skip outputs of earlier tiles
+        else rel = (u32)(off - o0);
+        s_off[j] = rel;
+        s_lo[j] = lo;
+        s_aid[j] = aid_src[src];
+        if (SELF) s_src[j] = src;
+    }
+    __syncthreads();
+    *n_out_p = n_out;
+    return n_rec;
+}
+
+// Thread t produces the EX_PER consecutive outputs [EX_PER t, EX_PER t + EX_PER) of the tile: one binary search
+// for the first, a linear walk over the record offsets for the rest.  Only outputs k < n_out are defined.
+template <bool SELF, bool CANON, bool MIX>
+__device__ __forceinline__ void make_tile_keys(const u32* s_off, const u32* s_lo, const u32* s_aid, const u32* s_src,
+                                               u32 n_rec, u32 n_out, const u32* __restrict__ aid_tgt, u32 n_dest,
+                                               const KeyMix& mix, u64 (&key)[EX_PER]) {
+    const u32 k0 = (u32)EX_PER * threadIdx.x;
+    if (k0 >= n_out) return;
+    u32 lo = 0, hi = n_rec;                       // last record with s_off <= k0
+    while (hi - lo > 1) {
+        const u32 mid = (lo + hi) >> 1;
+        if (s_off[mid] <= k0) lo = mid; else hi = mid;
+    }
+    u32 j = lo;
+    u32 a = s_aid[j];
+    u32 tb = s_lo[j] - s_off[j];                  // target index = tb + k (mod 2^32)
+    u32 src = SELF ? s_src[j] : 0u;
+    u32 next_off = (j + 1 < n_rec) ? s_off[j + 1] : 0xFFFFFFFFu;
+#pragma unroll
+    for (int q = 0; q < EX_PER; ++q) {
+        const u32 k = k0 + q;
+        if (k < n_out) {
+            if (k >= next_off) {                  // offsets strictly increase: at most one step per output
+                ++j;
+                a = s_aid[j];
+                tb = s_lo[j] - s_off[j];
+                if (SELF) src = s_src[j];
+                next_off = (j + 1 < n_rec) ? s_off[j + 1] : 0xFFFFFFFFu;
+            }
+            u32 tgt = tb + k;
+            if (SELF) tgt += (tgt >= src);
+            key[q] = make_pair_key<CANON, MIX>(a, aid_tgt[tgt], n_dest, mix);
+        }
+    }
+}
+
 // Persistent: CTA b writes tiles b, b + gridDim.x, ...  Per tile the records that own its outputs are staged in
-// shared memory; thread t then produces the EX_PER consecutive outputs [EX_PER t, EX_PER t + EX_PER): one binary
-// search for the first, a linear walk over the record offsets for the rest.  The keys go through a swizzled
-// shared-memory transpose and leave as 128-bit stores, 512 contiguous bytes per warp instruction.
+// shared memory; thread t then produces the EX_PER consecutive outputs [EX_PER t, EX_PER t + EX_PER).  The keys go
+// through a swizzled shared-memory transpose and leave as 128-bit stores, 512 contiguous bytes per warp instruction.
 // ghist != nullptr: the digit histograms of the distribution passes that will sort these keys (pl) are
 // accumulated here, in shared memory while the keys are still in registers, and flushed once per CTA -- the
 // sort's own histogram kernel (one more read of every key) is not needed.
@@ -161,13 +262,12 @@ expand_kernel(const u32* __restrict__ rec_src, const u32* __restrict__ rec_lo,
               const u32* __restrict__ aid_src, const u32* __restrict__ aid_tgt, u64 out_begin,
               u64 out_end, u64* __restrict__ dst, u32 n_dest, KeyMix mix, int64_t n_tiles, PassList pl,
               u64* __restrict__ ghist) {
-    constexpr int PITCH = EX_TILE + 2;
-    __shared__ __align__(16) u32 s_buf[3 * PITCH];
+    __shared__ __align__(16) u32 s_buf[3 * EX_PITCH];
     __shared__ u32 s_src[SELF ? EX_TILE + 1 : 1];
     extern __shared__ u32 s_hist[];                   // [pl.n][RS_RADIX] when ghist
     u32* s_off = s_buf;
-    u32* s_lo = s_buf + PITCH;
-    u32* s_aid = s_buf + 2 * PITCH;
+    u32* s_lo = s_buf + EX_PITCH;
+    u32* s_aid = s_buf + 2 * EX_PITCH;
     u64* s_out = reinterpret_cast<u64*>(s_buf);       // [EX_TILE]: re-uses s_off / s_lo once the keys sit in registers
     const bool hist = ghist != nullptr;
     if (hist)
@@ -175,93 +275,22 @@ expand_kernel(const u32* __restrict__ rec_src, const u32* __restrict__ rec_lo,
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const u64 o0 = out_begin + (u64)tile * EX_TILE;
-        const u32 n_out = (u32)min((u64)EX_TILE, out_end - o0);
-        const u32 r0 = tile_rec[tile];
-        const u32 r1 = tile_rec[tile + 1];                // record of the tile's last output (clamped)
-        // records that own outputs of this tile: r0 .. r_last, r_last = record of output o0 + n_out - 1
-        u32 r_last = r1;
-        if ((u64)tile * EX_TILE + EX_TILE + out_begin < out_end) {
-            // tile_rec[t+1] is the record of the NEXT tile's first output; it owns outputs of this
-            // tile only if it starts before that output
-            if (rec_off[r1] >= o0 + n_out) r_last = r1 - 1;
-        }
-        const u32 n_rec = r_last - r0 + 1;                // <= EX_TILE (offsets strictly increase)
-
-        for (u32 j = threadIdx.x; j < n_rec; j += EX_THREADS) {
-            const u32 r = r0 + j;
-            const u64 off = rec_off[r];
-            const u32 src = rec_src[r];
-            u32 lo = rec_lo[r];
-            u32 rel;
-            if (off <= o0) { rel = 0; lo += (u32)(o0 - off); }   // only j == 0: skip outputs of earlier tiles
-            else rel = (u32)(off - o0);
-            s_off[j] = rel;
-            s_lo[j] = lo;
-            s_aid[j] = aid_src[src];
-            if (SELF) s_src[j] = src;
-        }
-        __syncthreads();
-
+        u32 n_out;
+        const u32 n_rec = stage_tile_records<SELF>(rec_src, rec_lo, rec_off, tile_rec, aid_src, out_begin, out_end, tile,
+                                                   s_off, s_lo, s_aid, s_src, &n_out);
         u64 key[EX_PER];
         const u32 k0 = (u32)EX_PER * threadIdx.x;
-        if (k0 < n_out) {
-            u32 lo = 0, hi = n_rec;                       // last record with s_off <= k0
-            while (hi - lo > 1) {
-                const u32 mid = (lo + hi) >> 1;
-                if (s_off[mid] <= k0) lo = mid; else hi = mid;
-            }
-            u32 j = lo;
-            u32 a = s_aid[j];
-            u32 tb = s_lo[j] - s_off[j];                  // target index = tb + k (mod 2^32)
-            u32 src = SELF ? s_src[j] : 0u;
-            u32 next_off = (j + 1 < n_rec) ? s_off[j + 1] : 0xFFFFFFFFu;
+        make_tile_keys<SELF, CANON, MIX>(s_off, s_lo, s_aid, s_src, n_rec, n_out, aid_tgt, n_dest, mix, key);
+        if (hist && k0 < n_out) {
+            for (int p = 0; p < pl.n; ++p) {              // pass parameters are read once per pass, not per key
+                const int sh = pl.shift[p];
+                const u32 msk = (1u << pl.bits[p]) - 1u;
+                u32* hrow = s_hist + p * RS_RADIX;
 #pragma unroll
-            for (int q = 0; q < EX_PER; ++q) {
-                const u32 k = k0 + q;
-                if (k < n_out) {
-                    if (k >= next_off) {                  // offsets strictly increase: at most one step per output
-                        ++j;
-                        a = s_aid[j];
-                        tb = s_lo[j] - s_off[j];
-                        if (SELF) src = s_src[j];
-                        next_off = (j + 1 < n_rec) ? s_off[j + 1] : 0xFFFFFFFFu;
-                    }
-                    u32 tgt = tb + k;
-                    if (SELF) tgt += (tgt >= src);
-                    key[q] = make_pair_key<CANON, MIX>(a, aid_tgt[tgt], n_dest, mix);
-                }
-            }
-            if (hist) {
-                for (int p = 0; p < pl.n; ++p) {          // pass parameters are read once per pass, not per key
-                    const int sh = pl.shift[p];
-                    const u32 msk = (1u << pl.bits[p]) - 1u;
-                    u32* hrow = s_hist + p * RS_RADIX;
-#pragma unroll
-                    for (int q = 0; q < EX_PER; ++q)
-                        if (k0 + q < n_out) atomicAdd(&hrow[(u32)(key[q] >> sh) & msk], 1u);
-                }
+                for (int q = 0; q < EX_PER; ++q)
+                    if (k0 + q < n_out) atomicAdd(&hrow[(u32)(key[q] >> sh) & msk], 1u);
             }
         }
-#if OTTOCOV_EX_DIRECT
-        // measured variant (experiments/README.md): 8 consecutive keys leave straight from the registers as four
-        // 128-bit stores per thread (64 B per thread, sectors half-filled per instruction, merged in L2)
-        {
-            u64* tile_dst = dst + (size_t)tile * EX_TILE;
-            if (k0 < n_out) {
-#pragma unroll
-                for (int q = 0; q < EX_PER; q += 2) {
-                    if (k0 + q + 1 < n_out && vec_ok) {
-                        ulonglong2 v; v.x = key[q]; v.y = key[q + 1];
-                        __stcs(reinterpret_cast<ulonglong2*>(tile_dst + k0 + q), v);
-                    } else {
-                        if (k0 + q < n_out) __stcs(tile_dst + k0 + q, key[q]);
-                        if (k0 + q + 1 < n_out) __stcs(tile_dst + k0 + q + 1, key[q + 1]);
-                    }
-                }
-            }
-        }
-#else
         __syncthreads();                                  // every thread is done with the staged records
         if (k0 < n_out) {
 #pragma unroll
@@ -289,7 +318,6 @@ expand_kernel(const u32* __restrict__ rec_src, const u32* __restrict__ rec_lo,
                 __stcs(tile_dst + k, key0);
             }
         }
-#endif
         __syncthreads();                                  // s_buf is re-staged by the next tile
     }
     if (hist) {
@@ -298,6 +326,160 @@ expand_kernel(const u32* __restrict__ rec_src, const u32* __restrict__ rec_lo,
             const u32 c = s_hist[j];
             if (c) atomicAdd(&ghist[j], (u64)c);
         }
+    }
+}
+
+// ---- expansion fused with the FIRST distribution pass of the bucketed hash reduce -------------------------------
+// The first pass of an LSD sort needs no stability (there is no earlier order to preserve), and the digit is made of
+// hash bits (uniform whatever the aid skew).  So the tile's keys never go to HBM in expansion order: they are ranked
+// inside the tile with one shared-memory fetch-and-add per key (any order inside a digit will do), staged in digit
+// order, and each digit's run is appended to that digit's REGION -- room is reserved with one global atomic per
+// (tile, digit) on the region's fill counter.  Regions hold their expected share + slack; a reservation that
+// does not fit raises HR_FLAG_FUSED_OVERFLOW (the host re-runs the unfused way) and the run is dropped.
+// Saves one write and one read of every key (16 of 64 B/key) and the pass's look-back chain.
+//   reg_base[d]  byte address of region d (own HBM, or a peer's receive stripe mapped over NVLink: the multi-GPU
+//                exchange IS this pass when the digit's high bits are the destination rank)
+//   d = ((owner rank of the key) << sub_bits) | ((mixed key >> sh1) & (2^sub_bits - 1));  owner = 0 when n_dest <= 1
+//   keep range   only digits in [d_lo, d_hi) are kept (chunked runs take the hash space a digit range at a time, so
+//                every chunk holds complete sums and thresholds stay fused)
+//   pl / ghist   digit histograms of the REMAINING passes, over the kept keys, per destination rank:
+//                ghist[(dest * pl.n + p) * RS_RADIX + digit]
+struct ScatterArgs {
+    const u64* reg_base;     // [n_digits] device array of byte addresses
+    const u64* reg_cap;      // [n_digits] region capacities in keys
+    unsigned long long* cursor;   // [n_digits] keys appended to each region so far
+    u32* flags;
+    int sh1, sub_bits;
+    u32 n_digits, d_lo, d_hi;
+    u32 n_dest;
+};
+
+template <bool SELF, bool CANON, bool DIST>
+__global__ void __launch_bounds__(EX_THREADS, 4)
+expand_scatter_kernel(const u32* __restrict__ rec_src, const u32* __restrict__ rec_lo,
+                      const u64* __restrict__ rec_off, const u32* __restrict__ tile_rec,
+                      const u32* __restrict__ aid_src, const u32* __restrict__ aid_tgt, u64 out_begin,
+                      u64 out_end, KeyMix mix, int64_t n_tiles, PassList pl, u64* __restrict__ ghist, ScatterArgs sa) {
+    __shared__ __align__(16) u32 s_buf[3 * EX_PITCH];
+    __shared__ u32 s_src[SELF ? EX_TILE + 1 : 1];
+    __shared__ u32 s_cnt[RS_RADIX];                   // keys of the tile per digit, then their first staging slot
+    __shared__ u64 s_gptr[RS_RADIX];                  // byte address of the digit's run - 8 * first staging slot; 0 = dropped
+    __shared__ u32 s_scan[EX_THREADS / 32 + 1];
+    extern __shared__ u32 s_hist[];                   // [n_dest][pl.n][RS_RADIX]
+    u32* s_off = s_buf;
+    u32* s_lo = s_buf + EX_PITCH;
+    u32* s_aid = s_buf + 2 * EX_PITCH;
+    u64* s_out = reinterpret_cast<u64*>(s_buf);       // [EX_TILE]
+    const int tid = threadIdx.x;
+    const u32 nd = DIST ? sa.n_dest : 1u;
+    const int n_hist = (int)nd * pl.n * RS_RADIX;
+    for (int j = tid; j < n_hist; j += EX_THREADS) s_hist[j] = 0;
+    for (int j = tid; j < RS_RADIX; j += EX_THREADS) s_cnt[j] = 0;
+    const u32 sub_mask = (1u << sa.sub_bits) - 1u;
+    __syncthreads();
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        u32 n_out;
+        const u32 n_rec = stage_tile_records<SELF>(rec_src, rec_lo, rec_off, tile_rec, aid_src, out_begin, out_end, tile,
+                                                   s_off, s_lo, s_aid, s_src, &n_out);
+        u64 key[EX_PER];
+        const u32 k0 = (u32)EX_PER * tid;
+        // DIST: plain keys first -- the owner rank is a function of the plain aid -- mixed right below
+        if (DIST) make_tile_keys<SELF, CANON, false>(s_off, s_lo, s_aid, s_src, n_rec, n_out, aid_tgt, 0u, mix, key);
+        else make_tile_keys<SELF, CANON, true>(s_off, s_lo, s_aid, s_src, n_rec, n_out, aid_tgt, 0u, mix, key);
+        u32 dig[(EX_PER + 3) / 4];                    // digits, 8 bits each
+        u32 rnk[EX_PER / 2];                          // ranks inside (tile, digit), 16 bits each
+#pragma unroll
+        for (int q = 0; q < (EX_PER + 3) / 4; ++q) dig[q] = 0;
+#pragma unroll
+        for (int q = 0; q < EX_PER / 2; ++q) rnk[q] = 0;
+        u32 keep = 0;
+        if (k0 < n_out) {
+#pragma unroll
+            for (int q = 0; q < EX_PER; ++q) {
+                if (k0 + q < n_out) {
+                    u32 dest = 0;
+                    if (DIST) {
+                        const u64 plain = key[q];
+                        dest = hash_dest((u32)(plain >> 32), sa.n_dest);          // owner of the row (aid, .)
+                        key[q] = key_mix_fwd(mix, (u32)(plain >> 32), (u32)plain);
+                    }
+                    const u32 d = (dest << sa.sub_bits) | ((u32)(key[q] >> sa.sh1) & sub_mask);
+                    if (d >= sa.d_lo && d < sa.d_hi) {
+                        keep |= 1u << q;
+                        const u32 r = atomicAdd(&s_cnt[d], 1u);
+                        dig[q >> 2] |= d << (8 * (q & 3));
+                        rnk[q >> 1] |= r << (16 * (q & 1));
+                    }
+                }
+            }
+            for (int p = 0; p < pl.n; ++p) {              // histograms of the remaining passes, kept keys only
+                const int sh = pl.shift[p];
+                const u32 msk = (1u << pl.bits[p]) - 1u;
+#pragma unroll
+                for (int q = 0; q < EX_PER; ++q)
+                    if ((keep >> q) & 1u) {
+                        const u32 dest = DIST ? ((dig[q >> 2] >> (8 * (q & 3))) & 0xFFu) >> sa.sub_bits : 0u;
+                        atomicAdd(&s_hist[(dest * pl.n + p) * RS_RADIX + ((u32)(key[q] >> sh) & msk)], 1u);
+                    }
+            }
+        }
+        __syncthreads();                                  // ranks are final; the staged records are no longer needed
+        // per digit: first staging slot, and room in the digit's region
+        u32 c = 0;
+        if (tid < (int)sa.n_digits) c = s_cnt[tid];
+        u32 kept_total;
+        const u32 dstart = block_exclusive_scan<u32, EX_THREADS>(c, s_scan, &kept_total);
+        if (tid < (int)sa.n_digits) {
+            s_cnt[tid] = dstart;
+            u64 gp = 0;
+            if (c) {
+                const unsigned long long g = atomicAdd(&sa.cursor[tid], (unsigned long long)c);
+                if (g + c <= sa.reg_cap[tid]) gp = sa.reg_base[tid] + (g - (u64)dstart) * 8ull;
+                else atomicOr(sa.flags, HR_FLAG_FUSED_OVERFLOW);
+            }
+            s_gptr[tid] = gp;
+        }
+        __syncthreads();
+        if (keep) {
+#pragma unroll
+            for (int q = 0; q < EX_PER; ++q)
+                if ((keep >> q) & 1u) {
+                    const u32 d = (dig[q >> 2] >> (8 * (q & 3))) & 0xFFu;
+                    const u32 r = (rnk[q >> 1] >> (16 * (q & 1))) & 0xFFFFu;
+                    s_out[s_cnt[d] + r] = key[q];
+                }
+        }
+        __syncthreads();
+        // digit-ordered runs out: slot j belongs to the digit whose [first slot, next first slot) holds j; the digit
+        // is recomputed from the key itself (dest is not part of the mixed key: look it up by slot when n_dest > 1)
+#pragma unroll
+        for (int it = 0; it < EX_TILE / EX_THREADS; ++it) {
+            const u32 j = (u32)it * EX_THREADS + tid;
+            if (j < kept_total) {
+                const u64 k = s_out[j];
+                u32 d;
+                if (DIST) {                               // last digit whose first slot is <= j
+                    u32 lo = 0, hi = sa.n_digits;
+                    while (hi - lo > 1) {
+                        const u32 mid = (lo + hi) >> 1;
+                        if (s_cnt[mid] <= j) lo = mid; else hi = mid;
+                    }
+                    d = lo;
+                } else {
+                    d = (u32)(k >> sa.sh1) & sub_mask;
+                }
+                const u64 gp = s_gptr[d];
+                if (gp) __stcs(reinterpret_cast<u64*>(gp + 8ull * j), k);
+            }
+        }
+        __syncthreads();                                  // s_buf is re-staged by the next tile
+        if (tid < RS_RADIX) s_cnt[tid] = 0;               // (the barrier at the end of stage_tile_records orders this)
+    }
+    __syncthreads();
+    for (int j = tid; j < n_hist; j += EX_THREADS) {
+        const u32 c = s_hist[j];
+        if (c) atomicAdd(&ghist[j], (u64)c);
     }
 }
 
@@ -316,7 +498,9 @@ struct Segment {
 struct ExpandPlan {
     ottocov_spec spec;
     int A = 0;
-    u32 W = 0;
+    u32 W = 0;                       // symmetric range |dt| <= W ...
+    bool general = false;            // ... or the general range dt_lo <= dt <= dt_hi
+    int64_t dt_lo = 0, dt_hi = 0;
     bool sym = false;
     u32 user_min = 1;
     int aid_bits = 1;
@@ -345,13 +529,19 @@ static ExpandPlan* make_plan(ottocov_ctx* ctx, const ottocov_spec* spec, bool di
     try {
         pl->spec = *spec;
         pl->A = spec->type_this;
-        pl->W = (u32)(spec->window > 86400 ? 86400 : spec->window);   // count_co_events.py:33-36
+        // |dt| <= window (count_co_events.py:69) inside the pre-filter dt_min <= dt <= dt_max (:33-36, config.py:41-42)
+        const int64_t pre_lo = (spec->flags & OTTOCOV_DT_RANGE) ? spec->dt_min : -86400;
+        const int64_t pre_hi = (spec->flags & OTTOCOV_DT_RANGE) ? spec->dt_max : 86400;
+        pl->dt_lo = pre_lo > -spec->window ? pre_lo : -spec->window;
+        pl->dt_hi = pre_hi < spec->window ? pre_hi : spec->window;
+        pl->general = pl->dt_lo != -pl->dt_hi || pl->dt_hi > 0x7FFFFFFFll || pl->dt_hi < 0;
+        pl->W = pl->general ? 0u : (u32)pl->dt_hi;
         pl->aid_bits = ctx->info.aid_bits > 0 ? ctx->info.aid_bits : 1;
         pl->user_min = spec->min_count > 1 ? spec->min_count : 1;
         // symmetric shortcut: one canonical key per unordered event pair, mirrored after the reduce.  It
         // pays when few rows are left to mirror (a threshold) or when the keys are about to cross NVLink
         // anyway; OTTOCOV_SYM_OFF / OTTOCOV_SYM_ON force the choice.
-        const bool sym_kind = spec->next_mask == (1u << pl->A);
+        const bool sym_kind = spec->next_mask == (1u << pl->A) && !pl->general;
         pl->sym = sym_kind && !(spec->flags & OTTOCOV_SYM_OFF) &&
                   ((spec->flags & OTTOCOV_SYM_ON) || pl->user_min > 1 || distributed);
         const TypeArray& src = ctx->ta[pl->A];
@@ -362,11 +552,15 @@ static ExpandPlan* make_plan(ottocov_ctx* ctx, const ottocov_spec* spec, bool di
             Segment* sg = new Segment();
             pl->segs.push_back(sg);
             sg->tgt_type = B;
-            sg->self = (pl->A == B);
+            const bool self_in = (pl->A == B) && pl->dt_lo <= 0 && pl->dt_hi >= 0;
+            sg->self = pl->general ? self_in : (pl->A == B);
             const u32* xr = nullptr;
             if (!sg->self) xr = (B == (pl->A + 1) % 3) ? src.xrank[0] : src.xrank[1];
             DevBuf<u32> lo(ctx, src.n), cnt(ctx, src.n);
-            if (pl->sym)
+            if (pl->general)
+                COV_LAUNCH(ctx, OTTOCOV_K_WINDOW, 20.0 * src.n, window_range_kernel, (unsigned)ceil_div64(src.n, 256), 256, 0,
+                           src.skey, src.n, tgt.skey, (u32)tgt.n, pl->dt_lo, pl->dt_hi, self_in ? 1 : 0, lo.p, cnt.p);
+            else if (pl->sym)
                 COV_LAUNCH(ctx, OTTOCOV_K_WINDOW, 16.0 * src.n, window_fwd_kernel, (unsigned)ceil_div64(src.n, 256), 256, 0,
                            src.skey, src.n, pl->W, lo.p, cnt.p);
             else
@@ -436,6 +630,164 @@ static void expand_range(ottocov_ctx* ctx, const ExpandPlan* pl, u64 c0, u64 c1,
     }
 }
 
+// The whole plan expanded by expand_scatter_kernel: every segment appends to the same digit regions.
+// ghist: device [n_dest][rest.n][RS_RADIX], zeroed by the caller.
+static void expand_scatter_all(ottocov_ctx* ctx, const ExpandPlan* pl, const KeyMix& mix, const PassList& rest, u64* ghist,
+                               const ScatterArgs& sa) {
+    const TypeArray& src = ctx->ta[pl->A];
+    const u32 nd = sa.n_dest > 1 ? sa.n_dest : 1u;
+    const size_t hist_smem = (size_t)nd * rest.n * RS_RADIX * sizeof(u32);
+    for (Segment* sg : pl->segs) {
+        if (sg->n_pairs == 0) continue;
+        const int64_t n_tiles = ceil_div64((int64_t)sg->n_pairs, EX_TILE);
+        DevBuf<u32> tile_rec(ctx, n_tiles + 1);
+        COV_LAUNCH(ctx, OTTOCOV_K_EXPAND, 0, tile_search_kernel, (unsigned)ceil_div64(n_tiles + 1, 256), 256, 0,
+                   sg->rec_off.p, (int64_t)sg->n_rec, (u64)0, (u64)sg->n_pairs, n_tiles, tile_rec.p);
+        const TypeArray& tgt = ctx->ta[sg->tgt_type];
+        const double bytes = 8.0 * (double)sg->n_pairs;
+#define EXS_LAUNCH(SELF_, CANON_)                                                                                       \
+        do {                                                                                                            \
+            auto kern = sa.n_dest > 1 ? expand_scatter_kernel<SELF_, CANON_, true> : expand_scatter_kernel<SELF_, CANON_, false>; \
+            if (hist_smem > 8192) cov_func_smem(ctx, (const void*)kern, hist_smem);                                     \
+            int per_sm = 0;                                                                                             \
+            CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, EX_THREADS, hist_smem));            \
+            const unsigned grid = (unsigned)imin64(n_tiles, (int64_t)ctx->num_sms * (per_sm > 0 ? per_sm : 1));          \
+            COV_LAUNCH(ctx, OTTOCOV_K_EXPAND, bytes, kern, grid, EX_THREADS, hist_smem, sg->rec_src.p, sg->rec_lo.p,    \
+                       sg->rec_off.p, tile_rec.p, src.aid, tgt.aid, (u64)0, (u64)sg->n_pairs, mix, n_tiles, rest, ghist, sa); \
+        } while (0)
+        if (pl->sym) EXS_LAUNCH(false, true);
+        else if (sg->self) EXS_LAUNCH(true, false);
+        else EXS_LAUNCH(false, false);
+#undef EXS_LAUNCH
+    }
+}
+
+// Region table of one chunk (digits [d_lo, d_hi)): uniform regions of `cap` keys, or -- after an overflow -- exact
+// regions sized by the fill counters of the failed attempt (`fill`, which kept counting past the capacity).
+__global__ void __launch_bounds__(RS_RADIX) region_table_kernel(u64* reg_base, u64* reg_cap, u64* reg_off, u64 base_addr, u64 cap,
+                                                                const unsigned long long* fill, u64 pad, u32 d_lo, u32 d_hi) {
+    __shared__ u64 s_warp[RS_RADIX / 32 + 1];
+    const u32 d = threadIdx.x;
+    const bool in = d >= d_lo && d < d_hi;
+    u64 c = 0;
+    if (in) c = fill ? (((u64)fill[d] + pad + 1) & ~1ull) : cap;
+    u64 tot;
+    const u64 off = block_exclusive_scan<u64, RS_RADIX>(c, s_warp, &tot);
+    reg_cap[d] = c;
+    reg_off[d] = off;
+    reg_base[d] = in ? base_addr + off * 8ull : 0ull;
+}
+
+// Slack of a digit region over its expected share, in percent (test knob: a negative value forces the overflow
+// retry).  Hashed digits are uniform; what the slack absorbs is the multiplicity of hot pairs.
+static int fuse_slack_pct() {
+    static int v = -1000;
+    if (v == -1000) { const char* e = getenv("OTTOCOV_FUSE_SLACK_PCT"); v = e ? atoi(e) : 25; if (v < -90) v = -90; }
+    return v;
+}
+static bool fuse_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("OTTOCOV_NO_FUSED_PASS"); v = (e && atoi(e)) ? 0 : 1; }
+    return v != 0;
+}
+
+// Bucketed hash reduce with its first distribution pass fused into the expansion (hash_reduce.cu, HashPre).
+// The hash space is taken `digits per chunk` digit regions at a time when the key buffers would not fit the pair
+// budget; every chunk holds complete sums, so the threshold and the symmetric mirror stay fused whatever the chunking.
+// Returns the partial tables (disjoint key sets) in `partials`.
+static void count_fused(ottocov_ctx* ctx, const ExpandPlan* pl, const KeyMix& mix, u64 budget, u32 min_count,
+                        std::vector<ottocov_table*>& partials, ottocov_count_info& ci) {
+    const u64 P = pl->P;
+    const int bb = hashed_bucket_bits((int64_t)P, mix.kb);
+    BitField bucket_field[1] = {{mix.kb - bb, mix.kb}};
+    const PassList full = make_pass_list(bucket_field, 1);
+    BitField rest_field[1] = {{mix.kb - bb + full.bits[0], mix.kb}};
+    const PassList rest = make_pass_list(rest_field, 1);
+    const u32 n_digits = 1u << full.bits[0];
+    DevBuf<u64> reg(ctx, 3 * RS_RADIX);                                  // byte addresses | capacities | key offsets
+    u64* reg_base = reg.p; u64* reg_cap = reg.p + RS_RADIX; u64* reg_off = reg.p + 2 * RS_RADIX;
+    DevBuf<unsigned long long> cursor(ctx, 2 * RS_RADIX);                // fill counters | copy kept for an exact retry
+    DevBuf<unsigned long long> ctr(ctx, 2);
+    DevBuf<u64> ghist(ctx, (size_t)rest.n * RS_RADIX);
+    const u64 cap = (((u64)((double)P / n_digits * (1.0 + fuse_slack_pct() / 100.0)) + 4096) + 1) & ~1ull;
+    const u64 pad = 64;
+    unsigned long long fill[RS_RADIX];
+    bool exact = false;                  // regions of this chunk sized by `fill` (second attempt after an overflow)
+    u32 d0 = 0;
+    while (d0 < n_digits) {
+        u32 dc = 0;                      // digit regions of this chunk
+        u64 total = 0;                   // keys its buffer holds
+        if (!exact) {
+            dc = (u32)(budget / cap);
+            if (dc < 1) dc = 1;
+            if (dc > n_digits - d0) dc = n_digits - d0;
+            total = (u64)dc * cap;
+        } else {
+            while (d0 + dc < n_digits) {
+                const u64 need = ((u64)fill[d0 + dc] + pad + 1) & ~1ull;
+                if (dc > 0 && total + need > budget) break;
+                total += need; ++dc;
+            }
+        }
+        const bool single = dc == n_digits;
+        DevBuf<u64> keys(ctx, (size_t)total);
+        if (exact) CUDA_CHECK(cudaMemcpyAsync(cursor.p + RS_RADIX, cursor.p, RS_RADIX * sizeof(unsigned long long),
+                                              cudaMemcpyDeviceToDevice, ctx->stream));
+        CUDA_CHECK(cudaMemsetAsync(cursor.p, 0, RS_RADIX * sizeof(unsigned long long), ctx->stream));
+        CUDA_CHECK(cudaMemsetAsync(ctr.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
+        CUDA_CHECK(cudaMemsetAsync(ghist.p, 0, (size_t)rest.n * RS_RADIX * sizeof(u64), ctx->stream));
+        COV_LAUNCH(ctx, OTTOCOV_K_MISC, 0, region_table_kernel, 1, RS_RADIX, 0, reg_base, reg_cap, reg_off,
+                   reinterpret_cast<u64>(keys.p), cap, exact ? cursor.p + RS_RADIX : (const unsigned long long*)nullptr, pad,
+                   d0, d0 + dc);
+        ScatterArgs sa;
+        sa.reg_base = reg_base; sa.reg_cap = reg_cap; sa.cursor = cursor.p; sa.flags = reinterpret_cast<u32*>(ctr.p + 1);
+        sa.sh1 = full.shift[0]; sa.sub_bits = full.bits[0]; sa.n_digits = n_digits; sa.d_lo = d0; sa.d_hi = d0 + dc;
+        sa.n_dest = 0;
+        expand_scatter_all(ctx, pl, mix, rest, ghist.p, sa);
+        cov_trace(ctx, "count: expand + first pass (fused)");
+        // keys of this chunk: all of them when the chunk covers every digit (no host round trip), else the sum of
+        // the fill counters
+        u64 n_c = P;
+        bool overflow = false;
+        if (!single || exact) {
+            cov_readback(ctx, fill, cursor.p, RS_RADIX * sizeof(unsigned long long));
+            unsigned long long fl[2];
+            cov_readback(ctx, fl, ctr.p, sizeof(fl));
+            overflow = (fl[1] & HR_FLAG_FUSED_OVERFLOW) != 0;
+            n_c = 0;
+            for (u32 d = d0; d < d0 + dc; ++d) n_c += fill[d];
+        }
+        ottocov_table* part = nullptr;
+        if (!overflow && n_c > 0) {
+            DevBuf<u64> alt(ctx, (size_t)n_c);
+            HashPre pre;
+            pre.bb = bb; pre.first_bits = full.bits[0];
+            pre.seg_cnt = reinterpret_cast<const u64*>(cursor.p + d0); pre.n_a = 1; pre.n_b = (int)dc;
+            pre.seg_off = reg_off + d0; pre.ctr = ctr.p;
+            int passes = 0;
+            try {
+                part = hashed_reduce(ctx, keys.p, alt.p, (int64_t)n_c, mix, min_count, pl->sym, pl->sym, &passes, ghist.p, &pre);
+                ci.sort_passes = passes;
+            } catch (const FusedOverflow&) {
+                overflow = true;
+                cov_readback(ctx, fill, cursor.p, RS_RADIX * sizeof(unsigned long long));
+            }
+        }
+        if (overflow) {              // the counters kept counting: they now hold what each region really needs
+            if (exact) COV_THROW(OTTOCOV_ERR_CUDA, "fused first pass overflowed regions sized by its own counters");
+            exact = true;
+            cov_trace(ctx, "count: region overflow, retrying with exact regions");
+            continue;                // same d0
+        }
+        exact = false;
+        if (part) partials.push_back(part);
+        ci.n_chunks += 1;
+        ci.fused = 1;
+        d0 += dc;
+        cov_trace(ctx, "count: bucket passes + hash reduce");
+    }
+}
+
 // cudaMemGetInfo is a driver round trip (it serialises with whatever else talks to the driver), and free + parked
 // bytes barely move between steps: the figure is cached per context and refreshed when a count would not fit it.
 static u64 auto_budget(ottocov_ctx* ctx, bool refresh) {
@@ -482,6 +834,23 @@ ottocov_table* count_impl(ottocov_ctx* ctx, const ottocov_spec* spec) {
         ottocov_ctx* c; std::vector<ottocov_table*>& v;
         ~PartGuard() { for (auto* t : v) { dev_free(c, t->keys); dev_free(c, t->count); delete t; } }
     } pguard{ctx, partials};
+
+    // Fused path: bucketed hash reduce whose first pass runs inside the expansion.  Chunks are hash-digit ranges, so
+    // sums are complete per chunk and the user's threshold stays fused whatever the budget.
+    const int bb_all = hashed_bucket_bits((int64_t)P, mix.kb);
+    const bool hashed_any = hashed_reduce_supported(aid_bits) && !(spec->flags & OTTOCOV_HASH_OFF) &&
+                            ((spec->flags & OTTOCOV_HASH_ON) || pl->user_min > 1);
+    const bool fused = hashed_any && fuse_enabled() && bb_all > RS_MAX_BITS;     // at least one pass after the fused one
+    if (fused) {
+        count_fused(ctx, pl, mix, budget, pl->user_min, partials, ci);
+        mirrored = sym;
+        ottocov_table* result;
+        if (partials.empty()) result = make_empty_table(aid_bits);
+        else if (partials.size() == 1) { result = partials[0]; partials.clear(); }
+        else result = merge_tables_impl(ctx, partials.data(), (int)partials.size());     // disjoint key sets: a sort
+        ci.n_unique = result->n;
+        return result;
+    }
 
     BitField fields[2] = {{0, aid_bits}, {32, 32 + aid_bits}};
     for (u64 c0 = 0; c0 < P; c0 += budget) {
@@ -544,6 +913,163 @@ ottocov_table* count_impl(ottocov_ctx* ctx, const ottocov_spec* spec) {
     cov_trace(ctx, "count: mirror/merge");
     ci.n_unique = result->n;
     return result;
+}
+
+// ---- fused expansion + exchange (include/ottocov.h, "fused expansion + exchange") -----------------------------------
+static inline int64_t align16(int64_t v) { return (v + 15) & ~(int64_t)15; }
+
+static PassList xplan_rest_passes(const ottocov_xplan* plan) {
+    const int kb = 2 * plan->aid_bits;
+    BitField f[1] = {{kb - plan->bucket_bits + plan->sub_bits, kb}};
+    return make_pass_list(f, 1);
+}
+
+void xplan_make_impl(int n_ranks, int aid_bits, int64_t max_local_keys, int64_t total_keys, int64_t stripe_cap,
+                     int64_t mirror_cap, ottocov_xplan* out) {
+    if (n_ranks < 2 || n_ranks > XCH_MAX_RANKS) COV_THROW(OTTOCOV_ERR_ARG, "fused exchange needs 2..%d ranks", XCH_MAX_RANKS);
+    if (!hashed_reduce_supported(aid_bits) || 2 * aid_bits < 8) COV_THROW(OTTOCOV_ERR_ARG, "fused exchange needs 4 <= aid_bits <= 28");
+    if (max_local_keys < 0 || total_keys < 0) COV_THROW(OTTOCOV_ERR_ARG, "negative key count");
+    memset(out, 0, sizeof(*out));
+    const int kb = 2 * aid_bits;
+    int sub = 0;
+    while ((n_ranks << (sub + 1)) <= 128) ++sub;            // (owner, sub-digit) digits: n_ranks << sub <= 128
+    int bb = hashed_bucket_bits(total_keys / n_ranks, kb);  // buckets of the keys one rank receives
+    if (bb < sub + 1) bb = sub + 1;                          // at least one pass after the fused one
+    if (bb > kb) { bb = kb; if (sub > bb - 1) sub = bb - 1; }
+    out->n_ranks = n_ranks; out->aid_bits = aid_bits; out->bucket_bits = bb; out->sub_bits = sub;
+    out->rest_passes = xplan_rest_passes(out).n;
+    const int64_t n_sub = (int64_t)1 << sub;
+    if (stripe_cap <= 0) stripe_cap = (int64_t)((double)max_local_keys / (double)(n_ranks * n_sub) * 1.25) + 2048;
+    if (mirror_cap <= 0) { mirror_cap = max_local_keys / (8 * (int64_t)n_ranks); if (mirror_cap < (1 << 16)) mirror_cap = 1 << 16; }
+    out->stripe_cap = (stripe_cap + 1) & ~(int64_t)1;
+    out->mirror_cap = (mirror_cap + 3) & ~(int64_t)3;
+    int64_t o = 0;
+    out->off_counts = o;  o = align16(o + (int64_t)n_ranks * n_sub * 8);
+    out->off_status = o;  o = align16(o + (int64_t)n_ranks * 4 * 8);
+    out->off_hist = o;    o = align16(o + (int64_t)n_ranks * out->rest_passes * RS_RADIX * 8);
+    out->off_keys = o;    o = align16(o + (int64_t)n_ranks * n_sub * out->stripe_cap * 8);
+    out->off_mstatus = o; o = align16(o + (int64_t)n_ranks * 4 * 8);
+    out->off_mkeys = o;   o = align16(o + (int64_t)n_ranks * out->mirror_cap * 8);
+    out->off_mcnt = o;    o = align16(o + (int64_t)n_ranks * out->mirror_cap * 4);
+    out->total_bytes = o;
+}
+
+// one block per destination rank: this source's stripe counts, pass histograms and status go to every rank
+__global__ void __launch_bounds__(256) publish_scatter_kernel(PeerBases pb, ottocov_xplan plan, int rank,
+                                                             const unsigned long long* __restrict__ cursor,
+                                                             const u64* __restrict__ ghist, const u32* __restrict__ flags) {
+    const int dest = blockIdx.x;
+    const int n_sub = 1 << plan.sub_bits;
+    const u64 base = pb.p[dest];
+    u64* counts = reinterpret_cast<u64*>(base + plan.off_counts) + (size_t)rank * n_sub;
+    for (int j = threadIdx.x; j < n_sub; j += blockDim.x) counts[j] = cursor[dest * n_sub + j];
+    u64* hist = reinterpret_cast<u64*>(base + plan.off_hist) + (size_t)rank * plan.rest_passes * RS_RADIX;
+    const u64* mine = ghist + (size_t)dest * plan.rest_passes * RS_RADIX;
+    for (int j = threadIdx.x; j < plan.rest_passes * RS_RADIX; j += blockDim.x) hist[j] = mine[j];
+    if (threadIdx.x == 0) {
+        u64 need = 0;
+        for (int d = 0; d < plan.n_ranks * n_sub; ++d) need = cursor[d] > need ? cursor[d] : need;
+        u64* st = reinterpret_cast<u64*>(base + plan.off_status) + (size_t)rank * 4;
+        st[0] = (u64)(*flags);
+        st[1] = need;
+        st[2] = 0; st[3] = 0;
+    }
+}
+
+void expand_scatter_impl(ottocov_ctx* ctx, const ottocov_xplan* plan, int rank, const u64* peer_base_host) {
+    ExpandPlan* pl = static_cast<ExpandPlan*>(ctx->plan);
+    if (!pl) COV_THROW(OTTOCOV_ERR_STATE, "ottocov_expand_scatter before ottocov_expand_prepare");
+    struct PlanFree { ottocov_ctx* c; ~PlanFree() { free_plan(c); } } pf{ctx};
+    const int R = plan->n_ranks;
+    if (R < 2 || R > XCH_MAX_RANKS || rank < 0 || rank >= R) COV_THROW(OTTOCOV_ERR_ARG, "bad rank / n_ranks");
+    if (pl->aid_bits > plan->aid_bits) COV_THROW(OTTOCOV_ERR_ARG, "local aids need %d bits, the plan has %d", pl->aid_bits, plan->aid_bits);
+    const KeyMix mix = make_key_mix(plan->aid_bits);
+    const PassList rest = xplan_rest_passes(plan);
+    if (rest.n != plan->rest_passes || rest.n < 1) COV_THROW(OTTOCOV_ERR_ARG, "inconsistent exchange plan");
+    const int n_sub = 1 << plan->sub_bits;
+    const u32 n_digits = (u32)R * n_sub;
+    DevBuf<u64> reg(ctx, 2 * RS_RADIX);
+    DevBuf<unsigned long long> cursor(ctx, RS_RADIX + 2);               // + [flags word]
+    DevBuf<u64> ghist(ctx, (size_t)R * rest.n * RS_RADIX);
+    u64 h[2 * RS_RADIX];
+    memset(h, 0, sizeof(h));
+    PeerBases pb;
+    memset(&pb, 0, sizeof(pb));
+    for (int d = 0; d < R; ++d) {
+        pb.p[d] = peer_base_host[d];
+        for (int sb = 0; sb < n_sub; ++sb) {
+            h[d * n_sub + sb] = peer_base_host[d] + (u64)plan->off_keys + ((u64)(rank * n_sub + sb) * (u64)plan->stripe_cap) * 8ull;
+            h[RS_RADIX + d * n_sub + sb] = (u64)plan->stripe_cap;
+        }
+    }
+    CUDA_CHECK(cudaMemcpyAsync(reg.p, h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));    // pageable: staged before return
+    CUDA_CHECK(cudaMemsetAsync(cursor.p, 0, (RS_RADIX + 2) * sizeof(unsigned long long), ctx->stream));
+    CUDA_CHECK(cudaMemsetAsync(ghist.p, 0, (size_t)R * rest.n * RS_RADIX * sizeof(u64), ctx->stream));
+    ScatterArgs sa;
+    sa.reg_base = reg.p; sa.reg_cap = reg.p + RS_RADIX; sa.cursor = cursor.p;
+    sa.flags = reinterpret_cast<u32*>(cursor.p + RS_RADIX);
+    sa.sh1 = mix.kb - plan->bucket_bits; sa.sub_bits = plan->sub_bits; sa.n_digits = n_digits; sa.d_lo = 0; sa.d_hi = n_digits;
+    sa.n_dest = (u32)R;
+    if (pl->P > 0) expand_scatter_all(ctx, pl, mix, rest, ghist.p, sa);
+    COV_LAUNCH(ctx, OTTOCOV_K_PARTITION, 0, publish_scatter_kernel, R, 256, 0, pb, *plan, rank, cursor.p, ghist.p, sa.flags);
+}
+
+__global__ void __launch_bounds__(256) sum_hist_kernel(const u64* __restrict__ per_src, int n_src, int n, u64* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    u64 s = 0;
+    for (int r = 0; r < n_src; ++r) s += per_src[(size_t)r * n + j];
+    out[j] = s;
+}
+
+__global__ void __launch_bounds__(256) stripe_off_kernel(u64* off, int n, u64 cap) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) off[j] = (u64)j * cap;
+}
+
+ottocov_table* reduce_received_impl(ottocov_ctx* ctx, const ottocov_xplan* plan, u64 recv_area, u32 min_count, int sym,
+                                    int64_t* need_cap) {
+    const int R = plan->n_ranks;
+    const int n_sub = 1 << plan->sub_bits;
+    *need_cap = 0;
+    // what every source published: [R][n_sub] stripe counts, then [R][4] status words (contiguous in the layout)
+    const size_t words = (size_t)(plan->off_status - plan->off_counts) / 8 + (size_t)R * 4;
+    if (words * 8 > 4096) COV_THROW(OTTOCOV_ERR_ARG, "exchange header larger than the read-back pad");
+    u64 hdr[512];
+    cov_readback(ctx, hdr, reinterpret_cast<const void*>(recv_area + plan->off_counts), words * 8);
+    const u64* st = hdr + (size_t)(plan->off_status - plan->off_counts) / 8;
+    u64 need = 0; bool over = false;
+    for (int r = 0; r < R; ++r) {
+        if (st[r * 4 + 0] & HR_FLAG_FUSED_OVERFLOW) over = true;
+        if (st[r * 4 + 1] > need) need = st[r * 4 + 1];
+    }
+    if (over || need > (u64)plan->stripe_cap) { *need_cap = (int64_t)need; return nullptr; }
+    int64_t n = 0;
+    for (int j = 0; j < R * n_sub; ++j) n += (int64_t)hdr[j];
+    const KeyMix mix = make_key_mix(plan->aid_bits);
+    ottocov_table* out = nullptr;
+    memset(&ctx->last_count, 0, sizeof(ctx->last_count));
+    if (n == 0) { out = new ottocov_table(); out->aid_bits = plan->aid_bits; return out; }
+    const PassList rest = xplan_rest_passes(plan);
+    DevBuf<u64> ghist(ctx, (size_t)rest.n * RS_RADIX);
+    COV_LAUNCH(ctx, OTTOCOV_K_MISC, 0, sum_hist_kernel, (unsigned)ceil_div64(rest.n * RS_RADIX, 256), 256, 0,
+               reinterpret_cast<const u64*>(recv_area + plan->off_hist), R, rest.n * RS_RADIX, ghist.p);
+    DevBuf<u64> seg_off(ctx, (size_t)R * n_sub);
+    COV_LAUNCH(ctx, OTTOCOV_K_MISC, 0, stripe_off_kernel, (unsigned)ceil_div64(R * n_sub, 256), 256, 0, seg_off.p, R * n_sub,
+               (u64)plan->stripe_cap);
+    DevBuf<u64> alt(ctx, (size_t)n);
+    HashPre pre;
+    pre.bb = plan->bucket_bits; pre.first_bits = plan->sub_bits;
+    pre.seg_cnt = reinterpret_cast<const u64*>(recv_area + plan->off_counts); pre.seg_off = seg_off.p;
+    pre.n_a = R; pre.n_b = n_sub; pre.ctr = nullptr;
+    int passes = 0;
+    out = hashed_reduce(ctx, reinterpret_cast<u64*>(recv_area + plan->off_keys), alt.p, n, mix, min_count > 1 ? min_count : 1,
+                        sym != 0, false, &passes, ghist.p, &pre);
+    ctx->last_count.sort_passes = passes;
+    ctx->last_count.n_chunks = 1;
+    ctx->last_count.fused = 1;
+    ctx->last_count.n_unique = out->n;
+    return out;
 }
 
 // ---- multi-GPU building blocks: expand raw keys grouped by destination rank; reduce received keys --------

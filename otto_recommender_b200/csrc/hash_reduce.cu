@@ -25,8 +25,12 @@
 // adversarial input: buckets are balanced by the hash), a bucket tail runs past 2 M keys, or a tag
 // does not fit its field, a flag is raised and the host re-does the reduce with the full sort (the
 // mixed keys are un-mixed in place first).  Keys too wide for the packed word use an unpacked table
-// (64-bit key + 32-bit count); hash_reduce_big_kernel (one CTA per ~12 K-key bucket after one pass
-// less) is a measured, opt-in variant.
+// (64-bit key + 32-bit count).
+//
+// Fused first pass (round 2): the first distribution pass needs no stability (there is no earlier order to
+// keep), and hashed digits are uniform, so the expansion kernel itself scatters the keys into one slack region
+// per digit (expand.cu, expand_scatter_kernel).  hashed_reduce then starts from those regions (HashPre): the
+// remaining passes read them as segments.  HBM traffic: 8 P + (passes - 1) x 16 P + 8 P.
 #include "internal.cuh"
 #include "scan.cuh"
 
@@ -192,6 +196,7 @@ hash_reduce_kernel(const u64* __restrict__ keys, int64_t n, int rem_bits, KeyMix
     __shared__ unsigned long long s_base;
     __shared__ u32 s_over;
 
+    if (*flags & HR_FLAG_FUSED_OVERFLOW) return;           // incomplete input (see rs_onesweep_kernel): the host repeats the step
     const int tid = threadIdx.x;
     const int64_t t0 = (int64_t)blockIdx.x * HR_TILE;
     const int64_t t1 = min(n, t0 + (int64_t)HR_TILE);
@@ -254,71 +259,6 @@ hash_reduce_kernel(const u64* __restrict__ keys, int64_t n, int rem_bits, KeyMix
                          out_cap, flags);
 }
 
-// ---- big-bucket variant ---------------------------------------------------------------------------------------
-// One distribution pass costs as much as this whole kernel, so when TWO passes can already bring the buckets
-// down to ~12 K keys the third pass is dropped and the bucket is finished here instead: one CTA per bucket
-// (boundaries from a binary search per bucket), the bucket is walked 2^sub_bits times and round r counts only the
-// keys whose next sub_bits hash bits equal r -- each round's keys fit the same 8192-slot table.  The repeated
-// reads come from L2 (a bucket is ~90 KB); the number of shared-memory atomics, which bounds the kernel, is the
-// same one per key.
-constexpr int64_t HB_MAX_BUCKET = 4000000;       // keys; beyond that (a hot pair) the sort path serves the call
-static_assert(HB_MAX_BUCKET < (int64_t)HR_CMASK, "count field too narrow for a big bucket");
-
-__global__ void __launch_bounds__(256) bucket_bounds_kernel(const u64* __restrict__ keys, int64_t n, int rem_bits, int64_t nb,
-                                                            u32* __restrict__ bounds) {
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b > nb) return;
-    if (b == nb) { bounds[b] = (u32)n; return; }
-    const u64 target = (u64)b << rem_bits;
-    int64_t lo = 0, hi = n;                                // first index with keys >= target
-    while (lo < hi) {
-        const int64_t mid = lo + ((hi - lo) >> 1);
-        if (keys[mid] >= target) hi = mid; else lo = mid + 1;
-    }
-    bounds[b] = (u32)lo;
-}
-
-template <bool SYM>
-__global__ void __launch_bounds__(HR_THREADS, 3)
-hash_reduce_big_kernel(const u64* __restrict__ keys, const u32* __restrict__ bounds, int rem_bits, int sub_bits, KeyMix mix,
-                       u32 min_count, int mirror, u64* __restrict__ out_keys, u32* __restrict__ out_count,
-                       unsigned long long* __restrict__ out_n, u64 out_cap, u32* __restrict__ flags) {
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    u64* s_key = reinterpret_cast<u64*>(s_raw);                              // [HR_CAP] packed words
-    u32* s_scan = reinterpret_cast<u32*>(s_key + HR_CAP);                    // [HR_THREADS / 32 + 1]
-    __shared__ unsigned long long s_base;
-    __shared__ u32 s_over;
-    const int tid = threadIdx.x;
-    const int64_t s0 = bounds[blockIdx.x], e0 = bounds[blockIdx.x + 1];
-    if (s0 == e0) return;
-    if (e0 - s0 > HB_MAX_BUCKET) { if (tid == 0) atomicOr(flags, 4u); return; }
-    const u64 base = (u64)blockIdx.x << rem_bits;
-    const int rounds = 1 << sub_bits;
-    const int sub_shift = rem_bits - sub_bits;
-    if (tid == 0) s_over = 0;
-    for (int round = 0; round < rounds; ++round) {
-        hr_clear<true>(s_key, nullptr);
-        __syncthreads();
-        for (int64_t c0 = s0; c0 < e0; c0 += HR_TILE) {
-            u64 k[HR_IPT];
-#pragma unroll
-            for (int r = 0; r < HR_IPT; ++r) {
-                const int64_t i = c0 + r * HR_THREADS + tid;
-                k[r] = (i < e0) ? __ldg(keys + i) : HR_NONE;       // re-read every round: keep the lines in L2
-            }
-#pragma unroll
-            for (int r = 0; r < HR_IPT; ++r)
-                if (k[r] != HR_NONE && (int)((k[r] >> sub_shift) & (u64)(rounds - 1)) == round)
-                    hr_insert<true>(s_key, nullptr, k[r], base, 1u, flags);
-        }
-        __syncthreads();
-        if (!hr_emit<SYM, true>(s_key, nullptr, s_scan, &s_base, &s_over, base, mix, min_count, mirror, out_keys, out_count,
-                                out_n, out_cap, flags))
-            return;
-        __syncthreads();                                   // the table is cleared again by the next round
-    }
-}
-
 __global__ void __launch_bounds__(256) unmix_kernel(u64* __restrict__ keys, int64_t n, KeyMix mix) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) keys[i] = key_mix_inv(mix, keys[i]);
@@ -360,46 +300,23 @@ bool hashed_reduce_supported(int aid_bits) { return aid_bits >= 1 && 2 * aid_bit
 
 static size_t hr_smem_bytes(bool packed) { return (size_t)HR_CAP * 8 + (packed ? 0 : (size_t)HR_CAP * 4) + 32 * 4; }
 
-// How n mixed keys of kb bits are bucketed.
-//   small buckets (hash_reduce_kernel): <= OTTOCOV_HR_AVG (default 512) keys on average, tile-owned;
-//   big buckets (hash_reduce_big_kernel): <= 12288 keys on average, one CTA per bucket, 2^sub_bits rounds: it
-//   can save a distribution pass (742 M keys: 16 bucket bits = 2 passes instead of 21 = 3), but measured on the
-//   headline run the reduce then takes 10.7 ms instead of 5.4 (every key is looked at in each of the four rounds,
-//   four table scans per bucket) and the two 8-bit passes 4.9 ms each instead of 4.46: 21.1 ms against 19.3 ms.
-//   So it is opt-in: OTTOCOV_HR_MODE=2 takes big buckets whenever they are possible (the parity tests run
-//   with it in a child process), the default is small buckets.
-struct HashPlan { int bb; bool big; int sub_bits; };
-constexpr int64_t HB_AVG_BUCKET = 12288;
-constexpr int HB_SUB_BITS = 2;
-
-static HashPlan hashed_plan(int64_t n, int kb) {
+// How n mixed keys of kb bits are bucketed: <= OTTOCOV_HR_AVG (default 512) keys per bucket on average.
+// (A big-bucket variant that saves a pass at the price of four table rounds per bucket was measured slower in
+// round 1: experiments/round1_variants/hash_reduce_big_kernel.cu.txt.)
+int hashed_bucket_bits(int64_t n, int kb) {
     static int64_t avg_target = 0;
-    static int mode = 0;
     if (!avg_target) {
         const char* e = getenv("OTTOCOV_HR_AVG");                      // tuning knob
         avg_target = e ? atoll(e) : 512;
         if (avg_target < 16 || avg_target > 2048) avg_target = 512;
-        const char* m = getenv("OTTOCOV_HR_MODE");
-        mode = m ? atoi(m) : 0;
     }
-    HashPlan p;
-    p.big = false; p.sub_bits = 0; p.bb = 0;
-    while (p.bb < kb && (n >> p.bb) > avg_target) ++p.bb;
-    int bbig = 0;
-    while (bbig < kb && (n >> bbig) > HB_AVG_BUCKET) ++bbig;
-    const int passes_small = (p.bb + RS_MAX_BITS - 1) / RS_MAX_BITS, passes_big = (bbig + RS_MAX_BITS - 1) / RS_MAX_BITS;
-    const bool possible = kb <= HR_TAG_BITS && kb - bbig >= HB_SUB_BITS && n < (int64_t)0xFFFFFFFFll && bbig <= 20;
-    (void)passes_small; (void)passes_big;
-    if (mode == 2 && possible) {
-        p.bb = bbig; p.big = true; p.sub_bits = HB_SUB_BITS;
-    }
-    return p;
+    int bb = 0;
+    while (bb < kb && (n >> bb) > avg_target) ++bb;
+    return bb;
 }
 
-int hashed_bucket_bits(int64_t n, int kb) { return hashed_plan(n, kb).bb; }
-
 ottocov_table* hashed_reduce(ottocov_ctx* ctx, u64* keys, u64* alt, int64_t n, const KeyMix& mix, u32 min_count,
-                             bool sym, bool mirror, int* passes_out, u64* pre_hist) {
+                             bool sym, bool mirror, int* passes_out, u64* pre_hist, const HashPre* pre) {
     ottocov_table* out = new ottocov_table();
     out->aid_bits = mix.ab;
     if (passes_out) *passes_out = 0;
@@ -414,67 +331,59 @@ ottocov_table* hashed_reduce(ottocov_ctx* ctx, u64* keys, u64* alt, int64_t n, c
             const char* g = getenv("OTTOCOV_HR_NO_PACKED");             // test / tuning knob: wide table words
             no_packed = (g && atoi(g)) ? 1 : 0;
         }
-        const HashPlan plan = hashed_plan(n, mix.kb);
-        const int bb = plan.bb;
+        const int bb = pre ? pre->bb : hashed_bucket_bits(n, mix.kb);
         const int rem_bits = mix.kb - bb;
         BitField bucket_field[1] = {{rem_bits, mix.kb}};
+        PassList pl = make_pass_list(bucket_field, 1);
         u64* k = keys; u64* ka = alt; u32* v = nullptr; u32* va = nullptr;
-        const int passes = radix_sort_pairs(ctx, k, ka, v, va, n, bucket_field, 1, pre_hist);
+        int passes;
+        if (pre) {                      // pass 0 was done by whoever wrote the keys: they sit in its digit regions
+            const int b0 = pre->first_bits > 0 ? pre->first_bits : (pl.n > 0 ? pl.bits[0] : 0);
+            BitField rest_field[1] = {{rem_bits + b0, mix.kb}};
+            const PassList rest = make_pass_list(rest_field, 1);
+            if (rest.n < 1) COV_THROW(OTTOCOV_ERR_ARG, "fused first pass needs at least one more pass");
+            passes = 1 + radix_sort_passes(ctx, k, ka, v, va, n, rest, pre_hist, pre->seg_cnt, pre->seg_off, pre->n_a, pre->n_b,
+                                           pre->ctr ? reinterpret_cast<const u32*>(pre->ctr + 1) : nullptr);
+        } else {
+            passes = radix_sort_passes(ctx, k, ka, v, va, n, pl, pre_hist);
+        }
         if (passes_out) *passes_out = passes;
 
         // ---- count inside the buckets ------------------------------------------------------------------------
         const u64 cap = (u64)(sym ? 2 : 1) * ((u64)n / min_count) + 1024;
         DevBuf<u64> ok(ctx, cap);
         DevBuf<u32> oc(ctx, cap);
-        DevBuf<unsigned long long> ctr(ctx, 2);             // [0] rows written, [1] flags (low 32 bits)
-        CUDA_CHECK(cudaMemsetAsync(ctr.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
+        DevBuf<unsigned long long> ctr_own;
+        unsigned long long* ctr = pre ? pre->ctr : nullptr;   // [0] rows written, [1] flags (low 32 bits)
+        if (!ctr) {
+            ctr_own.alloc(ctx, 2);
+            ctr = ctr_own.p;
+            CUDA_CHECK(cudaMemsetAsync(ctr, 0, 2 * sizeof(unsigned long long), ctx->stream));
+        }
         // packed table words need the tag (mixed key relative to the tile's first bucket) to fit 42 bits: always
         // true for keys of <= 42 bits; wider keys qualify when 256 consecutive buckets fit
         const bool packed = (mix.kb <= HR_TAG_BITS || rem_bits + 8 <= HR_TAG_BITS) && !no_packed;
         const unsigned grid = (unsigned)ceil_div64(n, HR_TILE);
-        u32* flags = reinterpret_cast<u32*>(ctr.p + 1);
+        u32* flags = reinterpret_cast<u32*>(ctr + 1);
 #define HR_LAUNCH(SYM_, PACKED_)                                                                                      \
         do {                                                                                                          \
             auto kern = hash_reduce_kernel<SYM_, PACKED_>;                                                            \
-            static bool attr_done = false;                                                                            \
-            if (!attr_done) {                                                                                         \
-                CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hr_smem_bytes(PACKED_))); \
-                CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));          \
-                attr_done = true;                                                                                     \
-            }                                                                                                         \
+            cov_func_smem(ctx, (const void*)kern, hr_smem_bytes(PACKED_));                                            \
             COV_LAUNCH(ctx, OTTOCOV_K_RLE, 8.0 * n, kern, grid, HR_THREADS, hr_smem_bytes(PACKED_), k, n, rem_bits,    \
-                       mix, min_count, (SYM_ && mirror) ? 1 : 0, ok.p, oc.p, ctr.p, cap, flags);                      \
+                       mix, min_count, (SYM_ && mirror) ? 1 : 0, ok.p, oc.p, ctr, cap, flags);                        \
         } while (0)
-        if (plan.big) {
-            const int64_t nb = (int64_t)1 << bb;
-            DevBuf<u32> bounds(ctx, (size_t)nb + 1);
-            COV_LAUNCH(ctx, OTTOCOV_K_MISC, 0, bucket_bounds_kernel, (unsigned)ceil_div64(nb + 1, 256), 256, 0, k, n, rem_bits, nb,
-                       bounds.p);
-            static bool big_attr = false;
-            if (!big_attr) {
-                CUDA_CHECK(cudaFuncSetAttribute(hash_reduce_big_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hr_smem_bytes(true)));
-                CUDA_CHECK(cudaFuncSetAttribute(hash_reduce_big_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hr_smem_bytes(true)));
-                CUDA_CHECK(cudaFuncSetAttribute(hash_reduce_big_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-                CUDA_CHECK(cudaFuncSetAttribute(hash_reduce_big_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-                big_attr = true;
-            }
-            if (sym)
-                COV_LAUNCH(ctx, OTTOCOV_K_RLE, 8.0 * n, hash_reduce_big_kernel<true>, (unsigned)nb, HR_THREADS, hr_smem_bytes(true), k,
-                           bounds.p, rem_bits, plan.sub_bits, mix, min_count, mirror ? 1 : 0, ok.p, oc.p, ctr.p, cap, flags);
-            else
-                COV_LAUNCH(ctx, OTTOCOV_K_RLE, 8.0 * n, hash_reduce_big_kernel<false>, (unsigned)nb, HR_THREADS, hr_smem_bytes(true), k,
-                           bounds.p, rem_bits, plan.sub_bits, mix, min_count, 0, ok.p, oc.p, ctr.p, cap, flags);
-        } else if (sym) {
+        if (sym) {
             if (packed) HR_LAUNCH(true, true); else HR_LAUNCH(true, false);
         } else {
             if (packed) HR_LAUNCH(false, true); else HR_LAUNCH(false, false);
         }
 #undef HR_LAUNCH
         unsigned long long h[2];
-        cov_readback(ctx, h, ctr.p, sizeof(h));
+        cov_readback(ctx, h, ctr, sizeof(h));
         const int64_t rows = (int64_t)h[0];
         BitField full[2] = {{0, mix.ab}, {32, 32 + mix.ab}};
 
+        if (h[1] & (unsigned long long)HR_FLAG_FUSED_OVERFLOW) throw FusedOverflow{};
         if ((h[1] & 0xFFFFFFFFull) != 0 || force_fallback) {
             // ---- fallback: plain keys back, full sort, run-length reduce ---------------------------------------
             ok.release(); oc.release();

@@ -94,6 +94,7 @@ struct ottocov_ctx {
     void* pinned = nullptr;            // 4 KB page-locked landing pad for small device -> host read-backs
     cudaStream_t copy_stream = nullptr;        // host -> device column copies overlapped with the loader (events.cu)
     std::vector<cudaEvent_t> sync_events;      // pool of timing-less events for cross-stream ordering
+    std::unordered_map<const void*, size_t> func_smem;   // kernels opted in to > 48 KB dynamic shared memory on THIS device
     u64 budget_cache = 0;              // pair budget derived from free HBM (expand.cu::auto_budget); 0 = not computed
     void* plan = nullptr;              // ExpandPlan between ottocov_expand_prepare and ottocov_expand_run
     // top-k result
@@ -208,6 +209,8 @@ COV_HD u64 key_mix_inv(const KeyMix& m, u64 h) {     // -> plain key aid << 32 |
     return (x << 32) | y;
 }
 
+constexpr u32 HR_FLAG_FUSED_OVERFLOW = 16u;      // device flag: a region of the fused first pass was too small
+
 // ---- device building blocks (implemented in the .cu files) -------------------------------------
 // radix_sort.cu
 struct BitField { int lo, hi; };   // sort on key bits [lo, hi)
@@ -226,6 +229,13 @@ PassList make_pass_list(const BitField* fields, int n_fields);
 // digit counts of these keys (accumulated by whoever wrote them); saves the histogram read.
 int radix_sort_pairs(ottocov_ctx* ctx, u64*& keys, u64*& alt, u32*& vals, u32*& valt, int64_t n,
                      const BitField* fields, int n_fields, u64* pre_hist = nullptr);
+// seg_cnt (optional, keys only, needs pre_hist): the n input keys sit in n_a * n_b regions inside `keys`: region
+// a * n_b + b starts at key offset seg_off[.] and holds seg_cnt[.] keys (device arrays); logical order: b-major.
+int radix_sort_passes(ottocov_ctx* ctx, u64*& keys, u64*& alt, u32*& vals, u32*& valt, int64_t n, const PassList& pl,
+                      u64* pre_hist = nullptr, const u64* seg_cnt = nullptr, const u64* seg_off = nullptr, int n_a = 1,
+                      int n_b = 1, const u32* abort_flag = nullptr);     // abort_flag: see rs_onesweep_kernel
+// cudaFuncAttributeMaxDynamicSharedMemorySize opt-in, once per (context = device, kernel)
+void cov_func_smem(ottocov_ctx* ctx, const void* func, size_t bytes);
 
 void radix_partition_push(ottocov_ctx* ctx, const u64* keys, int64_t n, int shift, int bits,
                           const u64* ptr_base_host, int n_digits);
@@ -243,6 +253,18 @@ void expand_run_impl(ottocov_ctx* ctx, int n_ranks, u64* buf_a, u64* buf_b, int*
 void push_keys_impl(ottocov_ctx* ctx, const u64* keys, int64_t n, int n_ranks, const u64* dest_ptrs_host);
 ottocov_table* reduce_pairs_impl(ottocov_ctx* ctx, u64* keys, int64_t n, int aid_bits, u32 min_count, int sym,
                                  int strip_dest);
+
+// fused expansion + exchange (expand.cu, exchange.cu)
+void xplan_make_impl(int n_ranks, int aid_bits, int64_t max_local_keys, int64_t total_keys, int64_t stripe_cap,
+                     int64_t mirror_cap, ottocov_xplan* out);
+void expand_scatter_impl(ottocov_ctx* ctx, const ottocov_xplan* plan, int rank, const u64* peer_base_host);
+ottocov_table* reduce_received_impl(ottocov_ctx* ctx, const ottocov_xplan* plan, u64 recv_area, u32 min_count, int sym,
+                                    int64_t* need_cap);
+void mirror_push_impl(ottocov_ctx* ctx, const ottocov_xplan* plan, int rank, const ottocov_table* half, const u64* peer_base_host);
+ottocov_table* mirror_collect_impl(ottocov_ctx* ctx, const ottocov_xplan* plan, int rank, const ottocov_table* half,
+                                   u64 recv_area, int64_t* need_rows);
+constexpr int XCH_MAX_RANKS = 64;
+struct PeerBases { u64 p[XCH_MAX_RANKS]; };       // device addresses of every rank's receive area, passed by value
 
 // reduce.cu
 // sorted keys -> distinct keys + run lengths (vals == nullptr) or summed payload (vals != nullptr),
@@ -276,8 +298,22 @@ void partition_table_impl(ottocov_ctx* ctx, const ottocov_table* t, int n_ranks,
 // [mix.kb - bb, mix.kb); pre_hist (optional) = raw digit counts of exactly those passes (see radix_sort_pairs).
 bool hashed_reduce_supported(int aid_bits);
 int hashed_bucket_bits(int64_t n, int kb);
+// Fused first pass: whoever wrote the keys (expand_scatter_kernel) already distributed them on the lowest digit of
+// the bucket field [kb - bb, kb) (make_pass_list's pass 0) into n_a * n_b slack regions of seg_stride keys inside
+// `keys`; seg_cnt = their fill counters (device), ctr = device [2] (rows written, flags), zeroed before the keys were
+// written: a writer that ran out of room in a region sets HR_FLAG_FUSED_OVERFLOW there and hashed_reduce throws
+// FusedOverflow (the caller re-expands the unfused way).  pre_hist then covers the REMAINING passes only.
+struct FusedOverflow {};
+struct HashPre {
+    int bb;
+    int first_bits;          // width of the digit the writer partitioned on (0 = make_pass_list's pass 0 of the field)
+    const u64* seg_cnt;      // [n_a * n_b] fill counters of the regions (device)
+    const u64* seg_off;      // [n_a * n_b] key offset of each region inside `keys` (device)
+    int n_a, n_b;
+    unsigned long long* ctr;
+};
 ottocov_table* hashed_reduce(ottocov_ctx* ctx, u64* keys, u64* alt, int64_t n, const KeyMix& mix, u32 min_count,
-                             bool sym, bool mirror, int* passes_out, u64* pre_hist = nullptr);
+                             bool sym, bool mirror, int* passes_out, u64* pre_hist = nullptr, const HashPre* pre = nullptr);
 // plain keys (optionally with a destination stamp in bits 56..63) -> mixed keys, in place; also fills ghist
 // (device, [pl.n][RS_RADIX]) with the digit counts of the passes in pl (hashed_reduce's pre_hist)
 void mix_keys_inplace(ottocov_ctx* ctx, u64* keys, int64_t n, const KeyMix& mix, bool strip_dest, const PassList& pl,

@@ -96,13 +96,14 @@ constexpr int RS_WINDOW = OTTOCOV_RS_WINDOW;
 
 // lanes of the warp whose digit equals this lane's: one ballot per digit bit, 4 SASS instructions per bit
 // (test bit -> predicate, VOTE, predicated NOT, AND).  Bits at and above NB are zero in every lane.
+// Not `asm volatile`: the ballots of different rows are independent, and the scheduler may interleave them.
 template <int NB>
 __device__ __forceinline__ u32 match_digit_ballot(u32 d) {
     u32 peers = 0xffffffffu;
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
         u32 m;
-        asm volatile(
+        asm(
             "{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
             "and.b32 t, %1, %2;\n\t"
             "setp.ne.u32 p, t, 0;\n\t"
@@ -116,47 +117,53 @@ __device__ __forceinline__ u32 match_digit_ballot(u32 d) {
 }
 
 // Stable rank of each of the lane's IPT keys inside the warp's 32 x IPT-key segment (rows of 32 keys);
-// bumps the warp's running digit counters.  FULL = every row is valid (all tiles but the last).
-template <int ALGO, int NB, bool FULL, int IPT>
-__device__ __forceinline__ void rank_rows(const u64 (&key)[IPT], int shift, u32 mask, u32 radix, int my_n, int lane,
-                                          u32 lt, u32* my_whist, u32* mm, u32 (&rnk2)[IPT / 2]) {
+// bumps the running digit counters.  FULL = every row is valid (all tiles but the last).
+// The running counter of a digit is a read-modify-write in shared memory, so consecutive rows of one counter
+// array form a serial latency chain (ballots -> leader's load -> store -> shuffle), and with 2 CTAs of 8 warps
+// per SM nothing else hides it (ncu, round 1: 0.57 eligible warps per scheduler).  SPLIT cuts the warp's rows
+// into SPLIT groups of consecutive rows, each with its own counter array ("virtual warps" warp * SPLIT + g):
+// the SPLIT chains are independent and are issued interleaved, phase by phase.
+template <int NB, bool FULL, int IPT, int SPLIT>
+__device__ __forceinline__ void rank_rows(const u64 (&key)[IPT], int shift, u32 mask, int my_n, int lane,
+                                          u32 lt, u32* my_whist, u32 (&rnk2)[IPT / 2]) {
+    constexpr int G = IPT / SPLIT;               // rows per group
+    constexpr int STRIDE = 1 << NB;              // counters per group
+    static_assert(IPT % SPLIT == 0 && G % 2 == 0, "row groups must pair up for the 16-bit rank packing");
 #pragma unroll
-    for (int i = 0; i < IPT; ++i) {
-        const bool valid = FULL || i < my_n;
-        const u32 d = (u32)(key[i] >> shift) & mask;
-        u32 peers;
-        if (ALGO == 0) {
-            peers = __match_any_sync(0xffffffffu, valid ? d : radix);      // `radix` never matches a digit
-        } else if (ALGO == 1) {
-            peers = match_digit_ballot<NB>(d);
+    for (int j = 0; j < G; ++j) {
+        u32 d[SPLIT], peers[SPLIT], old[SPLIT];
+        int leader[SPLIT];
+        bool valid[SPLIT];
+#pragma unroll
+        for (int g = 0; g < SPLIT; ++g) {
+            const int i = g * G + j;
+            valid[g] = FULL || i < my_n;
+            d[g] = (u32)(key[i] >> shift) & mask;
+            peers[g] = match_digit_ballot<NB>(d[g]);
             if (!FULL) {
-                const u32 vm = __ballot_sync(0xffffffffu, valid);
-                peers &= valid ? vm : ~vm;
+                const u32 vm = __ballot_sync(0xffffffffu, valid[g]);
+                peers[g] &= valid[g] ? vm : ~vm;
             }
-        } else {
-            if (valid) atomicOr(&mm[d], 1u << lane);
-            __syncwarp();
-            peers = valid ? mm[d] : (1u << lane);
-            __syncwarp();
-            if (valid && lane == __ffs(peers) - 1) mm[d] = 0;              // ready for the next row
+            leader[g] = __ffs(peers[g]) - 1;
         }
-        const int leader = __ffs(peers) - 1;
-        u32 old = 0;
-        if (lane == leader && valid) {
-            old = my_whist[d];
-            my_whist[d] = old + __popc(peers);
+#pragma unroll
+        for (int g = 0; g < SPLIT; ++g) {
+            old[g] = 0;
+            if (lane == leader[g] && valid[g]) old[g] = my_whist[g * STRIDE + d[g]];
         }
-        old = __shfl_sync(0xffffffffu, old, leader);
-        const u32 r = old + __popc(peers & lt);
-        if (i & 1) rnk2[i >> 1] |= r << 16; else rnk2[i >> 1] = r;
+#pragma unroll
+        for (int g = 0; g < SPLIT; ++g)
+            if (lane == leader[g] && valid[g]) my_whist[g * STRIDE + d[g]] = old[g] + __popc(peers[g]);
+#pragma unroll
+        for (int g = 0; g < SPLIT; ++g) {
+            const int i = g * G + j;
+            const u32 r = __shfl_sync(0xffffffffu, old[g], leader[g]) + __popc(peers[g] & lt);
+            if (i & 1) rnk2[i >> 1] |= r << 16; else rnk2[i >> 1] = r;
+        }
         __syncwarp();
     }
 }
 
-// ALGO selects how lanes holding the same digit find each other (tuning knob OTTOCOV_RS_ALGO, measured in
-// experiments/README.md; 1 is the default):
-//   0  match.any            1  NB ballots (one per digit bit)            2  atomicOr on a per-warp mask table
-// phases A, D and F for one tile; FULL = all 4096 slots valid (every tile but the last): no predicates
 template <bool HAS_VALS, bool FULL, int IPT>
 __device__ __forceinline__ void load_rows(const u64* __restrict__ keys_in, const u32* __restrict__ vals_in, int64_t lbase,
                                           int my_n, u64 (&key)[IPT], u32 (&val)[IPT]) {
@@ -168,15 +175,17 @@ __device__ __forceinline__ void load_rows(const u64* __restrict__ keys_in, const
     }
 }
 
-template <bool HAS_VALS, bool FULL, int IPT>
+template <bool HAS_VALS, bool FULL, int IPT, int SPLIT, int NB>
 __device__ __forceinline__ void stage_rows(const u64 (&key)[IPT], const u32 (&val)[IPT], const u32 (&rnk2)[IPT / 2],
                                            int shift, u32 mask, int my_n, const u32* my_whist, u64* s_keys, u32* s_vals) {
+    constexpr int G = IPT / SPLIT;
+    constexpr int STRIDE = 1 << NB;
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
         if (FULL || i < my_n) {
             const u32 d = (u32)(key[i] >> shift) & mask;
             const u32 r = (i & 1) ? (rnk2[i >> 1] >> 16) : (rnk2[i >> 1] & 0xFFFFu);
-            const u32 pos = my_whist[d] + r;
+            const u32 pos = my_whist[(i / G) * STRIDE + d] + r;
             s_keys[pos] = key[i];
             if (HAS_VALS) s_vals[pos] = val[i];
         }
@@ -205,72 +214,170 @@ __device__ __forceinline__ void write_rows(const u64* s_keys, const u32* s_vals,
     }
 }
 
+// ---- segmented input ------------------------------------------------------------------------------------
+// The first distribution pass of the bucketed hash reduce is fused into the pair expansion (expand.cu): it needs
+// no stability, so the expansion scatters its keys straight into one region per digit, reserving room with one
+// atomic per (tile, digit).  The regions have slack, so the input of the NEXT pass is a list of segments
+// (offset, count) instead of one array.  The logical input is their concatenation in table order.
+// Table (device): n_segs, total tiles, then tile_start[n_segs + 1], in_off[n_segs], cnt[n_segs].
+struct RsSegs {
+    u32 n_segs;
+    u32 total_tiles;
+    u64 total_keys;
+    const u32* tile_start;     // [n_segs + 1] first tile of each segment (tiles never straddle segments)
+    const u64* in_off;         // [n_segs] offset of the segment in keys_in
+    const u64* cnt;            // [n_segs] keys in the segment
+};
+
+// One block.  Segment s = b * n_a + a (b-major: b is the digit the keys were partitioned on, a the writer
+// that filled the region) lives at slot a * n_b + b: key offset off_src[slot], count cnt_src[slot].
+__global__ void __launch_bounds__(256) rs_seg_build_kernel(const u64* __restrict__ cnt_src, const u64* __restrict__ off_src,
+                                                           int n_a, int n_b,
+                                                           u32 tile_keys, RsSegs* hdr, u32* tile_start, u64* in_off, u64* cnt) {
+    __shared__ u64 s_warp[256 / 32 + 1];
+    __shared__ u64 s_carry[2];
+    const int S = n_a * n_b;
+    if (threadIdx.x == 0) { s_carry[0] = 0; s_carry[1] = 0; }
+    __syncthreads();
+    for (int base = 0; base < S; base += 256) {
+        const int s = base + threadIdx.x;
+        u64 c = 0, slot = 0;
+        if (s < S) {
+            const int b = s / n_a, a = s % n_a;
+            slot = (u64)a * n_b + b;
+            c = cnt_src[slot];
+            in_off[s] = off_src[slot];
+            cnt[s] = c;
+        }
+        const u64 t = (c + tile_keys - 1) / tile_keys;
+        u64 tot;
+        const u64 ext = block_exclusive_scan<u64, 256>(t, s_warp, &tot);
+        const u64 c0 = s_carry[0];
+        if (s < S) tile_start[s] = (u32)(c0 + ext);
+        u64 ktot;
+        block_exclusive_scan<u64, 256>(c, s_warp, &ktot);
+        __syncthreads();
+        if (threadIdx.x == 0) { s_carry[0] = c0 + tot; s_carry[1] += ktot; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        tile_start[S] = (u32)s_carry[0];
+        hdr->n_segs = (u32)S;
+        hdr->total_tiles = (u32)s_carry[0];
+        hdr->total_keys = s_carry[1];
+        hdr->tile_start = tile_start;
+        hdr->in_off = in_off;
+        hdr->cnt = cnt;
+    }
+}
+
 #ifndef OTTOCOV_RS_MINB
 #define OTTOCOV_RS_MINB 2          // keys only: 40 keys per thread need the 128-register budget of 2 CTAs/SM
 #endif
 #ifndef OTTOCOV_RS_MINB_PAIRS
 #define OTTOCOV_RS_MINB_PAIRS 4    // (key, value) tiles of 4096: 64 registers, 4 CTAs/SM
 #endif
-template <bool HAS_VALS, int ALGO, int NB>
+#ifndef OTTOCOV_RS_SPLIT
+#define OTTOCOV_RS_SPLIT 2         // independent ranking chains per warp (rank_rows)
+#endif
+constexpr int RS_SPLIT = OTTOCOV_RS_SPLIT;
+
+template <bool HAS_VALS, int NB>
 __global__ void __launch_bounds__(RS_THREADS, HAS_VALS ? OTTOCOV_RS_MINB_PAIRS : OTTOCOV_RS_MINB)
 rs_onesweep_kernel(const u64* __restrict__ keys_in, u64* __restrict__ keys_out,
                    const u32* __restrict__ vals_in, u32* __restrict__ vals_out, int64_t n, int shift,
                    int bits, const u64* __restrict__ digit_base, const u64* __restrict__ ptr_base, u64* status,
-                   u32* ticket, u32 epoch) {
+                   u32* ticket, u32 epoch, const RsSegs* __restrict__ segs, const u32* __restrict__ abort_flag) {
+    // The writer of a segmented input (the fused expansion) ran out of room in a region: the input is incomplete and
+    // the host is about to repeat the step.  Every CTA of every later pass leaves at once (uniform branch), so nothing
+    // is ranked against histograms that do not match the data.
+    if (abort_flag != nullptr && (*abort_flag & HR_FLAG_FUSED_OVERFLOW)) return;
     constexpr int IPT = HAS_VALS ? RS_IPT_PAIRS : RS_IPT_KEYS;
     constexpr int RS_TILE = RS_THREADS * IPT;
+    constexpr int SPLIT = RS_SPLIT;
+    constexpr int STRIDE = 1 << NB;
+    constexpr int VW = RS_WARPS * SPLIT;                                      // virtual warps = counter arrays
     extern __shared__ __align__(16) unsigned char s_raw[];
     u64* s_keys = reinterpret_cast<u64*>(s_raw);                              // [RS_TILE]
-    u32* s_whist = reinterpret_cast<u32*>(s_keys + RS_TILE);                  // [RS_WARPS][RS_RADIX]
-    u32* s_dstart = s_whist + RS_WARPS * RS_RADIX;                            // [RS_RADIX]
+    u32* s_whist = reinterpret_cast<u32*>(s_keys + RS_TILE);                  // [VW][STRIDE]
+    u32* s_dstart = s_whist + VW * STRIDE;                                    // [RS_RADIX]
     u64* s_gptr = reinterpret_cast<u64*>(s_dstart + RS_RADIX);                // [RS_RADIX]
     u32* s_scan = reinterpret_cast<u32*>(s_gptr + RS_RADIX);                  // [RS_WARPS + 1] (+pad to 48)
-    u32* s_tile = s_scan + 48;                                                // [1] (+pad to 16)
-    u32* s_match = s_tile + 16;                                               // [RS_WARPS][RS_RADIX] if ALGO == 2
-    u32* s_vals = s_match + (ALGO == 2 ? RS_WARPS * RS_RADIX : 0);            // [RS_TILE] if HAS_VALS
+    u32* s_tile = s_scan + 48;                                                // [8]: tile, tile_n, input offset (u64)
+    u32* s_vals = s_tile + 16;                                                // [RS_TILE] if HAS_VALS
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 radix = 1u << bits, mask = radix - 1u;
 
-    if (tid == 0) *s_tile = atomicAdd(ticket, 1u);
-    for (int j = tid; j < RS_WARPS * RS_RADIX; j += RS_THREADS) {
-        s_whist[j] = 0;
-        if (ALGO == 2) s_match[j] = 0;
+    if (warp == 0) {
+        u32 t = 0;
+        if (lane == 0) t = atomicAdd(ticket, 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        u64 in_base = (u64)t * RS_TILE;
+        int64_t left = n - (int64_t)in_base;
+        if (segs) {
+            if (t >= segs->total_tiles) left = 0;
+            else {
+                // last segment whose first tile is <= t (empty segments share their successor's first tile)
+                const u32* ts = segs->tile_start;
+                u32 lo = 0, hi = segs->n_segs;
+                while (hi - lo > 1) {
+                    const u32 step = (hi - lo + 31) / 32;
+                    const u32 idx = lo + lane * step;
+                    const u32 v = idx < hi ? ts[idx] : 0xFFFFFFFFu;
+                    const u32 m = __ballot_sync(0xffffffffu, v <= t);
+                    const u32 j = 31 - __clz(m);
+                    lo += j * step;
+                    hi = min(hi, lo + step);
+                }
+                const u64 within = (u64)(t - ts[lo]) * RS_TILE;
+                in_base = segs->in_off[lo] + within;
+                left = (int64_t)(segs->cnt[lo] - within);
+            }
+        }
+        if (lane == 0) {
+            s_tile[0] = t;
+            s_tile[1] = (u32)(left <= 0 ? 0 : (left < RS_TILE ? left : RS_TILE));
+            *reinterpret_cast<u64*>(s_tile + 2) = in_base;
+        }
     }
+    for (int j = tid; j < VW * STRIDE; j += RS_THREADS) s_whist[j] = 0;
     __syncthreads();
-    const int64_t tile = *s_tile;
-    const int64_t tile_base = tile * RS_TILE;
-    const int tile_n = (int)min((int64_t)RS_TILE, n - tile_base);
+    const int64_t tile = s_tile[0];
+    const int tile_n = (int)s_tile[1];
+    if (tile_n == 0) return;                                 // a ticket beyond the last tile (segmented launches are
+    const u64 in_base = *reinterpret_cast<u64*>(s_tile + 2); // sized by an upper bound): never published, never awaited
     const bool full = tile_n == RS_TILE;
 
     // -- A: load (warp-striped: every access is a coalesced 256 B row) ------------------------------
     u64 key[IPT];
     u32 val[IPT];
-    const int64_t lbase = tile_base + (int64_t)warp * 32 * IPT + lane;
-    const int my_n = (int)min((int64_t)IPT, (n - lbase + 31) / 32);        // valid items of this lane (may be <= 0)
+    const int lw = warp * 32 * IPT + lane;                                  // first slot of this lane in the tile
+    const int64_t lbase = (int64_t)in_base + lw;
+    int my_n = (tile_n - lw + 31) / 32;                                     // valid items of this lane (may be <= 0)
+    if (my_n > IPT) my_n = IPT;
     if (full) load_rows<HAS_VALS, true>(keys_in, vals_in, lbase, my_n, key, val);
     else load_rows<HAS_VALS, false>(keys_in, vals_in, lbase, my_n, key, val);
 
-    // -- B: stable rank of every key inside its warp's 512-key segment; the per-warp digit counts fall
+    // -- B: stable rank of every key inside its (virtual) warp's segment; the per-warp digit counts fall
     //       out of the same pass.  Lanes holding the same digit are found with one ballot per digit
     //       bit (match.any is far slower than `bits` ballots on this part); the lowest such lane
-    //       bumps the warp's running counter for the digit, no atomics needed.
-    u32* my_whist = s_whist + warp * RS_RADIX;
+    //       bumps the running counter for the digit, no atomics needed.
+    u32* my_whist = s_whist + warp * SPLIT * STRIDE;
     const u32 lt = lanemask_lt();
     u32 rnk2[IPT / 2];                       // two 16-bit ranks per register
-    u32* mm = (ALGO == 2) ? s_match + warp * RS_RADIX : nullptr;
-    if (full) rank_rows<ALGO, NB, true>(key, shift, mask, radix, my_n, lane, lt, my_whist, mm, rnk2);
-    else rank_rows<ALGO, NB, false>(key, shift, mask, radix, my_n, lane, lt, my_whist, mm, rnk2);
+    if (full) rank_rows<NB, true, IPT, SPLIT>(key, shift, mask, my_n, lane, lt, my_whist, rnk2);
+    else rank_rows<NB, false, IPT, SPLIT>(key, shift, mask, my_n, lane, lt, my_whist, rnk2);
     __syncthreads();
 
-    // -- C: offsets over warps, tile totals, digit starts; publish the aggregate ----------------------
+    // -- C: offsets over (virtual) warps, tile totals, digit starts; publish the aggregate --------------
     u32 total = 0;
     if (tid < (int)radix) {
         u32 run = 0;
 #pragma unroll
-        for (int w = 0; w < RS_WARPS; ++w) {
-            const u32 c = s_whist[w * RS_RADIX + tid];
-            s_whist[w * RS_RADIX + tid] = run;
+        for (int w = 0; w < VW; ++w) {
+            const u32 c = s_whist[w * STRIDE + tid];
+            s_whist[w * STRIDE + tid] = run;
             run += c;
         }
         total = run;
@@ -283,7 +390,7 @@ rs_onesweep_kernel(const u64* __restrict__ keys_in, u64* __restrict__ keys_out,
         st_volatile_u64(mine, (tile == 0 ? ST_FLAG_PREFIX : ST_FLAG_AGG) | tag | (u64)total);
         s_dstart[tid] = dstart;
 #pragma unroll
-        for (int w = 0; w < RS_WARPS; ++w) s_whist[w * RS_RADIX + tid] += dstart;   // absolute slots
+        for (int w = 0; w < VW; ++w) s_whist[w * STRIDE + tid] += dstart;   // absolute slots
     }
     __syncthreads();
 
@@ -322,8 +429,8 @@ rs_onesweep_kernel(const u64* __restrict__ keys_in, u64* __restrict__ keys_out,
     }
 
     // -- D: scatter into the digit-ordered staging buffer ---------------------------------------------------
-    if (full) stage_rows<HAS_VALS, true>(key, val, rnk2, shift, mask, my_n, my_whist, s_keys, s_vals);
-    else stage_rows<HAS_VALS, false>(key, val, rnk2, shift, mask, my_n, my_whist, s_keys, s_vals);
+    if (full) stage_rows<HAS_VALS, true, IPT, SPLIT, NB>(key, val, rnk2, shift, mask, my_n, my_whist, s_keys, s_vals);
+    else stage_rows<HAS_VALS, false, IPT, SPLIT, NB>(key, val, rnk2, shift, mask, my_n, my_whist, s_keys, s_vals);
     __syncthreads();
 
     // -- F: coalesced per-digit runs out --------------------------------------------------------------------
@@ -331,12 +438,21 @@ rs_onesweep_kernel(const u64* __restrict__ keys_in, u64* __restrict__ keys_out,
     else write_rows<HAS_VALS, false, IPT>(s_keys, s_vals, s_gptr, shift, mask, tid, tile_n, keys_out, vals_out);
 }
 
-static size_t rs_smem_bytes(bool has_vals, int algo) {
-    size_t b = (size_t)rs_tile(has_vals) * 8 + (size_t)RS_WARPS * RS_RADIX * 4 + RS_RADIX * 4 + RS_RADIX * 8 +
-               48 * 4 + 16 * 4;
-    if (algo == 2) b += (size_t)RS_WARPS * RS_RADIX * 4;
+static size_t rs_smem_bytes(bool has_vals, int nb) {
+    size_t b = (size_t)rs_tile(has_vals) * 8 + (size_t)RS_WARPS * RS_SPLIT * ((size_t)1 << nb) * 4 + RS_RADIX * 4 +
+               RS_RADIX * 8 + 48 * 4 + 16 * 4;
     if (has_vals) b += (size_t)rs_tile(true) * 4;
     return b;
+}
+
+// Opt-in to more than 48 KB of dynamic shared memory.  Function attributes belong to the CURRENT DEVICE, so the
+// opt-in is tracked per context (one context per device), never in a process-wide static.
+void cov_func_smem(ottocov_ctx* ctx, const void* func, size_t bytes) {
+    auto it = ctx->func_smem.find(func);
+    if (it != ctx->func_smem.end() && it->second >= bytes) return;
+    CUDA_CHECK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    CUDA_CHECK(cudaFuncSetAttribute(func, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    ctx->func_smem[func] = bytes;
 }
 
 static void ensure_sweep_state(ottocov_ctx* ctx, size_t words) {
@@ -385,18 +501,52 @@ PassList make_pass_list(const BitField* fields, int n_fields) {
     return pl;
 }
 
+// one distribution pass: grid = n_tiles CTAs (an upper bound when the input is segmented)
+static void launch_pass(ottocov_ctx* ctx, int family, bool has_vals, const u64* keys, u64* out, const u32* vals, u32* vout,
+                        int64_t n, int64_t n_tiles, int shift, int bits, const u64* digit_base, const u64* ptr_base,
+                        u32* ticket, const RsSegs* segs, const u32* abort_flag = nullptr) {
+    const u32 epoch = next_epoch(ctx);
+    const double pass_bytes = (has_vals ? 24.0 : 16.0) * (double)n;
+#define RS_LAUNCH(HV, NBITS)                                                                                          \
+    do {                                                                                                              \
+        auto kern = rs_onesweep_kernel<HV, NBITS>;                                                                    \
+        const size_t smem = rs_smem_bytes(HV, NBITS);                                                                 \
+        cov_func_smem(ctx, (const void*)kern, smem);                                                                  \
+        COV_LAUNCH(ctx, family, pass_bytes, kern, (unsigned)n_tiles, RS_THREADS, smem, keys, out, vals, vout, n, shift, \
+                   bits, digit_base, ptr_base, ctx->sweep_status, ticket, epoch, segs, abort_flag);                   \
+    } while (0)
+#define RS_DISPATCH(HV)                                                                                               \
+    if (bits <= 4) RS_LAUNCH(HV, 4);                                                                                  \
+    else if (bits <= 6) RS_LAUNCH(HV, 6);                                                                             \
+    else if (bits == 7) RS_LAUNCH(HV, 7);                                                                             \
+    else RS_LAUNCH(HV, 8)
+    if (has_vals) { RS_DISPATCH(true); } else { RS_DISPATCH(false); }
+#undef RS_DISPATCH
+#undef RS_LAUNCH
+}
+
 // pre_hist (optional): device array [passes][RS_RADIX] of raw digit counts of exactly these keys and fields
 // (make_pass_list order), e.g. accumulated by the kernel that wrote the keys; it is scanned in place and
 // the histogram read of the keys is skipped.
+// seg_cnt / seg_off (optional, keys only): the input is not one array but n_a * n_b regions inside `keys`
+// (rs_seg_build_kernel's layout) holding seg_cnt[slot] keys from key offset seg_off[slot] (device arrays), n keys in
+// total; the first pass reads them as segments and writes `alt` contiguously.  `keys` must hold at least n keys for
+// the later passes.
 int radix_sort_pairs(ottocov_ctx* ctx, u64*& keys, u64*& alt, u32*& vals, u32*& valt, int64_t n,
                      const BitField* fields, int n_fields, u64* pre_hist) {
-    const PassList pl = make_pass_list(fields, n_fields);
-    if (n <= 1 || pl.n == 0) return 0;
+    return radix_sort_passes(ctx, keys, alt, vals, valt, n, make_pass_list(fields, n_fields), pre_hist);
+}
+
+int radix_sort_passes(ottocov_ctx* ctx, u64*& keys, u64*& alt, u32*& vals, u32*& valt, int64_t n, const PassList& pl,
+                      u64* pre_hist, const u64* seg_cnt, const u64* seg_off, int n_a, int n_b, const u32* abort_flag) {
+    if (n <= 0 || pl.n == 0 || (n == 1 && !seg_cnt)) return 0;
     const bool has_vals = vals != nullptr;
+    if (seg_cnt && has_vals) COV_THROW(OTTOCOV_ERR_ARG, "segmented radix input is keys-only");
 
     DevBuf<u64> ghist;
     u64* gh = pre_hist;
     if (!gh) {
+        if (seg_cnt) COV_THROW(OTTOCOV_ERR_ARG, "segmented radix input needs the pass histograms");
         ghist.alloc(ctx, (size_t)pl.n * RS_RADIX);
         gh = ghist.p;
         CUDA_CHECK(cudaMemsetAsync(gh, 0, (size_t)pl.n * RS_RADIX * sizeof(u64), ctx->stream));
@@ -406,44 +556,28 @@ int radix_sort_pairs(ottocov_ctx* ctx, u64*& keys, u64*& alt, u32*& vals, u32*& 
     }
     COV_LAUNCH(ctx, OTTOCOV_K_MISC, 0, rs_scan_hist_kernel, pl.n, RS_RADIX, 0, gh);
 
-    const int64_t n_tiles = ceil_div64(n, rs_tile(has_vals));
-    ensure_sweep_state(ctx, (size_t)n_tiles * RS_RADIX);
+    const int64_t tile = rs_tile(has_vals);
+    const int n_segs = seg_cnt ? n_a * n_b : 0;
+    const int64_t n_tiles = ceil_div64(n, tile);
+    const int64_t n_tiles_first = seg_cnt ? n / tile + n_segs : n_tiles;       // upper bound: one partial tile per segment
+    ensure_sweep_state(ctx, (size_t)(n_tiles_first > n_tiles ? n_tiles_first : n_tiles) * RS_RADIX);
     CUDA_CHECK(cudaMemsetAsync(ctx->sweep_ticket, 0, RS_MAX_PASSES * sizeof(u32), ctx->stream));
 
-    static int algo = -1;
-    if (algo < 0) {
-        const char* e = getenv("OTTOCOV_RS_ALGO");            // tuning knob, default = ballots
-        algo = e ? atoi(e) : 1;
-        if (algo < 0 || algo > 2) algo = 1;
+    DevBuf<unsigned char> segbuf;
+    const RsSegs* segs = nullptr;
+    if (seg_cnt) {
+        const size_t o_ts = 64, o_in = o_ts + (((size_t)n_segs + 1) * 4 + 7) / 8 * 8, o_cn = o_in + (size_t)n_segs * 8;
+        segbuf.alloc(ctx, o_cn + (size_t)n_segs * 8);
+        COV_LAUNCH(ctx, OTTOCOV_K_MISC, 0, rs_seg_build_kernel, 1, 256, 0, seg_cnt, seg_off, n_a, n_b, (u32)tile,
+                   reinterpret_cast<RsSegs*>(segbuf.p), reinterpret_cast<u32*>(segbuf.p + o_ts),
+                   reinterpret_cast<u64*>(segbuf.p + o_in), reinterpret_cast<u64*>(segbuf.p + o_cn));
+        segs = reinterpret_cast<const RsSegs*>(segbuf.p);
     }
-    const size_t smem = rs_smem_bytes(has_vals, algo);
-    const double pass_bytes = (has_vals ? 24.0 : 16.0) * (double)n;
     for (int p = 0; p < pl.n; ++p) {
-        const u32 epoch = next_epoch(ctx);
-        const int bits = pl.bits[p];
-#define RS_LAUNCH(HV, AL, NBITS)                                                                            \
-        do {                                                                                                \
-            auto kern = rs_onesweep_kernel<HV, AL, NBITS>;                                                  \
-            static bool attr_done = false;                                                                  \
-            if (!attr_done) {                                                                               \
-                CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(HV, 2))); \
-                CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); \
-                attr_done = true;                                                                           \
-            }                                                                                               \
-            COV_LAUNCH(ctx, OTTOCOV_K_SORT_PASS, pass_bytes, kern, (unsigned)n_tiles, RS_THREADS, smem, keys, alt, \
-                       (const u32*)vals, valt, n, pl.shift[p], bits, gh + (size_t)p * RS_RADIX,        \
-                       (const u64*)nullptr, ctx->sweep_status, ctx->sweep_ticket + p, epoch);                                    \
-        } while (0)
-#define RS_DISPATCH(HV)                                                                                     \
-        if (algo == 0) RS_LAUNCH(HV, 0, 8);                                                                 \
-        else if (algo == 2) RS_LAUNCH(HV, 2, 8);                                                            \
-        else if (bits <= 4) RS_LAUNCH(HV, 1, 4);                                                            \
-        else if (bits <= 6) RS_LAUNCH(HV, 1, 6);                                                            \
-        else if (bits == 7) RS_LAUNCH(HV, 1, 7);                                                            \
-        else RS_LAUNCH(HV, 1, 8)
-        if (has_vals) { RS_DISPATCH(true); } else { RS_DISPATCH(false); }
-#undef RS_DISPATCH
-#undef RS_LAUNCH
+        const bool first_seg = (p == 0 && segs);
+        launch_pass(ctx, OTTOCOV_K_SORT_PASS, has_vals, keys, alt, vals, valt, n, first_seg ? n_tiles_first : n_tiles,
+                    pl.shift[p], pl.bits[p], gh + (size_t)p * RS_RADIX, nullptr, ctx->sweep_ticket + p, first_seg ? segs : nullptr,
+                    abort_flag);
         u64* tk = keys; keys = alt; alt = tk;
         if (has_vals) { u32* tv = vals; vals = valt; valt = tv; }
     }
@@ -460,22 +594,11 @@ void radix_partition_push(ottocov_ctx* ctx, const u64* keys, int64_t n, int shif
     DevBuf<u64> pb(ctx, RS_RADIX);
     u64 h[RS_RADIX];
     for (int d = 0; d < RS_RADIX; ++d) h[d] = d < n_digits ? ptr_base_host[d] : 0;
+    // `h` is pageable: the runtime stages it before cudaMemcpyAsync returns, so the stack frame may go away
     CUDA_CHECK(cudaMemcpyAsync(pb.p, h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
     const int64_t n_tiles = ceil_div64(n, rs_tile(false));
     ensure_sweep_state(ctx, (size_t)n_tiles * RS_RADIX);
     CUDA_CHECK(cudaMemsetAsync(ctx->sweep_ticket, 0, RS_MAX_PASSES * sizeof(u32), ctx->stream));
-    const u32 epoch = next_epoch(ctx);
-    auto kern = (bits <= 4) ? rs_onesweep_kernel<false, 1, 4> : rs_onesweep_kernel<false, 1, 8>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<false, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(false, 2)));
-        CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<false, 1, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<false, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(false, 2)));
-        CUDA_CHECK(cudaFuncSetAttribute(rs_onesweep_kernel<false, 1, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        attr_done = true;
-    }
-    COV_LAUNCH(ctx, OTTOCOV_K_PARTITION, 16.0 * n, kern, (unsigned)n_tiles, RS_THREADS, rs_smem_bytes(false, 1), keys,
-               (u64*)nullptr, (const u32*)nullptr, (u32*)nullptr, n, shift, bits, (const u64*)nullptr, (const u64*)pb.p,
-               ctx->sweep_status, ctx->sweep_ticket, epoch);
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));      // `h` lives on this stack frame
+    launch_pass(ctx, OTTOCOV_K_PARTITION, false, keys, nullptr, nullptr, nullptr, n, n_tiles, shift, bits, nullptr, pb.p,
+                ctx->sweep_ticket, nullptr);
 }

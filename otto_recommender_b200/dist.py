@@ -1,9 +1,17 @@
 """Multi-GPU co-event counting: sessions sharded across ranks, counts re-sharded by hash(aid).
 
-The reference is single-process; this is the one place the path gains a
-collective.  Sessions are independent (pairs never cross a session; parts never split one,
-etl/jsonl_to_parquet.py:35-40) and counts are an associative integer sum keyed by (aid, aid_next),
-so:
+The reference is single-process; this is the one place the path gains an
+exchange.  Sessions are independent (pairs never cross a session; parts never split one,
+etl/jsonl_to_parquet.py:35-40) and counts are an associative integer sum keyed by (aid, aid_next).
+
+Default path (round 2), `count_exchange_scatter`: the first distribution pass of the bucketed hash reduce
+runs inside the pair expansion, and its digit is (owner rank of the key, low hash-bucket bits), so the
+expansion kernel stores every key straight into a stripe of its OWNER's HBM (torch symmetric memory =
+CUDA IPC mappings over NVLink).  A step is: barrier - expansion/scatter + publish - barrier - remaining
+passes + hash reduce on what arrived [- mirrored rows pushed the same way - barrier - one sort].  No key
+touches local HBM before it crosses, no NCCL data collective, no per-destination counts on the host.
+
+Earlier paths, kept as baselines (`bench.py --exchange nccl|push`):
 
     rank r:  load its session shard -> expand -> local reduce-by-key        (no communication)
              stable partition of the local table by dest = hash(aid) % R    (ottocov_table_partition)
@@ -216,6 +224,144 @@ def count_exchange_push(engine, name: str, min_count: int = 1, group=None, aid_b
     for t in (half, mirrored, theirs):
         t.free()
     return full
+
+
+class ScatterExchange:
+    """State of the fused expansion + exchange for one (engine, process group): the agreed plan per co-event kind
+    and the receive area in symmetric memory.  Collective decisions are taken from values every rank reads
+    identically (the status words each source publishes to ALL ranks), so the ranks never diverge and a step needs
+    no NCCL call; the only collective outside the first step of a kind is re-allocating a larger receive area."""
+
+    def __init__(self, engine, group=None):
+        self.engine, self.group = engine, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.dev = torch.device("cuda", engine.device)
+        self.plans = {}              # name -> (plan, total_keys it was made for)
+        self.capacity = 0
+        self.regrows = 0
+
+    def _ensure(self, nbytes: int):
+        if nbytes <= self.capacity:
+            return
+        import torch.distributed._symmetric_memory as symm_mem
+        self.capacity = int(nbytes * 1.1) + (1 << 20)           # the same arithmetic on every rank
+        self.buf = symm_mem.empty(self.capacity, dtype=torch.uint8, device=self.dev)
+        gname = self.group.group_name if self.group is not None else dist.group.WORLD.group_name
+        self.handle = symm_mem.rendezvous(self.buf, gname)
+        self.peer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
+
+    def _agree(self, n_keys: int):
+        """max and sum of the ranks' key counts (first step of a kind only: one small collective + host read-back)"""
+        mine = torch.tensor([n_keys], dtype=torch.int64, device=self.dev)
+        allc = torch.empty(self.world, dtype=torch.int64, device=self.dev)
+        dist.all_gather_into_tensor(allc, mine, group=self.group)
+        v = allc.cpu()
+        return int(v.max()), int(v.sum())
+
+    def count(self, name: str, min_count: int, aid_bits: int):
+        eng = self.engine
+        n_keys, sym = eng.expand_prepare(name, min_count=min_count)
+        entry = self.plans.get(name)
+        if entry is None:
+            mx, tot = self._agree(n_keys)
+            entry = (eng.make_xplan(self.world, aid_bits, mx, tot), tot)
+        plan, tot = entry
+        while True:
+            self._ensure(plan.total_bytes)
+            self.handle.barrier(channel=0)                    # nobody still works in its receive area
+            eng.expand_scatter(plan, self.rank, self.peer_ptrs)
+            self.handle.barrier(channel=1)                    # every key and every status word has landed
+            half, need = eng.reduce_received(plan, self.peer_ptrs[self.rank], min_count, sym)
+            if half is not None:
+                break
+            # some stripe overflowed; `need` is the same on every rank: grow and repeat the step
+            self.regrows += 1
+            plan = eng.make_xplan(self.world, aid_bits, 0, tot, stripe_cap=int(need * 1.1) + 4096, mirror_cap=plan.mirror_cap)
+            n_keys, sym = eng.expand_prepare(name, min_count=min_count)
+        if sym:
+            while True:
+                eng.mirror_push(plan, self.rank, half, self.peer_ptrs)
+                self.handle.barrier(channel=2)
+                full, need = eng.mirror_collect(plan, self.rank, half, self.peer_ptrs[self.rank])
+                if full is not None:
+                    break
+                self.regrows += 1
+                plan = eng.make_xplan(self.world, aid_bits, 0, tot, stripe_cap=plan.stripe_cap, mirror_cap=int(need * 1.25) + 4096)
+                self._ensure(plan.total_bytes)
+                self.handle.barrier(channel=0)                # the layout moved: nobody may still read the old stripes
+            half.free()
+            half = full
+        self.plans[name] = (plan, tot)
+        return half
+
+
+def count_exchange_scatter(engine, name: str, min_count: int = 1, group=None, aid_bits: Optional[int] = None):
+    """This rank's shard (all rows whose aid hashes to it) of the global thresholded table of one co-event kind:
+    expansion fused with the first bucket pass AND the exchange (see the module docstring)."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return engine.count(name, min_count=min_count)
+    if aid_bits is None:
+        aid_bits = global_aid_bits(engine, group)
+    cache = engine.__dict__.setdefault("_scatter_exchanges", {})   # lives and dies with the engine
+    ex = cache.get(id(group))
+    if ex is None:
+        ex = cache[id(group)] = ScatterExchange(engine, group)
+    return ex.count(name, min_count, aid_bits)
+
+
+def count_scatter_emulated(engine, shards, name: str, min_count: int, aid_bits: int, stripe_cap: int = 0,
+                           mirror_cap: int = 0):
+    """The same flow with R "ranks" played one after the other by ONE engine on one GPU (tests, smoke): every
+    rank's receive area is a local buffer, so the peer stores of the expansion land in ordinary HBM.  `shards`
+    = list of (session, aid, ts, type) column tuples, one per rank.  Returns (tables per rank, regrows)."""
+    R = len(shards)
+    dev = torch.device("cuda", engine.device)
+    counts = []
+    for cols in shards:
+        engine.load_events(*cols)
+        counts.append(engine.expand_prepare(name, min_count=min_count)[0])
+    plan = engine.make_xplan(R, aid_bits, max(counts), sum(counts), stripe_cap=stripe_cap, mirror_cap=mirror_cap)
+    regrows = 0
+    while True:
+        bufs = [torch.zeros(plan.total_bytes, dtype=torch.uint8, device=dev) for _ in range(R)]
+        bases = [b.data_ptr() for b in bufs]
+        sym = False
+        for r, cols in enumerate(shards):
+            engine.load_events(*cols)
+            _, sym = engine.expand_prepare(name, min_count=min_count)
+            engine.expand_scatter(plan, r, bases)
+        halves, need = [], 0
+        for r in range(R):
+            h, nd = engine.reduce_received(plan, bases[r], min_count, sym)
+            halves.append(h)
+            need = max(need, nd)
+        if need == 0:
+            break
+        assert all(h is None for h in halves), "every rank must see the overflow"
+        regrows += 1
+        plan = engine.make_xplan(R, aid_bits, 0, sum(counts), stripe_cap=int(need * 1.1) + 4096, mirror_cap=plan.mirror_cap)
+    if not sym:
+        return halves, regrows
+    while True:
+        for r in range(R):
+            engine.mirror_push(plan, r, halves[r], bases)
+        fulls, need = [], 0
+        for r in range(R):
+            f, nd = engine.mirror_collect(plan, r, halves[r], bases[r])
+            fulls.append(f)
+            need = max(need, nd)
+        if need == 0:
+            break
+        assert all(f is None for f in fulls)
+        regrows += 1
+        # a new layout: the key stripes are no longer needed, only the mirror stripes move
+        plan = engine.make_xplan(R, aid_bits, 0, sum(counts), stripe_cap=plan.stripe_cap, mirror_cap=int(need * 1.25) + 4096)
+        bufs = [torch.zeros(plan.total_bytes, dtype=torch.uint8, device=dev) for _ in range(R)]
+        bases = [b.data_ptr() for b in bufs]
+    for h in halves:
+        h.free()
+    return fulls, regrows
 
 
 def gather_table(table, group=None, dst: int = 0):

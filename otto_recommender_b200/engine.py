@@ -21,12 +21,29 @@ def _is_torch(x) -> bool:
 
 
 def _as_col(x, np_dtype, torch_dtype_name):
-    """-> (pointer, where, keepalive)"""
+    """-> (pointer, where, keepalive).  A column wider than its target type is range-checked before it is narrowed:
+    the C side only ever sees int32 / int8 values, so raw OTTO millisecond timestamps (~1.66e12) or 64-bit session
+    ids would otherwise wrap silently.  `ts` must be in SECONDS, as etl/jsonl_to_parquet.py:28 writes it."""
+    info = np.iinfo(np_dtype)
     if _is_torch(x):
         import torch
-        t = x.to(getattr(torch, torch_dtype_name)).contiguous()
+        dt = getattr(torch, torch_dtype_name)
+        if x.dtype != dt and x.numel() and not (np_dtype == np.uint64 and x.dtype == torch.int64):
+            if x.dtype.is_floating_point or x.dtype == torch.bool:
+                raise ValueError(f"column of dtype {x.dtype} where {torch_dtype_name} is expected")
+            lo, hi = int(x.min()), int(x.max())
+            if lo < info.min or hi > info.max:
+                raise ValueError(f"column values [{lo}, {hi}] do not fit {torch_dtype_name} (timestamps must be seconds)")
+        t = x.to(dt).contiguous()
         return t.data_ptr(), (_lib.DEVICE if t.is_cuda else _lib.HOST), t
-    a = np.ascontiguousarray(x, dtype=np_dtype)
+    a = np.asarray(x)
+    if a.dtype != np_dtype and a.size:
+        if a.dtype.kind not in "iu":
+            raise ValueError(f"column of dtype {a.dtype} where {np.dtype(np_dtype).name} is expected")
+        lo, hi = int(a.min()), int(a.max())
+        if lo < info.min or hi > info.max:
+            raise ValueError(f"column values [{lo}, {hi}] do not fit {np.dtype(np_dtype).name} (timestamps must be seconds)")
+    a = np.ascontiguousarray(a, dtype=np_dtype)
     return a.ctypes.data, _lib.HOST, a
 
 
@@ -239,7 +256,11 @@ class Engine:
         flags = 0 if symmetric is None else (2 if symmetric else 1)
         if hashed is not None:
             flags |= 8 if hashed else 4
-        return _lib.Spec(th, mask, w, budget, max(int(min_count), 0), flags)
+        # the +-24 h pre-filter of self_merge (config.MIN/MAX_TIME_TO_NEXT, count_co_events.py:33-36)
+        dt_min, dt_max = int(self.config.MIN_TIME_TO_NEXT), int(self.config.MAX_TIME_TO_NEXT)
+        if (dt_min, dt_max) != (-86400, 86400):
+            flags |= 16
+        return _lib.Spec(th, mask, w, budget, max(int(min_count), 0), flags, dt_min, dt_max)
 
     # ---- exchange-before-reduce building blocks (multi-GPU) ---------------------------------------------
     def expand_prepare(self, name: Optional[str] = None, *, type_this=None, next_types=None, window=None,
@@ -281,6 +302,48 @@ class Engine:
                                                    max(int(min_count), 0), int(symmetric), mode,
                                                    ctypes.byref(h)))
         return Table(self, h.value)
+
+    # ---- fused expansion + exchange (default multi-GPU path) ------------------------------------------------
+    def make_xplan(self, n_ranks: int, aid_bits: int, max_local_keys: int, total_keys: int, stripe_cap: int = 0,
+                   mirror_cap: int = 0) -> "_lib.XPlan":
+        """Stripe capacities + layout of a rank's receive area; pure arithmetic, identical on every rank."""
+        plan = _lib.XPlan()
+        rc = self._lib.ottocov_xplan_make(int(n_ranks), int(aid_bits), int(max_local_keys), int(total_keys), int(stripe_cap),
+                                          int(mirror_cap), ctypes.byref(plan))
+        if rc != 0:
+            msg = self._lib.ottocov_last_error(None)
+            raise OttocovError(rc, msg.decode() if msg else "ottocov_xplan_make failed")
+        return plan
+
+    def expand_scatter(self, plan, rank: int, peer_bases: Sequence[int]):
+        """After expand_prepare: expand this rank's keys straight into their owners' stripes (peer_bases[r] = device
+        address of rank r's receive area) and publish counts / histograms / status to every rank.  Enqueue only."""
+        arr = (ctypes.c_uint64 * len(peer_bases))(*[int(p) for p in peer_bases])
+        self._sync_stream()
+        self._check(self._lib.ottocov_expand_scatter(self._ctx, ctypes.byref(plan), int(rank), arr))
+
+    def reduce_received(self, plan, recv_area: int, min_count: int = 1, symmetric: bool = False):
+        """Remaining passes + hash reduce over the stripes this rank received.  -> (Table | None, need_cap): need_cap > 0
+        means some rank overflowed a stripe (every rank reads the same value): grow the plan and repeat the step."""
+        h, need = ctypes.c_void_p(), ctypes.c_int64()
+        self._sync_stream()
+        self._check(self._lib.ottocov_reduce_received(self._ctx, ctypes.byref(plan), int(recv_area), max(int(min_count), 0),
+                                                      int(symmetric), ctypes.byref(h), ctypes.byref(need)))
+        return (Table(self, h.value) if h.value else None), int(need.value)
+
+    def mirror_push(self, plan, rank: int, half: Table, peer_bases: Sequence[int]):
+        """Transposed off-diagonal rows of a half table -> the stripes of their owner ranks.  Enqueue only."""
+        arr = (ctypes.c_uint64 * len(peer_bases))(*[int(p) for p in peer_bases])
+        self._sync_stream()
+        self._check(self._lib.ottocov_mirror_push(self._ctx, ctypes.byref(plan), int(rank), half._h, arr))
+
+    def mirror_collect(self, plan, rank: int, half: Table, recv_area: int):
+        """-> (full Table | None, need_rows): own half rows + the transposed rows received, sorted by key."""
+        h, need = ctypes.c_void_p(), ctypes.c_int64()
+        self._sync_stream()
+        self._check(self._lib.ottocov_mirror_collect(self._ctx, ctypes.byref(plan), int(rank), half._h, int(recv_area),
+                                                     ctypes.byref(h), ctypes.byref(need)))
+        return (Table(self, h.value) if h.value else None), int(need.value)
 
     def mirror(self, table: Table, transpose_only: bool = False) -> Table:
         """Half table (rows aid <= aid_next) -> full symmetric table (or only the transposed rows)."""

@@ -357,6 +357,64 @@ def test_exchange_first_emulated_ranks(engine, name, mc):
         assert got == want, (name, mc, R)
 
 
+def _session_shards(s, a, t, y, R):
+    """contiguous session ranges balanced by the pair-work proxy, as bench.py / dist.py shard them"""
+    from otto_recommender_b200.dist import shard_bounds
+    order = np.lexsort((t, s))
+    s, a, t, y = s[order], a[order], t[order], y[order]
+    us, lens = np.unique(s, return_counts=True)
+    b = shard_bounds(lens, R)
+    cuts = np.concatenate([[0], np.cumsum(lens)])[b]
+    return [tuple(x[cuts[r]:cuts[r + 1]] for x in (s, a, t, y)) for r in range(R)]
+
+
+@pytest.mark.parametrize("R", [2, 3, 8])
+def test_scatter_exchange_emulated_vs_oracle(engine, R):
+    """The default multi-GPU flow (expansion fused with the first bucket pass and the exchange: every key is stored
+    straight into a stripe of its owner's receive area; mirrored rows of symmetric kinds pushed the same way) with
+    the R ranks played by one engine.  All five kinds against the plain-C oracle run on the WHOLE event set: every
+    row on its owner rank, the union equal to the oracle's thresholded table."""
+    from otto_recommender_b200.dist import count_scatter_emulated
+    for seed, kw in ((55, dict(n_sessions=900, n_aids=300, max_len=50)), (56, dict(n_sessions=2500, n_aids=40, max_len=30))):
+        s, a, t, y = small_events(seed, **kw)
+        info = engine.load_events(s, a, t, y)
+        shards = _session_shards(s, a, t, y, R)
+        for name in NAMES:
+            oa, ob, oc, emitted, _ = c_oracle.count_name(s, a, t, y, name)
+            for mc in (1, 3):
+                ka, kb, kc = c_oracle.merge_tables([(oa, ob, oc)], min_count=mc)
+                tabs, regrows = count_scatter_emulated(engine, shards, name, mc, info["aid_bits"])
+                got = {}
+                for r, tab in enumerate(tabs):
+                    ga, gb, gc = tab.fetch()
+                    assert np.all(hash_dest(ga, R) == r), "row on the wrong rank"
+                    assert np.all(np.diff(ga.astype(np.int64) << 32 | gb) > 0)            # sorted, distinct
+                    for k, v in zip(zip(ga.tolist(), gb.tolist()), gc.tolist()):
+                        assert k not in got
+                        got[k] = v
+                    tab.free()
+                assert got == _dict(ka, kb, kc), (name, mc, R, seed)
+
+
+def test_scatter_exchange_regrows_consistently(engine):
+    """Stripes far too small: every rank reads the same published need, the plan grows, the step repeats; the mirror
+    stripes likewise.  Same table as the oracle."""
+    from otto_recommender_b200.dist import count_scatter_emulated
+    s, a, t, y = small_events(57, n_sessions=1500, n_aids=200, max_len=40)
+    info = engine.load_events(s, a, t, y)
+    R = 4
+    shards = _session_shards(s, a, t, y, R)
+    for name in ("click_to_click", "click_to_cart_or_buy"):
+        oa, ob, oc, _, _ = c_oracle.count_name(s, a, t, y, name)
+        ka, kb, kc = c_oracle.merge_tables([(oa, ob, oc)], min_count=2)
+        tabs, regrows = count_scatter_emulated(engine, shards, name, 2, info["aid_bits"], stripe_cap=64, mirror_cap=8)
+        assert regrows >= (2 if name == "click_to_click" else 1)
+        got = {}
+        for tab in tabs:
+            got.update(tab.to_dict())
+        assert got == _dict(ka, kb, kc), name
+
+
 def test_push_keys_emulated_peers(engine):
     """ottocov_push_keys with every 'peer' receive buffer living at an offset of one local tensor: the
     result must be exactly the grouped output of the two-buffer expand_run."""
@@ -471,7 +529,7 @@ def test_hash_reduce_hot_pairs(engine):
         p_sort = engine.count_info()["sort_passes"]
         got = engine.count("click_to_click", min_count=3, hashed=True)
         fell_back = engine.count_info()["sort_passes"] > p_sort
-        assert fell_back == expect_fallback
+        assert fell_back == expect_fallback, engine.count_info()
         assert got.to_dict() == want.to_dict()
         d = got.to_dict()
         assert d[(5, 9)] == d[(9, 5)] and d[(5, 9)] >= (n // 2) ** 2
@@ -503,23 +561,81 @@ def test_reduce_pairs_hashed(engine, mc):
             assert tabs[True] == tabs[False] == tabs[None], (name, R, mc)
 
 
-def test_hash_reduce_big_bucket_mode():
-    """The big-bucket variant (one CTA per ~12 K-key bucket, four rounds over the same shared-memory table) is
-    chosen automatically only at sizes where it saves a distribution pass (hundreds of millions of keys).
-    OTTOCOV_HR_MODE=2 prefers it whenever it is possible; the library reads the knob once per process, so the
-    hash-reduce, threshold, symmetric and exchange tests are re-run in a child process with it set."""
+def _fused_cases(engine, seed=13, n_sessions=40_000):
+    """All five kinds on an OTTO-shaped slice big enough for >= 2 bucket passes of click_to_click and
+    click_to_cart_or_buy (the first pass then runs inside the expansion), against the plain-C oracle."""
+    d = generate_numpy(SynthSpec(n_sessions=n_sessions, seed=seed))
+    s, a, t, y = d["session"], d["aid"], d["ts"], d["type"]
+    engine.load_events(s, a, t, y)
+    fused_seen = 0
+    for name in NAMES:
+        oa, ob, oc, emitted, _ = c_oracle.count_name(s, a, t, y, name)
+        for mc in (1, 2, 3):
+            ka, kb, kc = c_oracle.merge_tables([(oa, ob, oc)], min_count=mc)
+            for sym in (None, False):
+                for budget in (None, max(emitted // 7, 5000)):          # digit-range chunks when the budget is small
+                    got = engine.count(name, min_count=mc, symmetric=sym, hashed=True, pair_budget=budget)
+                    ci = engine.count_info()
+                    assert ci["n_pairs"] == emitted
+                    fused_seen += ci["fused"]
+                    if ci["fused"] and budget is not None:
+                        assert ci["n_chunks"] >= 3, ci
+                    ga, gb, gc = got.fetch()
+                    assert np.array_equal(ga, ka) and np.array_equal(gb, kb) and np.array_equal(gc, kc), (name, mc, sym, budget)
+                    got.free()
+    return fused_seen
+
+
+def test_fused_first_pass_vs_oracle(engine):
+    assert _fused_cases(engine) >= 12          # click_to_click and click_to_cart_or_buy take the fused path
+
+
+def test_fused_first_pass_overflow_and_unfused_children():
+    """(1) OTTOCOV_FUSE_SLACK_PCT=-60: every digit region is too small, the expansion raises the overflow flag and the
+    chunk is re-run with regions sized by the fill counters; (2) OTTOCOV_NO_FUSED_PASS=1: the unfused bucket passes.
+    Both knobs are read once per process, so the cases run in child processes; same tables as the oracle."""
     import subprocess
     import sys
-    if os.environ.get("OTTOCOV_HR_MODE"):
+    if os.environ.get("OTTOCOV_FUSE_SLACK_PCT") or os.environ.get("OTTOCOV_NO_FUSED_PASS"):
         pytest.skip("already inside the child run")
-    env = dict(os.environ, OTTOCOV_HR_MODE="2")
-    here = os.path.dirname(os.path.abspath(__file__))
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_parity.py"), "-q", "-x", "-m", "gpu",
-                        "-p", "no:cacheprovider", "-k",
-                        "hash_reduce_vs_oracle or hash_reduce_many or hash_reduce_hot or fused_threshold or symmetric_shortcut "
-                        "or exchange_first or reduce_pairs_hashed or arbitrary_specs"],
-                       env=env, capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    for extra in ({"OTTOCOV_FUSE_SLACK_PCT": "-60"}, {"OTTOCOV_NO_FUSED_PASS": "1"}):
+        env = dict(os.environ, **extra)
+        r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
+                            "-k", "fused_child or hash_reduce_hot or hash_reduce_many"],
+                           env=env, capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, str(extra) + r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_fused_child(engine):
+    if os.environ.get("OTTOCOV_FUSE_SLACK_PCT"):
+        assert _fused_cases(engine, seed=14, n_sessions=30_000) >= 12
+    elif os.environ.get("OTTOCOV_NO_FUSED_PASS"):
+        assert _fused_cases(engine, seed=14, n_sessions=30_000) == 0
+    else:
+        pytest.skip("runs inside test_fused_first_pass_overflow_and_unfused_children")
+
+
+def test_asymmetric_time_range(engine):
+    """config.MIN_TIME_TO_NEXT / MAX_TIME_TO_NEXT other than the reference's +-24 h (count_co_events.py:33-36 filters
+    MIN <= ts_next - ts <= MAX before the per-kind |dt| <= W): e.g. MIN = 0 means "the next event cannot precede this
+    one".  Counts are no longer symmetric; the general window kernel serves these configs."""
+    from otto_recommender_b200 import Engine
+    from otto_recommender_b200.config import CoEventConfig
+    s, a, t, y = small_events(61, n_sessions=500, n_aids=40, max_len=40)
+    for lo, hi in ((0, 86400), (1, 86400), (-86400, -1), (-3600, 7200), (100, 50), (-86400, 86400)):
+        eng = Engine(0, config=CoEventConfig(MIN_TIME_TO_NEXT=lo, MAX_TIME_TO_NEXT=hi))
+        try:
+            eng.load_events(s, a, t, y)
+            for name, (th, mask, w) in c_oracle.NAMES.items():
+                oa, ob, oc, emitted, _ = c_oracle.count(s, a, t, y, th, mask, w, dt_min=lo, dt_max=hi)
+                ga, gb, gc = eng.count(name).fetch()
+                assert eng.count_info()["n_pairs"] == emitted, (name, lo, hi)
+                assert np.array_equal(ga, oa) and np.array_equal(gb, ob) and np.array_equal(gc.astype(np.uint32), oc), (name, lo, hi)
+                ka, kb, kc = c_oracle.merge_tables([(oa, ob, oc)], min_count=2)
+                ha, hb, hc = eng.count(name, min_count=2, hashed=True).fetch()
+                assert np.array_equal(ha, ka) and np.array_equal(hb, kb) and np.array_equal(hc, kc), (name, lo, hi)
+        finally:
+            eng.close()
 
 
 def test_pipelined_host_load(engine):

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol(built_lib):
         assert hasattr(lib, name), f"{name} declared in ottocov.h but not exported"
     # the ctypes table binds exactly the declared functions
     assert declared == set(_lib.SYMBOLS)
-    assert _lib.load_library().ottocov_version() == 100
+    assert _lib.load_library().ottocov_version() == 200
 
 
 def test_no_cpu_fallback(built_lib):
@@ -145,3 +145,23 @@ def test_key_mix_is_a_bijection():
     counts = np.bincount(top, minlength=256)
     assert counts.max() < 2.0 * len(keys) / 256 and counts.min() > 0.4 * len(keys) / 256
     assert lib.ottocov_key_mix(29, 0, 0) == 2 ** 64 - 1      # out of range is loud
+
+
+def test_columns_wider_than_the_abi_are_range_checked():
+    """The C ABI takes int32 / int8 columns; wider inputs are narrowed only after a range check (raw OTTO
+    millisecond timestamps or 64-bit session ids must not wrap silently)."""
+    from otto_recommender_b200.engine import _as_col
+    ok = np.array([1_660_000_000, 1_660_000_100], dtype=np.int64)
+    p, where, keep = _as_col(ok, np.int32, "int32")
+    assert keep.dtype == np.int32 and keep.tolist() == ok.tolist()
+    with pytest.raises(ValueError):
+        _as_col(ok * 1000, np.int32, "int32")                      # milliseconds
+    with pytest.raises(ValueError):
+        _as_col(np.array([0, 3, 200], dtype=np.int64), np.int8, "int8")
+    with pytest.raises(ValueError):
+        _as_col(np.array([0.5, 1.0]), np.int32, "int32")
+    import torch
+    with pytest.raises(ValueError):
+        _as_col(torch.tensor([1_660_000_000_000], dtype=torch.int64), np.int32, "int32")
+    _, _, t = _as_col(torch.tensor([5, 6], dtype=torch.int64), np.int32, "int32")
+    assert t.dtype == torch.int32

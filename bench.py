@@ -336,7 +336,8 @@ def run_ours(args):
     torch.cuda.empty_cache()
 
     eng = Engine(device=local_rank)
-    exchange = covdist.count_exchange_first if args.exchange == "nccl" else covdist.count_exchange_push
+    exchange = {"nccl": covdist.count_exchange_first, "push": covdist.count_exchange_push,
+                "scatter": covdist.count_exchange_scatter}[args.exchange]
     state = {"tables": []}
 
     def count_all(budget=None):
@@ -416,9 +417,18 @@ def run_ours(args):
     # ---- e2e: host (pinned) columns in, results back on the host, through the public API ------------
     host_cols = [c.cpu().pin_memory() for c in cols]
 
+    host_parts = Engine.split_at_sessions(*host_cols, 12) if world == 1 else None
+
     def step_e2e():
-        eng.load_events(*host_cols)                       # H2D inside
-        count_all(args.pair_budget)
+        if world == 1 and not args.no_streamed_e2e:
+            # the public ingest call: the population as parts in host memory (what reading the ETL's parquet parts
+            # gives), copied on a second stream and counted group by group behind the copies
+            for t in state["tables"]:
+                t.free()
+            state["tables"] = eng.count_parts(host_parts, names, [MIN_COUNT_TO_SAVE[n] for n in names])
+        else:
+            eng.load_events(*host_cols)                   # H2D inside
+            count_all(args.pair_budget)
         d2h = 0
         for f in state["tables"]:
             ax, nv, ay, ac = eng.topk(f, TOP_K, pinned=True)   # D2H inside
@@ -492,8 +502,10 @@ def run_ours(args):
             "sort_passes": first["sort_passes"], "fused_first_pass": bool(first.get("fused", 0)), "chunks": first["n_chunks"],
             "peak_bytes_rank0": mem["peak_bytes"],
             "parallelism": (f"session-sharded x{world}, keys re-sharded by hash(aid): " +
-                            ("expansion scatters into the owners' HBM over NVLink (peer stores)" if args.exchange == "push"
-                             else "NCCL all-to-all"))
+                            {"scatter": "the expansion stores every key straight into its owner's HBM over NVLink (fused first "
+                                        "bucket pass + exchange, peer stores)",
+                             "push": "round-1 path: keys written locally, then one partition pass with peer stores",
+                             "nccl": "NCCL all-to-all"}[args.exchange])
             if world > 1 else "single GPU",
             "l2": "inputs (event columns, pair keys) are far larger than the 126 MB L2; no flush needed",
         },
@@ -597,9 +609,12 @@ def main():
     ap.add_argument("--ref-parts", type=int, default=4, help="--impl reference: fixed parts per step")
     ap.add_argument("--ref-part-sessions", type=int, default=50_000, help="--impl reference: sessions per part")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--exchange", default="push", choices=["push", "nccl"],
-                    help="N > 1: the expansion stores keys straight into their owners' HBM over NVLink (push) or NCCL all-to-all (nccl)")
+    ap.add_argument("--exchange", default="scatter", choices=["scatter", "push", "nccl"],
+                    help="N > 1: scatter = the expansion stores keys straight into their owners' HBM over NVLink (default); "
+                         "push = round-1 path (local keys + one partition pass with peer stores); nccl = NCCL all-to-all")
     ap.add_argument("--no-clock-sampler", action="store_true", help="do not sample clocks during the timed region")
+    ap.add_argument("--no-streamed-e2e", action="store_true",
+                    help="N = 1 e2e through load_events + count instead of the streamed count_parts")
     ap.add_argument("--clusters", type=int, default=50, help="--workload popularity: pseudo-clusters")
     ap.add_argument("--cpu-sample-events", type=int, default=10_000_000, help="--workload popularity: events of the CPU sample")
     args = ap.parse_args()

@@ -141,6 +141,22 @@ int ottocov_get_events_info(ottocov_ctx* ctx, ottocov_events_info* out);
 int ottocov_count(ottocov_ctx* ctx, const ottocov_spec* spec, ottocov_table** out);
 int ottocov_get_count_info(ottocov_ctx* ctx, ottocov_count_info* out);
 
+/* ---- streamed ingest + count: replaces the whole per-file loop of count_co_events_all_files
+ * (model/count_co_events.py:83-100: read part, unique(), self-merge, count) PLUS the merge of the part tables
+ * (concat_files_w_stats, :112-168) for one population, with the host -> device copy of the parts overlapped with the
+ * counting.  Input = the parquet parts as the ETL wrote them (etl/jsonl_to_parquet.py:23-29, 59-84: columns
+ * session i32, aid i32, ts i32 seconds, type i8; a session never spans two parts, :35-40), one host buffer per
+ * column per part -- nothing is concatenated on the host.  One contiguous host array cut at session boundaries is
+ * the special case.  Parts are copied on a second stream (all aid columns first: the key width must be known before
+ * the first key is made) and processed in groups as they land: loader (any row order inside a part), window ranges,
+ * expansion fused with the first bucket pass; the remaining passes, the hash reduce with the fused threshold and
+ * the symmetric mirror run once over all groups.  tables_out[k] is the table of specs[k] (same result as
+ * ottocov_load_events of the concatenation + ottocov_count).  Afterwards no events are loaded (ottocov_count
+ * needs a new ottocov_load_events); ottocov_get_events_info reports the totals over all parts. */
+int ottocov_count_parts(ottocov_ctx* ctx, int n_parts, const int32_t* const* session, const int32_t* const* aid,
+                        const int32_t* const* ts, const int8_t* const* type, const int64_t* rows,
+                        const ottocov_spec* specs, int n_specs, ottocov_table** tables_out);
+
 /* ---- tables: the (aid, aid_next, count) frames the reference writes per part and re-reads in
  * concat_files_w_stats (model/count_co_events.py:97-100, :112-115). */
 int ottocov_table_from_arrays(ottocov_ctx* ctx, const int32_t* aid, const int32_t* aid_next,
@@ -180,6 +196,20 @@ int ottocov_topk_fetch(ottocov_ctx* ctx, int32_t* aid_x, int32_t* n_valid, int32
  * df_aids[['aid']].unique().join(df_count[['aid','aid_next']], on='aid')  (model/retrieve.py:75-91). */
 int ottocov_topk_lookup(ottocov_ctx* ctx, const int32_t* aids, int64_t n, int where, int32_t* n_valid,
                         int32_t* aid_y /*[n*k]*/, int32_t* cnt /*[n*k]*/);
+
+/* ---- derived co-count features: replaces get_df_count_for_co_event_type
+ * (model/retrieve.py:18-63) on a count table given in FILE order (count descending, as count_co_events.py:173-179
+ * wrote it): per-aid top-first_n by (count desc, aid_next asc) with, for every kept row,
+ *   count_pop = int16(min((count - min) / (q - min), 1) * 10000), q = the 0.9999 quantile of count (:33-35); the caller
+ *               passes quantile_row = the row of the ASCENDING count order that its quantile rule selects
+ *               (numpy 'nearest': round((n - 1) * 0.9999)), the device sorts the column and reads it
+ *   perc_pop  = int16(row_nr / n * 10000), row_nr from 1 in file order (:36-38)
+ *   rank      = 1-based ordinal rank inside the aid (:41-44),  count_rel = int8(count / max count of the aid * 100) (:45-49)
+ * Rows come back ordered by (aid, rank).  IEEE double arithmetic, bit-identical to the host restatement. */
+int ottocov_count_features(ottocov_ctx* ctx, const int32_t* aid, const int32_t* aid_next, const int32_t* count, int64_t n,
+                           int where, int first_n, int64_t quantile_row, int64_t* n_rows);
+int ottocov_count_features_fetch(ottocov_ctx* ctx, int32_t* aid, int32_t* aid_next, int32_t* count, int16_t* count_pop,
+                                 int16_t* perc_pop, int16_t* rank, int8_t* count_rel, int64_t cap_rows, int where);
 
 /* ---- popularity of aids inside session clusters: replaces, for ONE clustering, the body of
  * model/count_popularity.py:56-85 -- groupby([cluster, aid]) with six counts (clicks, carts, orders; all time and

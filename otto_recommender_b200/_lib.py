@@ -63,6 +63,8 @@ SYMBOLS = {
     "ottocov_kernel_stats": (c_int, [c_void_p, POINTER(KernelStat), c_int]),
     "ottocov_kernel_family_name": (c_char_p, [c_int]),
     "ottocov_load_events": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int]),
+    "ottocov_count_parts": (c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
+                                    POINTER(c_int64), POINTER(Spec), c_int, POINTER(c_void_p)]),
     "ottocov_get_events_info": (c_int, [c_void_p, POINTER(EventsInfo)]),
     "ottocov_count": (c_int, [c_void_p, POINTER(Spec), POINTER(c_void_p)]),
     "ottocov_expand_prepare": (c_int, [c_void_p, POINTER(Spec), POINTER(c_int64), POINTER(c_int)]),
@@ -94,6 +96,9 @@ SYMBOLS = {
     "ottocov_sort_u64": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int]),
     "ottocov_key_mix": (c_uint64, [c_int, c_uint32, c_uint32]),
     "ottocov_key_unmix": (c_uint64, [c_int, c_uint64]),
+    "ottocov_count_features": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int64, POINTER(c_int64)]),
+    "ottocov_count_features_fetch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                             c_int64, c_int]),
     "ottocov_count_popularity": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int32, c_int,
                                          POINTER(c_int64)]),
     "ottocov_popularity_fetch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int]),

@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 SO = os.path.join(HERE, os.environ.get("OTTOCOV_SO_NAME", "libottocov.so"))      # tuning builds: other name + -D flags
 EXTRA_DEFS = os.environ.get("OTTOCOV_NVCC_DEFS", "").split()
-SOURCES = ["api.cu", "radix_sort.cu", "events.cu", "expand.cu", "reduce.cu", "hash_reduce.cu", "topk.cu", "popularity.cu", "exchange.cu"]
+SOURCES = ["api.cu", "radix_sort.cu", "events.cu", "expand.cu", "reduce.cu", "hash_reduce.cu", "topk.cu", "popularity.cu", "exchange.cu", "features.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xptxas", "-v",

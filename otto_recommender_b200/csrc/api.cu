@@ -204,6 +204,7 @@ int ottocov_destroy(ottocov_ctx* ctx) {
     free_events(ctx);
     free_topk(ctx);
     free_popularity(ctx);
+    free_features(ctx);
     free_plan(ctx);
     if (ctx->sweep_status) cudaFreeAsync(ctx->sweep_status, ctx->stream);
     if (ctx->scan_status) cudaFreeAsync(ctx->scan_status, ctx->stream);
@@ -278,14 +279,33 @@ int ottocov_load_events(ottocov_ctx* ctx, const int32_t* session, const int32_t*
     if (n < 0) COV_THROW(OTTOCOV_ERR_ARG, "n < 0");
     if (n > 0 && (!session || !aid || !ts || !type)) COV_THROW(OTTOCOV_ERR_ARG, "NULL column");
     if (where != OTTOCOV_HOST && where != OTTOCOV_DEVICE) COV_THROW(OTTOCOV_ERR_ARG, "bad `where`");
+    ctx->info_only = false;
     load_events_impl(ctx, session, aid, ts, type, n, where);
+    API_END(ctx)
+}
+
+int ottocov_count_parts(ottocov_ctx* ctx, int n_parts, const int32_t* const* session, const int32_t* const* aid,
+                        const int32_t* const* ts, const int8_t* const* type, const int64_t* rows,
+                        const ottocov_spec* specs, int n_specs, ottocov_table** tables_out) {
+    API_BEGIN(ctx)
+    if (n_parts < 0 || n_specs < 1 || !specs || !tables_out) COV_THROW(OTTOCOV_ERR_ARG, "bad argument");
+    if (n_parts > 0 && (!session || !aid || !ts || !type || !rows)) COV_THROW(OTTOCOV_ERR_ARG, "NULL part table");
+    ctx->info_only = false;
+    try {
+        count_parts_impl(ctx, n_parts, session, aid, ts, type, rows, specs, n_specs, tables_out);
+    } catch (...) {
+        for (int k = 0; k < n_specs; ++k)
+            if (tables_out[k]) { dev_free(ctx, tables_out[k]->keys); dev_free(ctx, tables_out[k]->count); delete tables_out[k]; tables_out[k] = nullptr; }
+        free_events(ctx);
+        throw;
+    }
     API_END(ctx)
 }
 
 int ottocov_get_events_info(ottocov_ctx* ctx, ottocov_events_info* out) {
     API_BEGIN(ctx)
     if (!out) COV_THROW(OTTOCOV_ERR_ARG, "NULL out");
-    if (!ctx->loaded) COV_THROW(OTTOCOV_ERR_STATE, "no events loaded");
+    if (!ctx->loaded && !ctx->info_only) COV_THROW(OTTOCOV_ERR_STATE, "no events loaded");
     *out = ctx->info;
     API_END(ctx)
 }
@@ -497,6 +517,23 @@ int ottocov_topk_lookup(ottocov_ctx* ctx, const int32_t* aids, int64_t n, int wh
     API_BEGIN(ctx)
     if (n < 0 || (n > 0 && (!aids || !n_valid || !aid_y || !cnt))) COV_THROW(OTTOCOV_ERR_ARG, "bad argument");
     topk_lookup_impl(ctx, aids, n, where, n_valid, aid_y, cnt);
+    API_END(ctx)
+}
+
+int ottocov_count_features(ottocov_ctx* ctx, const int32_t* aid, const int32_t* aid_next, const int32_t* count, int64_t n,
+                           int where, int first_n, int64_t quantile_row, int64_t* n_rows) {
+    API_BEGIN(ctx)
+    if (n < 0 || (n > 0 && (!aid || !aid_next || !count))) COV_THROW(OTTOCOV_ERR_ARG, "bad argument");
+    if (where != OTTOCOV_HOST && where != OTTOCOV_DEVICE) COV_THROW(OTTOCOV_ERR_ARG, "bad `where`");
+    count_features_impl(ctx, aid, aid_next, count, n, where, first_n, quantile_row);
+    if (n_rows) *n_rows = ctx->feat_n;
+    API_END(ctx)
+}
+
+int ottocov_count_features_fetch(ottocov_ctx* ctx, int32_t* aid, int32_t* aid_next, int32_t* count, int16_t* count_pop,
+                                 int16_t* perc_pop, int16_t* rank, int8_t* count_rel, int64_t cap_rows, int where) {
+    API_BEGIN(ctx)
+    count_features_fetch_impl(ctx, aid, aid_next, count, count_pop, perc_pop, rank, count_rel, cap_rows, where);
     API_END(ctx)
 }
 

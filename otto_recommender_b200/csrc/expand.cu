@@ -23,6 +23,12 @@
 #include "internal.cuh"
 #include "scan.cuh"
 
+#ifndef OTTOCOV_EXS_ABLATE
+#define OTTOCOV_EXS_ABLATE 0      // timing experiments on expand_scatter_kernel (results are WRONG when non-zero):
+#endif                            // 1 no pass histograms, 2 no global stores, 3 no shared-memory ranking atomics
+#ifndef OTTOCOV_EXS_MINB
+#define OTTOCOV_EXS_MINB 6        // 40 registers without spills; measured 5.84 (4 CTAs/SM) -> 5.40 (5) -> 5.27 ms (6) on 742 M keys
+#endif
 constexpr int EX_THREADS = 256;
 constexpr int EX_TILE = 2048;
 constexpr int EX_PER = EX_TILE / EX_THREADS;          // consecutive outputs per thread
@@ -355,7 +361,7 @@ struct ScatterArgs {
 };
 
 template <bool SELF, bool CANON, bool DIST>
-__global__ void __launch_bounds__(EX_THREADS, 4)
+__global__ void __launch_bounds__(EX_THREADS, OTTOCOV_EXS_MINB)
 expand_scatter_kernel(const u32* __restrict__ rec_src, const u32* __restrict__ rec_lo,
                       const u64* __restrict__ rec_off, const u32* __restrict__ tile_rec,
                       const u32* __restrict__ aid_src, const u32* __restrict__ aid_tgt, u64 out_begin,
@@ -365,6 +371,7 @@ expand_scatter_kernel(const u32* __restrict__ rec_src, const u32* __restrict__ r
     __shared__ u32 s_cnt[RS_RADIX];                   // keys of the tile per digit, then their first staging slot
     __shared__ u64 s_gptr[RS_RADIX];                  // byte address of the digit's run - 8 * first staging slot; 0 = dropped
     __shared__ u32 s_scan[EX_THREADS / 32 + 1];
+    __shared__ unsigned char s_dig[DIST ? EX_TILE : 4];   // DIST: digit of every staged key (the owner is not part of the mixed key)
     extern __shared__ u32 s_hist[];                   // [n_dest][pl.n][RS_RADIX]
     u32* s_off = s_buf;
     u32* s_lo = s_buf + EX_PITCH;
@@ -407,13 +414,17 @@ expand_scatter_kernel(const u32* __restrict__ rec_src, const u32* __restrict__ r
                     const u32 d = (dest << sa.sub_bits) | ((u32)(key[q] >> sa.sh1) & sub_mask);
                     if (d >= sa.d_lo && d < sa.d_hi) {
                         keep |= 1u << q;
+#if OTTOCOV_EXS_ABLATE == 3
+                        const u32 r = (k0 + q) & 15u; if (q == 0) atomicAdd(&s_cnt[d], 8u);
+#else
                         const u32 r = atomicAdd(&s_cnt[d], 1u);
+#endif
                         dig[q >> 2] |= d << (8 * (q & 3));
                         rnk[q >> 1] |= r << (16 * (q & 1));
                     }
                 }
             }
-            for (int p = 0; p < pl.n; ++p) {              // histograms of the remaining passes, kept keys only
+            for (int p = 0; p < (OTTOCOV_EXS_ABLATE == 1 ? 0 : pl.n); ++p) {   // histograms of the remaining passes, kept keys only
                 const int sh = pl.shift[p];
                 const u32 msk = (1u << pl.bits[p]) - 1u;
 #pragma unroll
@@ -425,20 +436,17 @@ expand_scatter_kernel(const u32* __restrict__ rec_src, const u32* __restrict__ r
             }
         }
         __syncthreads();                                  // ranks are final; the staged records are no longer needed
-        // per digit: first staging slot, and room in the digit's region
+        // per digit: first staging slot, and room in the digit's region.  The reservation is a global fetch-and-add
+        // (~1 us round trip): it is issued here and its result is first used after the keys have been staged, so the
+        // round trip hides behind the barrier and the shared-memory scatter.
         u32 c = 0;
         if (tid < (int)sa.n_digits) c = s_cnt[tid];
         u32 kept_total;
         const u32 dstart = block_exclusive_scan<u32, EX_THREADS>(c, s_scan, &kept_total);
+        unsigned long long g = 0;
         if (tid < (int)sa.n_digits) {
             s_cnt[tid] = dstart;
-            u64 gp = 0;
-            if (c) {
-                const unsigned long long g = atomicAdd(&sa.cursor[tid], (unsigned long long)c);
-                if (g + c <= sa.reg_cap[tid]) gp = sa.reg_base[tid] + (g - (u64)dstart) * 8ull;
-                else atomicOr(sa.flags, HR_FLAG_FUSED_OVERFLOW);
-            }
-            s_gptr[tid] = gp;
+            if (c) g = atomicAdd(&sa.cursor[tid], (unsigned long long)c);
         }
         __syncthreads();
         if (keep) {
@@ -448,29 +456,28 @@ expand_scatter_kernel(const u32* __restrict__ rec_src, const u32* __restrict__ r
                     const u32 d = (dig[q >> 2] >> (8 * (q & 3))) & 0xFFu;
                     const u32 r = (rnk[q >> 1] >> (16 * (q & 1))) & 0xFFFFu;
                     s_out[s_cnt[d] + r] = key[q];
+                    if (DIST) s_dig[s_cnt[d] + r] = (unsigned char)d;
                 }
         }
+        if (tid < (int)sa.n_digits) {
+            u64 gp = 0;
+            if (c) {
+                if (g + c <= sa.reg_cap[tid]) gp = sa.reg_base[tid] + (g - (u64)dstart) * 8ull;
+                else atomicOr(sa.flags, HR_FLAG_FUSED_OVERFLOW);
+            }
+            s_gptr[tid] = gp;
+        }
         __syncthreads();
-        // digit-ordered runs out: slot j belongs to the digit whose [first slot, next first slot) holds j; the digit
-        // is recomputed from the key itself (dest is not part of the mixed key: look it up by slot when n_dest > 1)
+        // digit-ordered runs out: the digit of slot j is recomputed from the key itself (single GPU) or read back from
+        // the byte staged next to it (the owner rank is not part of the mixed key)
 #pragma unroll
         for (int it = 0; it < EX_TILE / EX_THREADS; ++it) {
             const u32 j = (u32)it * EX_THREADS + tid;
             if (j < kept_total) {
                 const u64 k = s_out[j];
-                u32 d;
-                if (DIST) {                               // last digit whose first slot is <= j
-                    u32 lo = 0, hi = sa.n_digits;
-                    while (hi - lo > 1) {
-                        const u32 mid = (lo + hi) >> 1;
-                        if (s_cnt[mid] <= j) lo = mid; else hi = mid;
-                    }
-                    d = lo;
-                } else {
-                    d = (u32)(k >> sa.sh1) & sub_mask;
-                }
+                const u32 d = DIST ? (u32)s_dig[j] : ((u32)(k >> sa.sh1) & sub_mask);
                 const u64 gp = s_gptr[d];
-                if (gp) __stcs(reinterpret_cast<u64*>(gp + 8ull * j), k);
+                if (gp && OTTOCOV_EXS_ABLATE != 2) __stcs(reinterpret_cast<u64*>(gp + 8ull * j), k);
             }
         }
         __syncthreads();                                  // s_buf is re-staged by the next tile
@@ -913,6 +920,267 @@ ottocov_table* count_impl(ottocov_ctx* ctx, const ottocov_spec* spec) {
     cov_trace(ctx, "count: mirror/merge");
     ci.n_unique = result->n;
     return result;
+}
+
+// ---- streamed ingest + count (include/ottocov.h, ottocov_count_parts) ----------------------------------------------
+__global__ void __launch_bounds__(256) aid_max_kernel(const int32_t* __restrict__ aid, int64_t n, int* __restrict__ out) {
+    int mx = -2147483647 - 1, mn = 2147483647;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int a = aid[i];
+        mx = max(mx, a); mn = min(mn, a);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMax(&out[0], mx); atomicMin(&out[1], mn); }
+}
+
+__global__ void init_minmax_kernel(int* out) { out[0] = -2147483647 - 1; out[1] = 2147483647; }
+
+// per-kind state carried over the groups
+struct PartsAccum {
+    ottocov_spec spec;
+    bool sym = false;
+    bool started = false;
+    u32 user_min = 1;
+    int bb = 0;
+    PassList full, rest;
+    u32 n_digits = 0;
+    u64 P_total = 0, n_pairs = 0;
+    std::vector<u64*> bufs;                    // one region buffer per group (cov_alloc)
+    std::vector<u64> cap;                      // region capacity of each group
+    DevBuf<unsigned long long> cursor;         // [groups][RS_RADIX] fill counters
+    DevBuf<u64> reg;                           // [groups][2][RS_RADIX] byte addresses | capacities
+    DevBuf<u64> ghist;
+    DevBuf<unsigned long long> ctr;
+};
+
+void count_parts_impl(ottocov_ctx* ctx, int n_parts, const int32_t* const* session, const int32_t* const* aid,
+                      const int32_t* const* ts, const int8_t* const* type, const int64_t* rows, const ottocov_spec* specs,
+                      int n_specs, ottocov_table** tables_out) {
+    free_events(ctx);
+    memset(&ctx->last_count, 0, sizeof(ctx->last_count));
+    for (int k = 0; k < n_specs; ++k) tables_out[k] = nullptr;
+    int64_t N = 0;
+    for (int p = 0; p < n_parts; ++p) {
+        if (rows[p] < 0) COV_THROW(OTTOCOV_ERR_ARG, "negative row count");
+        if (rows[p] > 0 && (!session[p] || !aid[p] || !ts[p] || !type[p])) COV_THROW(OTTOCOV_ERR_ARG, "NULL column");
+        N += rows[p];
+    }
+    ottocov_events_info total;
+    memset(&total, 0, sizeof(total));
+    total.was_sorted = 1;
+    total.session_min = total.ts_min = 2147483647; total.session_max = total.ts_max = -2147483647 - 1;
+    if (N == 0) {
+        for (int k = 0; k < n_specs; ++k) tables_out[k] = make_empty_table(1);
+        ctx->info = total; ctx->info.session_min = ctx->info.session_max = ctx->info.ts_min = ctx->info.ts_max = 0;
+        return;
+    }
+    // ---- groups of consecutive parts, ~equal rows: big enough to amortise the per-group host round trips, small
+    //      enough that the work on a group hides behind the copy of the next one
+    int n_groups = n_parts < 10 ? n_parts : 10;
+    std::vector<int> g_first(n_groups + 1, 0);
+    {
+        int64_t acc = 0; int g = 1;
+        for (int p = 0; p < n_parts && g < n_groups; ++p) {
+            acc += rows[p];
+            if (acc * n_groups >= N * g) { g_first[g++] = p + 1; }
+        }
+        for (; g <= n_groups; ++g) g_first[g] = n_parts;
+        g_first[n_groups] = n_parts;
+    }
+    std::vector<int64_t> off(n_parts + 1, 0);
+    for (int p = 0; p < n_parts; ++p) off[p + 1] = off[p] + rows[p];
+
+    DevBuf<int32_t> d_session(ctx, N), d_aid(ctx, N), d_ts(ctx, N);
+    DevBuf<int8_t> d_type(ctx, N);
+    if (!ctx->copy_stream) CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    cudaStream_t cs = ctx->copy_stream;
+    std::vector<cudaEvent_t> used;
+    struct EventReturn {
+        ottocov_ctx* c; std::vector<cudaEvent_t>& v;
+        ~EventReturn() { for (cudaEvent_t e : v) c->sync_events.push_back(e); }
+    } event_return{ctx, used};
+    auto new_event = [&]() {
+        cudaEvent_t e;
+        if (!ctx->sync_events.empty()) { e = ctx->sync_events.back(); ctx->sync_events.pop_back(); }
+        else CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        used.push_back(e);
+        return e;
+    };
+    cudaEvent_t e0 = new_event();                       // the device blocks may still be in use by earlier work
+    CUDA_CHECK(cudaEventRecord(e0, ctx->stream));
+    CUDA_CHECK(cudaStreamWaitEvent(cs, e0, 0));
+    ctx->begin(OTTOCOV_K_LOAD);
+    for (int p = 0; p < n_parts; ++p)                   // aid and type of every part first: the key width is global
+        if (rows[p]) {
+            CUDA_CHECK(cudaMemcpyAsync(d_aid.p + off[p], aid[p], rows[p] * 4, cudaMemcpyHostToDevice, cs));
+            CUDA_CHECK(cudaMemcpyAsync(d_type.p + off[p], type[p], rows[p], cudaMemcpyHostToDevice, cs));
+        }
+    cudaEvent_t e_aid = new_event();
+    CUDA_CHECK(cudaEventRecord(e_aid, cs));
+    std::vector<cudaEvent_t> e_grp(n_groups);
+    for (int g = 0; g < n_groups; ++g) {
+        for (int p = g_first[g]; p < g_first[g + 1]; ++p)
+            if (rows[p]) {
+                CUDA_CHECK(cudaMemcpyAsync(d_session.p + off[p], session[p], rows[p] * 4, cudaMemcpyHostToDevice, cs));
+                CUDA_CHECK(cudaMemcpyAsync(d_ts.p + off[p], ts[p], rows[p] * 4, cudaMemcpyHostToDevice, cs));
+            }
+        e_grp[g] = new_event();
+        CUDA_CHECK(cudaEventRecord(e_grp[g], cs));
+    }
+    ctx->end(OTTOCOV_K_LOAD, 13.0 * N);
+    ctx->stats[OTTOCOV_K_LOAD].launches -= 1;           // copies, not kernels
+    // no exit path may return while a copy still reads the caller's host buffers, or leave the main stream ahead of them
+    struct JoinCopies {
+        ottocov_ctx* c; cudaEvent_t last; bool done = false;
+        ~JoinCopies() { cudaStreamWaitEvent(c->stream, last, 0); if (!done) cudaStreamSynchronize(c->copy_stream); }
+    } join_copies{ctx, e_grp[n_groups - 1]};
+
+    // ---- global key width ------------------------------------------------------------------------------------------
+    CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, e_aid, 0));
+    DevBuf<int> d_mm(ctx, 2);
+    COV_LAUNCH(ctx, OTTOCOV_K_MISC, 0, init_minmax_kernel, 1, 1, 0, d_mm.p);
+    COV_LAUNCH(ctx, OTTOCOV_K_LOAD, 4.0 * N, aid_max_kernel, (int)imin64(ceil_div64(N, 1024), (int64_t)ctx->num_sms * 8), 256, 0,
+               d_aid.p, N, d_mm.p);
+    int mm[2];
+    cov_readback(ctx, mm, d_mm.p, sizeof(mm));
+    if (mm[1] < 0) COV_THROW(OTTOCOV_ERR_DATA, "negative aid %d", mm[1]);
+    int aid_bits = 0;
+    for (u32 v = (u32)mm[0]; v; v >>= 1) ++aid_bits;
+    if (aid_bits == 0) aid_bits = 1;
+    const bool hashable = hashed_reduce_supported(aid_bits);
+    const KeyMix mix = make_key_mix(aid_bits);
+
+    std::vector<PartsAccum> acc(n_specs);
+    struct AccGuard {
+        ottocov_ctx* c; std::vector<PartsAccum>& v;
+        ~AccGuard() { for (auto& a : v) for (u64* b : a.bufs) dev_free(c, b); }
+    } acc_guard{ctx, acc};
+    bool fallback = !hashable;                          // keys too wide for the hash path: plain load + count below
+    std::vector<int64_t> g_rows(n_groups);
+
+    for (int g = 0; g < n_groups && !fallback; ++g) {
+        const int64_t r0 = off[g_first[g]], r1 = off[g_first[g + 1]];
+        g_rows[g] = r1 - r0;
+        CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, e_grp[g], 0));
+        if (r1 == r0) continue;
+        load_events_impl(ctx, d_session.p + r0, d_aid.p + r0, d_ts.p + r0, d_type.p + r0, r1 - r0, OTTOCOV_DEVICE);
+        const ottocov_events_info gi = ctx->info;
+        total.n_rows_in += gi.n_rows_in; total.n_events += gi.n_events;
+        for (int t = 0; t < 3; ++t) total.n_by_type[t] += gi.n_by_type[t];
+        total.session_min = gi.session_min < total.session_min ? gi.session_min : total.session_min;
+        total.session_max = gi.session_max > total.session_max ? gi.session_max : total.session_max;
+        total.ts_min = gi.ts_min < total.ts_min ? gi.ts_min : total.ts_min;
+        total.ts_max = gi.ts_max > total.ts_max ? gi.ts_max : total.ts_max;
+        total.was_sorted = total.was_sorted && gi.was_sorted;
+        ctx->info.aid_bits = aid_bits;                  // keys of every group are made with the global width
+        for (int k = 0; k < n_specs; ++k) {
+            PartsAccum& a = acc[k];
+            ExpandPlan* pl = make_plan(ctx, &specs[k], false);
+            struct PlanGuard { ExpandPlan* p; ~PlanGuard() { delete p; } } plan_guard{pl};
+            if (!a.started) {
+                a.started = true;
+                a.spec = specs[k];
+                a.sym = pl->sym;
+                a.user_min = pl->user_min;
+                // bucket bits from the key count this kind will have if the other groups look like this one
+                const u64 P_est = (u64)((double)pl->P * (double)N / (double)(r1 - r0)) + 1;
+                a.bb = hashed_bucket_bits((int64_t)P_est, mix.kb);
+                if (a.bb <= RS_MAX_BITS) a.bb = (RS_MAX_BITS + 1 < mix.kb) ? RS_MAX_BITS + 1 : mix.kb;   // >= 1 pass after the fused one
+                BitField f[1] = {{mix.kb - a.bb, mix.kb}};
+                a.full = make_pass_list(f, 1);
+                if (a.full.n < 2) { fallback = true; break; }         // keys of < 9 bits: not worth a fused pass
+                BitField rf[1] = {{mix.kb - a.bb + a.full.bits[0], mix.kb}};
+                a.rest = make_pass_list(rf, 1);
+                a.n_digits = 1u << a.full.bits[0];
+                a.cursor.alloc(ctx, (size_t)n_groups * RS_RADIX);
+                a.reg.alloc(ctx, (size_t)n_groups * 2 * RS_RADIX);
+                a.ghist.alloc(ctx, (size_t)a.rest.n * RS_RADIX);
+                a.ctr.alloc(ctx, 2);
+                CUDA_CHECK(cudaMemsetAsync(a.cursor.p, 0, (size_t)n_groups * RS_RADIX * sizeof(unsigned long long), ctx->stream));
+                CUDA_CHECK(cudaMemsetAsync(a.ghist.p, 0, (size_t)a.rest.n * RS_RADIX * sizeof(u64), ctx->stream));
+                CUDA_CHECK(cudaMemsetAsync(a.ctr.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
+            }
+            if (pl->sym != a.sym) COV_THROW(OTTOCOV_ERR_CUDA, "inconsistent symmetric choice across groups");
+            a.n_pairs += pl->sym ? 2 * pl->P : pl->P;
+            const u64 capg = ((((u64)((double)pl->P / a.n_digits * (1.0 + fuse_slack_pct() / 100.0)) + 4096) + 1) & ~1ull);
+            a.cap.resize(n_groups, 0);
+            a.bufs.resize(n_groups, nullptr);
+            if (pl->P == 0) continue;
+            a.cap[g] = capg;
+            a.bufs[g] = (u64*)cov_alloc(ctx, (size_t)a.n_digits * capg * 8);
+            a.P_total += pl->P;
+            u64* reg_base = a.reg.p + (size_t)g * 2 * RS_RADIX;
+            DevBuf<u64> tmp_off(ctx, RS_RADIX);
+            COV_LAUNCH(ctx, OTTOCOV_K_MISC, 0, region_table_kernel, 1, RS_RADIX, 0, reg_base, reg_base + RS_RADIX, tmp_off.p,
+                       reinterpret_cast<u64>(a.bufs[g]), capg, (const unsigned long long*)nullptr, (u64)0, 0u, a.n_digits);
+            ScatterArgs sa;
+            sa.reg_base = reg_base; sa.reg_cap = reg_base + RS_RADIX; sa.cursor = a.cursor.p + (size_t)g * RS_RADIX;
+            sa.flags = reinterpret_cast<u32*>(a.ctr.p + 1);
+            sa.sh1 = a.full.shift[0]; sa.sub_bits = a.full.bits[0]; sa.n_digits = a.n_digits; sa.d_lo = 0; sa.d_hi = a.n_digits;
+            sa.n_dest = 0;
+            expand_scatter_all(ctx, pl, mix, a.rest, a.ghist.p, sa);
+        }
+    }
+    total.aid_max = mm[0];
+    total.aid_bits = aid_bits;
+
+    // ---- remaining passes + hash reduce per kind, over the regions of all groups -------------------------------------------
+    if (!fallback) {
+        for (int k = 0; k < n_specs && !fallback; ++k) {
+            PartsAccum& a = acc[k];
+            memset(&ctx->last_count, 0, sizeof(ctx->last_count));
+            ctx->last_count.n_pairs = (int64_t)a.n_pairs;
+            if (!a.started || a.P_total == 0) { tables_out[k] = make_empty_table(aid_bits); continue; }
+            // one array of n keys for the ping-pong of the passes; region offsets are taken relative to it (mod 2^64)
+            DevBuf<u64> base(ctx, (size_t)a.P_total), alt(ctx, (size_t)a.P_total);
+            std::vector<u64> h_off((size_t)n_groups * a.n_digits);
+            for (int g = 0; g < n_groups; ++g)
+                for (u32 d = 0; d < a.n_digits; ++d)
+                    h_off[(size_t)g * a.n_digits + d] =
+                        a.bufs[g] ? (u64)((reinterpret_cast<int64_t>(a.bufs[g]) - reinterpret_cast<int64_t>(base.p)) / 8 +
+                                          (int64_t)((u64)d * a.cap[g])) : 0ull;      // signed distance, stored mod 2^64
+            DevBuf<u64> seg_off(ctx, h_off.size()), seg_cnt(ctx, h_off.size());
+            CUDA_CHECK(cudaMemcpyAsync(seg_off.p, h_off.data(), h_off.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+            CUDA_CHECK(cudaStreamSynchronize(ctx->stream));          // h_off is a local vector
+            for (int g = 0; g < n_groups; ++g)                        // [g][RS_RADIX] counters -> dense [g][n_digits]
+                CUDA_CHECK(cudaMemcpyAsync(seg_cnt.p + (size_t)g * a.n_digits, a.cursor.p + (size_t)g * RS_RADIX,
+                                           a.n_digits * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+            HashPre pre;
+            pre.bb = a.bb; pre.first_bits = a.full.bits[0]; pre.seg_cnt = seg_cnt.p; pre.seg_off = seg_off.p;
+            pre.n_a = n_groups; pre.n_b = (int)a.n_digits; pre.ctr = a.ctr.p;
+            int passes = 0;
+            try {
+                tables_out[k] = hashed_reduce(ctx, base.p, alt.p, (int64_t)a.P_total, mix, a.user_min, a.sym, a.sym, &passes,
+                                              a.ghist.p, &pre);
+            } catch (const FusedOverflow&) {
+                fallback = true;                                      // a hot pair outgrew a region: plain path below
+                break;
+            }
+            ctx->last_count.sort_passes = passes;
+            ctx->last_count.n_chunks = n_groups;
+            ctx->last_count.fused = 1;
+            ctx->last_count.n_unique = tables_out[k]->n;
+            for (u64*& b : a.bufs) { dev_free(ctx, b); b = nullptr; }
+        }
+    }
+    if (fallback) {
+        // the columns are all on the device by now (or will be: the main stream waits for the last copy)
+        for (int k = 0; k < n_specs; ++k)
+            if (tables_out[k]) { dev_free(ctx, tables_out[k]->keys); dev_free(ctx, tables_out[k]->count); delete tables_out[k]; tables_out[k] = nullptr; }
+        for (auto& a : acc) for (u64*& b : a.bufs) { dev_free(ctx, b); b = nullptr; }
+        CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, e_grp[n_groups - 1], 0));
+        load_events_impl(ctx, d_session.p, d_aid.p, d_ts.p, d_type.p, N, OTTOCOV_DEVICE);
+        total = ctx->info;
+        for (int k = 0; k < n_specs; ++k) tables_out[k] = count_impl(ctx, &specs[k]);
+    }
+    free_events(ctx);
+    ctx->info = total;
+    ctx->info_only = true;
 }
 
 // ---- fused expansion + exchange (include/ottocov.h, "fused expansion + exchange") -----------------------------------

@@ -77,6 +77,7 @@ struct ottocov_ctx {
     size_t cached_bytes = 0, live_bytes = 0, peak_bytes = 0;
     // events
     bool loaded = false;
+    bool info_only = false;            // `info` holds the totals of an ottocov_count_parts run (no events are loaded)
     ottocov_events_info info;
     TypeArray ta[3];
     ottocov_count_info last_count;
@@ -104,6 +105,12 @@ struct ottocov_ctx {
     int32_t* topk_nvalid = nullptr;
     int32_t* topk_aid_y = nullptr;
     int32_t* topk_cnt = nullptr;
+    // derived count features of the last ottocov_count_features (features.cu): kept rows, struct of arrays
+    bool feat_valid = false;
+    int64_t feat_n = 0, feat_cap = 0;
+    int32_t* feat_i32 = nullptr;       // [3][feat_cap] aid | aid_next | count
+    int16_t* feat_i16 = nullptr;       // [3][feat_cap] count_pop | perc_pop | rank
+    int8_t* feat_i8 = nullptr;         // [feat_cap] count_rel
     // popularity result (popularity.cu): rows kept by the last ottocov_count_popularity
     bool pop_valid = false;
     int64_t pop_n = 0, pop_stride = 0;
@@ -248,6 +255,9 @@ void free_events(ottocov_ctx* ctx);
 // expand.cu
 ottocov_table* count_impl(ottocov_ctx* ctx, const ottocov_spec* spec);
 void free_plan(ottocov_ctx* ctx);
+void count_parts_impl(ottocov_ctx* ctx, int n_parts, const int32_t* const* session, const int32_t* const* aid,
+                      const int32_t* const* ts, const int8_t* const* type, const int64_t* rows, const ottocov_spec* specs,
+                      int n_specs, ottocov_table** tables_out);
 void expand_prepare_impl(ottocov_ctx* ctx, const ottocov_spec* spec, int64_t* n_keys, int* symmetric);
 void expand_run_impl(ottocov_ctx* ctx, int n_ranks, u64* buf_a, u64* buf_b, int* result_in_b, int64_t* rows_per_dest);
 void push_keys_impl(ottocov_ctx* ctx, const u64* keys, int64_t n, int n_ranks, const u64* dest_ptrs_host);
@@ -324,6 +334,13 @@ void topk_impl(ottocov_ctx* ctx, const ottocov_table* t, int k);
 void free_topk(ottocov_ctx* ctx);
 void topk_lookup_impl(ottocov_ctx* ctx, const int32_t* aids, int64_t n, int where, int32_t* n_valid, int32_t* aid_y,
                       int32_t* cnt);
+
+// features.cu
+void count_features_impl(ottocov_ctx* ctx, const int32_t* aid, const int32_t* aid_next, const int32_t* count, int64_t n,
+                         int where, int first_n, int64_t quantile_row);
+void count_features_fetch_impl(ottocov_ctx* ctx, int32_t* aid, int32_t* aid_next, int32_t* count, int16_t* count_pop,
+                               int16_t* perc_pop, int16_t* rank, int8_t* count_rel, int64_t cap, int where);
+void free_features(ottocov_ctx* ctx);
 
 // popularity.cu
 void count_popularity_impl(ottocov_ctx* ctx, const int32_t* cluster, const int32_t* aid, const int32_t* ts,

@@ -29,8 +29,8 @@ def _as_col(x, np_dtype, torch_dtype_name):
         import torch
         dt = getattr(torch, torch_dtype_name)
         if x.dtype != dt and x.numel() and not (np_dtype == np.uint64 and x.dtype == torch.int64):
-            if x.dtype.is_floating_point or x.dtype == torch.bool:
-                raise ValueError(f"column of dtype {x.dtype} where {torch_dtype_name} is expected")
+            if x.dtype.is_floating_point and not bool((x == x.floor()).all()):
+                raise ValueError(f"column of dtype {x.dtype} with non-integral values where {torch_dtype_name} is expected")
             lo, hi = int(x.min()), int(x.max())
             if lo < info.min or hi > info.max:
                 raise ValueError(f"column values [{lo}, {hi}] do not fit {torch_dtype_name} (timestamps must be seconds)")
@@ -38,7 +38,7 @@ def _as_col(x, np_dtype, torch_dtype_name):
         return t.data_ptr(), (_lib.DEVICE if t.is_cuda else _lib.HOST), t
     a = np.asarray(x)
     if a.dtype != np_dtype and a.size:
-        if a.dtype.kind not in "iu":
+        if a.dtype.kind not in "iufb" or (a.dtype.kind == "f" and not np.all(a == np.floor(a))):
             raise ValueError(f"column of dtype {a.dtype} where {np.dtype(np_dtype).name} is expected")
         lo, hi = int(a.min()), int(a.max())
         if lo < info.min or hi > info.max:
@@ -262,6 +262,61 @@ class Engine:
             flags |= 16
         return _lib.Spec(th, mask, w, budget, max(int(min_count), 0), flags, dt_min, dt_max)
 
+    # ---- streamed ingest + count ------------------------------------------------------------------------------
+    def count_parts(self, parts, names: Sequence[str], min_counts: Optional[Sequence[int]] = None) -> List[Table]:
+        """The per-file loop of count_co_events_all_files + the merge of the part tables for one population
+        (count_co_events.py:83-100, :112-168), with the host -> device copy of the parts overlapped with the counting.
+
+        parts: list of (session, aid, ts, type) column tuples as the ETL wrote them (one tuple per parquet part; a
+        session never spans two parts).  Host arrays (numpy, or torch CPU tensors -- pinned ones copy asynchronously).
+        Returns one Table per name, identical to load_events(concatenation) + count(name, min_count=...)."""
+        keep = []
+        n_parts = len(parts)
+        cols = [(ctypes.c_void_p * max(n_parts, 1))() for _ in range(4)]
+        rows = (ctypes.c_int64 * max(n_parts, 1))()
+        for i, p in enumerate(parts):
+            s, a, t, y = p
+            n = len(s)
+            for j, (x, npd, tdn) in enumerate(((s, np.int32, "int32"), (a, np.int32, "int32"), (t, np.int32, "int32"),
+                                               (y, np.int8, "int8"))):
+                ptr, where, k = _as_col(x, npd, tdn)
+                if where != _lib.HOST:
+                    raise ValueError("count_parts takes host columns (the parts as read from parquet)")
+                if len(k) != n:
+                    raise ValueError("columns of a part differ in length")
+                keep.append(k)
+                cols[j][i] = ptr
+            rows[i] = n
+        if min_counts is None:
+            min_counts = [self.config.MIN_COUNT_TO_SAVE.get(nm, 1) for nm in names]
+        specs = (_lib.Spec * len(names))()
+        for k, (nm, mc) in enumerate(zip(names, min_counts)):
+            specs[k] = self._spec(nm, None, None, None, None, mc, None, None)
+        out = (ctypes.c_void_p * len(names))()
+        self._sync_stream()
+        self.load_generation += 1
+        self._check(self._lib.ottocov_count_parts(self._ctx, n_parts, cols[0], cols[1], cols[2], cols[3], rows, specs,
+                                                  len(names), out))
+        del keep
+        return [Table(self, h) for h in out]
+
+    @staticmethod
+    def split_at_sessions(session, aid, ts, type_, n_parts: int):
+        """One population in contiguous host columns ordered by session -> n_parts column-view tuples cut at session
+        boundaries (what reading the ETL's parts would give).  O(n_parts log n) on the host, no copies."""
+        s = session.numpy() if _is_torch(session) else np.asarray(session)
+        n = len(s)
+        cuts = [0]
+        for i in range(1, n_parts):
+            r = n * i // n_parts
+            if r <= cuts[-1] or r >= n:
+                continue
+            r = int(np.searchsorted(s, s[r], side="left"))         # back to the first row of that session
+            if r > cuts[-1]:
+                cuts.append(r)
+        cuts.append(n)
+        return [tuple(x[cuts[i]:cuts[i + 1]] for x in (session, aid, ts, type_)) for i in range(len(cuts) - 1)]
+
     # ---- exchange-before-reduce building blocks (multi-GPU) ---------------------------------------------
     def expand_prepare(self, name: Optional[str] = None, *, type_this=None, next_types=None, window=None,
                        min_count: int = 1, symmetric: Optional[bool] = None) -> Tuple[int, bool]:
@@ -442,6 +497,32 @@ class Engine:
         self._check(self._lib.ottocov_topk_lookup(self._ctx, a.ctypes.data, n, _lib.HOST, nv.ctypes.data, ay.ctypes.data,
                                                   ac.ctypes.data))
         return nv, ay, ac
+
+    # ---- derived co-count features (model/retrieve.py:18-63) ------------------------------------------------------
+    def count_features(self, aid, aid_next, count, first_n: int) -> Dict[str, np.ndarray]:
+        """get_df_count_for_co_event_type on a count table given in FILE order: per-aid top-first_n (count desc,
+        aid_next asc) with count_pop / perc_pop / rank / count_rel, all computed on the device.
+        -> {'aid', 'aid_next', 'count', 'count_pop' (i16), 'perc_pop' (i16), 'rank' (i16), 'count_rel' (i8)}."""
+        pa, wa, ka = _as_col(aid, np.int32, "int32")
+        pb, wb, kb = _as_col(aid_next, np.int32, "int32")
+        pc, wc, kc = _as_col(count, np.int32, "int32")
+        if len({wa, wb, wc}) != 1:
+            raise ValueError("all three columns must live on the same side (host or device)")
+        n = len(ka)
+        # numpy's method='nearest': the row of the ascending order closest to (n - 1) * q (retrieve.py:34 uses
+        # polars' quantile(0.9999, 'nearest'))
+        qrow = int(np.around((n - 1) * 0.9999)) if n else 0
+        rows = ctypes.c_int64()
+        self._sync_stream()
+        self._check(self._lib.ottocov_count_features(self._ctx, pa, pb, pc, n, wa, int(first_n), qrow, ctypes.byref(rows)))
+        m = int(rows.value)
+        o = {"aid": np.empty(m, np.int32), "aid_next": np.empty(m, np.int32), "count": np.empty(m, np.int32),
+             "count_pop": np.empty(m, np.int16), "perc_pop": np.empty(m, np.int16), "rank": np.empty(m, np.int16),
+             "count_rel": np.empty(m, np.int8)}
+        self._check(self._lib.ottocov_count_features_fetch(self._ctx, *(o[k].ctypes.data for k in
+                                                           ("aid", "aid_next", "count", "count_pop", "perc_pop", "rank", "count_rel")),
+                                                           m, _lib.HOST))
+        return o
 
     # ---- popularity inside session clusters (model/count_popularity.py:56-85) ---------------------------------
     POPULARITY_RANK_COLUMNS = ("rank_clicks", "rank_carts", "rank_orders", "rank_clicks_7d", "rank_carts_7d",

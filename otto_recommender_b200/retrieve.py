@@ -1,9 +1,8 @@
 """Per-aid top-N of a co-event count table + the derived count features of the consumer.
 
 Mirror of ``get_df_count_for_co_event_type`` (reference model/retrieve.py:18-63): same arguments,
-same output columns.  The segmented top-N (retrieve.py:41-47) runs on the GPU
-(``ottocov_table_topk``); the population-level features (:33-38) and ``count_rel`` (:49) are cheap
-vector arithmetic on the fetched columns.
+same output columns.  The segmented top-N (retrieve.py:41-47), the population-level features
+(:33-38) and ``count_rel`` (:49) all run on the GPU (``ottocov_count_features``, csrc/features.cu).
 
 Tie rule: the reference ranks with ``rank('ordinal', reverse=True).over('aid')`` on a frame sorted
 by aid only, so rows with equal count keep file order, which is itself unspecified upstream.  Here
@@ -36,34 +35,16 @@ def get_df_count_for_co_event_type(count_type: str, dir_counts: str, first_n: Op
         first_n = config.RETRIEVAL_FIRST_N_CO_COUNTS[count_type]
     t = pq.read_table(f"{dir_counts}/{count_type}.parquet", columns=["aid", "aid_next", "count"])
     aid, aid_next, count = (t[c].to_numpy() for c in ("aid", "aid_next", "count"))
-    n = len(aid)
     cols = [f"{count_type}_count", f"{count_type}_count_pop", f"{count_type}_perc_pop", f"{count_type}_rank",
             f"{count_type}_count_rel"]
-    if n == 0:
+    if len(aid) == 0:
         return pd.DataFrame({"aid": np.zeros(0, np.int32), "aid_next": np.zeros(0, np.int32),
                              **{c: np.zeros(0, np.int32) for c in cols}})
-    # over the entire population (retrieve.py:33-38)
-    cmin = count.min()
-    q = np.quantile(count, 0.9999, method="nearest")
-    denom = max(float(q - cmin), 1e-12)
-    count_pop = (np.minimum((count - cmin) / denom, 1.0) * 10_000).astype(np.int16)
-    perc_pop = (np.arange(1, n + 1) / n * 10_000).astype(np.int16)
-    # over pairs: segmented top-N on the GPU (retrieve.py:41-47)
-    eng = get_engine()
-    tab = eng.table_from_arrays(aid, aid_next, count.astype(np.uint32))
-    ax, nv, ay, ac = eng.topk(tab, first_n)
-    tab.free()
-    o_aid, o_next, o_cnt, o_rank = topn_long(ax, nv, ay, ac)
-    max_count = np.repeat(ac[:, 0], nv)
-    count_rel = (o_cnt / max_count * 100).astype(np.int8)                     # retrieve.py:49
-    # carry the population features of the kept rows
-    key_all = (aid.astype(np.int64) << 32) | aid_next.astype(np.int64)
-    order = np.argsort(key_all, kind="stable")
-    pos = order[np.searchsorted(key_all[order], (o_aid.astype(np.int64) << 32) | o_next.astype(np.int64))]
-    return pd.DataFrame({
-        "aid": o_aid, "aid_next": o_next,
-        cols[0]: o_cnt, cols[1]: count_pop[pos], cols[2]: perc_pop[pos], cols[3]: o_rank, cols[4]: count_rel,
-    })
+    # everything below the file read runs on the GPU (ottocov_count_features): the population statistics
+    # (retrieve.py:33-38), the segmented top-N (:41-47) and count_rel (:45-49)
+    f = get_engine().count_features(aid, aid_next, count, first_n)
+    return pd.DataFrame({"aid": f["aid"], "aid_next": f["aid_next"], cols[0]: f["count"], cols[1]: f["count_pop"],
+                         cols[2]: f["perc_pop"], cols[3]: f["rank"], cols[4]: f["count_rel"]})
 
 
 def get_pairs_co_event_type(df_aids, df_count, type: int = 0) -> pd.DataFrame:

@@ -8,7 +8,8 @@ import pytest
 import torch
 
 from conftest import small_events
-from oracle import c_oracle, ref_restatement as rr
+from oracle import c_oracle
+from oracle import ref_restatement as rr
 from otto_recommender_b200 import OttocovError
 from otto_recommender_b200.dist import hash_dest
 from otto_recommender_b200.retrieve import topn_long
@@ -298,6 +299,39 @@ def test_topk_lookup_candidates(engine):
             assert qnv[i] == nv[r] and np.array_equal(qy[i], gy[r]) and np.array_equal(qc[i], gc[r])
         else:
             assert qnv[i] == 0 and np.all(qy[i] == -1) and np.all(qc[i] == 0)
+
+
+def test_count_features_on_device(engine):
+    """ottocov_count_features == the restatement of get_df_count_for_co_event_type (retrieve.py:18-63), all seven
+    columns: (1) a canonical file (count desc, aid asc, aid_next asc) with heavy ties; (2) distinct counts in an
+    arbitrary FILE order -- perc_pop must follow the file row, the quantile the sorted counts."""
+    import pyarrow as pa
+    rng = np.random.default_rng(9)
+    for case in ("canonical_ties", "arbitrary_order"):
+        n = 60_000
+        key = rng.choice(400 * 400, n, replace=False)
+        aid, nxt = (key // 400).astype(np.int32), (key % 400).astype(np.int32) * 3
+        if case == "canonical_ties":
+            cnt = np.minimum(rng.geometric(0.05, n), 300).astype(np.int32)
+            o = np.lexsort((nxt, aid, -cnt.astype(np.int64)))
+        else:
+            cnt = (rng.permutation(n) + 5).astype(np.int32)
+            o = rng.permutation(n)
+        aid, nxt, cnt = aid[o], nxt[o], cnt[o]
+        tab = pa.table({"aid": aid, "aid_next": nxt, "count": cnt})
+        for first_n in (1, 10, 20, 32):
+            want = rr.count_features(tab, "click_to_click", first_n)
+            got = engine.count_features(aid, nxt, cnt, first_n)
+            ren = {"aid": "aid", "aid_next": "aid_next", "click_to_click_count": "count", "click_to_click_count_pop": "count_pop",
+                   "click_to_click_perc_pop": "perc_pop", "click_to_click_rank": "rank", "click_to_click_count_rel": "count_rel"}
+            for col, arr in want.items():
+                assert np.array_equal(got[ren[col]], arr), (case, first_n, col)
+    e = engine.count_features(np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.int32), 10)
+    assert all(len(v) == 0 for v in e.values())
+    one = engine.count_features(np.array([7]), np.array([9]), np.array([4]), 10)       # q == min: the division guard
+    w1 = rr.count_features(pa.table({"aid": np.array([7], np.int32), "aid_next": np.array([9], np.int32),
+                                     "count": np.array([4], np.int32)}), "click_to_click", 10)
+    assert one["count_pop"].tolist() == w1["click_to_click_count_pop"].tolist() and one["perc_pop"].tolist() == [10000]
 
 
 def test_partition_by_hash(engine):
@@ -673,6 +707,56 @@ def test_pipelined_host_load(engine):
     with pytest.raises(OttocovError) as e:
         engine.load_events(s, neg, t, y)
     assert e.value.code == -3
+
+
+def test_count_parts_streamed(engine):
+    """ottocov_count_parts: the parts of one population handed over as separate host buffers, copied on a second stream
+    and counted group by group behind the copies (expansion fused with the first bucket pass per group; the remaining
+    passes + hash reduce once over the regions of all groups).  Same tables as load_events(concatenation) + count, for
+    every kind, thresholded or not; rows inside a part may come in any order; empty parts are fine."""
+    from otto_recommender_b200 import Engine
+    d = generate_numpy(SynthSpec(n_sessions=60_000, seed=17))
+    s, a, t, y = d["session"], d["aid"], d["ts"], d["type"]
+    names = list(NAMES)
+    mcs = [3, 2, 1, 2, 1]
+    info = engine.load_events(s, a, t, y)
+    want = [engine.count(n, min_count=mc).fetch() for n, mc in zip(names, mcs)]
+    oa, ob, oc, emitted, _ = c_oracle.count_name(s, a, t, y, "click_to_click")
+    ka, kb, kc = c_oracle.merge_tables([(oa, ob, oc)], min_count=3)
+    assert np.array_equal(want[0][0], ka) and np.array_equal(want[0][2], kc)
+    rng = np.random.default_rng(5)
+    for n_parts in (1, 7, 23):
+        parts = Engine.split_at_sessions(s, a, t, y, n_parts)
+        assert sum(len(p[0]) for p in parts) == len(s)
+        assert all(p[0][0] != q[0][-1] for p, q in zip(parts[1:], parts[:-1]))        # cut at session boundaries
+        if n_parts == 7:                                                              # any row order inside a part; an empty part
+            parts = [tuple(x[o] for x in p) for p in parts for o in [rng.permutation(len(p[0]))]]
+            parts.insert(3, tuple(x[:0] for x in parts[0]))
+        tabs = engine.count_parts(parts, names, mcs)
+        ci = engine.count_info()
+        assert ci["fused"] == 1
+        got_info = engine.events_info()
+        for k in ("n_rows_in", "n_events", "n_by_type", "aid_bits", "aid_max", "session_min", "session_max", "ts_min", "ts_max"):
+            assert got_info[k] == info[k], k
+        for n, tab, w in zip(names, tabs, want):
+            for x, z in zip(tab.fetch(), w):
+                assert np.array_equal(x, z), (n, n_parts)
+            tab.free()
+        with pytest.raises(OttocovError) as e:          # the events of the parts are gone: count needs a new load
+            engine.count("click_to_click")
+        assert e.value.code == -4
+    # invalid data inside a part is reported, nothing is left behind
+    bad = y.copy(); bad[len(bad) // 3] = 9
+    with pytest.raises(OttocovError) as e:
+        engine.count_parts(Engine.split_at_sessions(s, a, t, bad, 5), ["click_to_click"], [2])
+    assert e.value.code == -3
+    tiny = small_events(3, n_sessions=30)               # too few keys for a fused pass: the plain path serves the call
+    o = np.lexsort((tiny[2], tiny[0]))
+    tiny = tuple(x[o] for x in tiny)
+    engine.load_events(*tiny)
+    w = engine.count("click_to_cart_or_buy", min_count=1).fetch()
+    g = engine.count_parts(Engine.split_at_sessions(*tiny, 3), ["click_to_cart_or_buy"], [1])[0].fetch()
+    assert all(np.array_equal(x, z) for x, z in zip(g, w))
 
 
 def test_hash_reduce_packed_relative_tags():

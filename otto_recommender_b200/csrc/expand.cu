@@ -1199,8 +1199,16 @@ void xplan_make_impl(int n_ranks, int aid_bits, int64_t max_local_keys, int64_t 
     if (max_local_keys < 0 || total_keys < 0) COV_THROW(OTTOCOV_ERR_ARG, "negative key count");
     memset(out, 0, sizeof(*out));
     const int kb = 2 * aid_bits;
+    // (owner, sub-digit) digits: n_ranks << sub <= max_digits.  Fewer digits = longer per-digit runs per tile (the
+    // stores that cross NVLink), more digits = fewer bits left for the owner's remaining passes.
+    static int max_digits = 0;
+    if (!max_digits) {
+        const char* e = getenv("OTTOCOV_XCH_DIGITS");       // tuning knob
+        max_digits = e ? atoi(e) : 32;                      // measured at N = 2 (step ms): 128 -> 16.55, 64 -> 16.20, 32 -> 16.11, 16 -> 17.08
+        if (max_digits < 2 || max_digits > 256) max_digits = 32;
+    }
     int sub = 0;
-    while ((n_ranks << (sub + 1)) <= 128) ++sub;            // (owner, sub-digit) digits: n_ranks << sub <= 128
+    while ((n_ranks << (sub + 1)) <= max_digits) ++sub;
     int bb = hashed_bucket_bits(total_keys / n_ranks, kb);  // buckets of the keys one rank receives
     if (bb < sub + 1) bb = sub + 1;                          // at least one pass after the fused one
     if (bb > kb) { bb = kb; if (sub > bb - 1) sub = bb - 1; }

@@ -101,3 +101,50 @@ def test_merge_and_topn_restatement_vs_numpy():
     assert np.array_equal(top["aid_next"].to_numpy(), tb)
     assert np.array_equal(top["count"].to_numpy(), tc)
     assert np.array_equal(top["rank"].to_numpy(), tr)
+
+
+# ---- reference-run pin --------------------------------------------------------------------------------------
+def _ref_fixtures():
+    import glob
+    return sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_*.json")))
+
+
+def check_against_reference_fixture(path, count_fn, topn_fn):
+    """Shared by the CPU (oracles) and GPU (CUDA path) tests: tables equal the reference's own output; the top-N is
+    compared tie-aware (the reference keeps file order among equal counts)."""
+    g = json.load(open(path))
+    rows = np.array(g["rows"])
+    s, a, t, y = (rows[:, i] for i in range(4))
+    for kind, want in g["counts"].items():
+        got = count_fn(s, a, t, y, kind)
+        assert got == {(r[0], r[1]): r[2] for r in want}, (path, kind)
+        kept = topn_fn(s, a, t, y, kind, g["topn"][kind]["first_n"])
+        for aid, counts in g["topn"][kind]["kept_counts_per_aid"].items():
+            assert sorted(kept.get(int(aid), []), reverse=True) == counts, (path, kind, aid)
+
+
+def test_reference_run_fixtures():
+    """tests/golden/ref_*.json are written by tools/gen_reference_fixtures.py from the UNMODIFIED reference functions
+    under polars.  polars is not installable in the build container, so the files may be absent: then this test
+    skips LOUDLY and the oracle stays pinned only by hand-verified vectors (parity unpinned by the reference)."""
+    files = _ref_fixtures()
+    if not files:
+        pytest.skip("PARITY UNPINNED: no tests/golden/ref_*.json -- run tools/gen_reference_fixtures.py where polars "
+                    "(~0.15-0.16) is available to pin the oracle against the reference's own output")
+
+    def count_fn(s, a, t, y, kind):
+        oa, ob, oc, _, _ = c_oracle.count_name(s, a, t, y, kind)
+        d = _dict(oa, ob, oc)
+        assert d == rr.table_to_dict(rr.count_events_all_names(s, a, t, y)[kind])
+        return d
+
+    def topn_fn(s, a, t, y, kind, first_n):
+        oa, ob, oc, _, _ = c_oracle.count_name(s, a, t, y, kind)
+        ta, tb, tc, _ = c_oracle.top_n(oa, ob, oc, first_n)
+        out = {}
+        for x, c in zip(ta.tolist(), tc.tolist()):
+            out.setdefault(x, []).append(c)
+        return out
+
+    for f in files:
+        check_against_reference_fixture(f, count_fn, topn_fn)

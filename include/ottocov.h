@@ -100,6 +100,8 @@ typedef struct {
     int32_t sort_passes;     /* distribution passes per chunk (a pass fused into the expansion counts) */
     int32_t fused;           /* 1 = the first pass of the bucketed hash reduce ran inside the expansion     */
     int32_t reserved;
+    int64_t h2d_bytes;       /* ottocov_count_parts: bytes copied host -> device (the session column travels  */
+                             /* run-length encoded when it compresses); 0 for the other calls                */
 } ottocov_count_info;
 
 /* Per-kernel-family accounting for roofline reports (bench.py). */

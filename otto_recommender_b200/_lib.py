@@ -34,7 +34,7 @@ class EventsInfo(Structure):
 
 class CountInfo(Structure):
     _fields_ = [("n_pairs", c_int64), ("n_unique", c_int64), ("n_chunks", c_int32), ("sort_passes", c_int32),
-                ("fused", c_int32), ("reserved", c_int32)]
+                ("fused", c_int32), ("reserved", c_int32), ("h2d_bytes", c_int64)]
 
 
 class XPlan(Structure):

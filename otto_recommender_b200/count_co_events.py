@@ -183,18 +183,19 @@ def concat_files_w_stats(name, dir_stats, files_stats=None):
 
 
 # ---- fused path (extension): whole population in HBM, no part files ----------------------------------
-def count_population(dir_sessions, names=None) -> Dict[str, Table]:
-    """All parts of one population loaded at once; phase 1+2 without the per-part files.  Equal to
-    the phased path whenever the reference's lossy merge steps do not trigger (exact mode)."""
+def count_population(dir_sessions, names=None, min_counts=None) -> Dict[str, Table]:
+    """All parts of one population counted in one go: phase 1 + 2 without the per-part files.  The parquet parts
+    are handed to the engine as they were read (one host buffer per column per part, nothing concatenated on the
+    host); it copies them on a second stream and counts group by group behind the copies
+    (``ottocov_count_parts``).  Equal to the phased path whenever the reference's lossy merge steps do not trigger
+    (exact mode).  min_counts: per-name thresholds fused into the reduce (default 1 = keep every pair, like the
+    part files)."""
     files = sorted(glob.glob(f"{dir_sessions}/*.parquet"))
-    cols = [_read_events(f) for f in files]
+    names = list(names or config.CO_EVENTS_TO_COUNT)
+    parts = [_read_events(f) for f in files]
     eng = get_engine()
-    if cols:
-        eng.load_events(*[np.concatenate([c[i] for c in cols]) for i in range(4)])
-    else:
-        z = np.zeros(0, np.int32)
-        eng.load_events(z, z, z, np.zeros(0, np.int8))
-    return {name: eng.count(name) for name in (names or config.CO_EVENTS_TO_COUNT)}
+    tabs = eng.count_parts(parts, names, list(min_counts) if min_counts is not None else [1] * len(names))
+    return dict(zip(names, tabs))
 
 
 def _layout(alias: str):

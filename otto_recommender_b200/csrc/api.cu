@@ -216,6 +216,7 @@ int ottocov_destroy(ottocov_ctx* ctx) {
     if (ctx->scan_ticket) cudaFree(ctx->scan_ticket);
     if (ctx->scan_totals) cudaFree(ctx->scan_totals);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->host_stage) cudaFreeHost(ctx->host_stage);
     for (ProfEvent& pe : ctx->prof_pending) { if (pe.a) cudaEventDestroy(pe.a); if (pe.b) cudaEventDestroy(pe.b); }
     for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->sync_events) cudaEventDestroy(e);

@@ -22,6 +22,9 @@
 // tiles are addressed by output offset) and the partial tables are merged at the end.
 #include "internal.cuh"
 #include "scan.cuh"
+#include <atomic>
+#include <thread>
+#include <memory>
 
 #ifndef OTTOCOV_EXS_ABLATE
 #define OTTOCOV_EXS_ABLATE 0      // timing experiments on expand_scatter_kernel (results are WRONG when non-zero):
@@ -940,6 +943,56 @@ __global__ void __launch_bounds__(256) aid_max_kernel(const int32_t* __restrict_
 
 __global__ void init_minmax_kernel(int* out) { out[0] = -2147483647 - 1; out[1] = 2147483647; }
 
+// ---- the session column crosses PCIe run-length encoded ---------------------------------------------------------------
+// The ETL writes each part ordered by session (etl/jsonl_to_parquet.py:59-84), so the 4-byte session column -- 31 % of
+// the 13 B/event the loader needs -- is ~17 equal values in a row.  Host threads turn it into (session id, first row)
+// runs while the DMA engine is busy with the aid and type columns; the runs (8 B per SESSION instead of 4 B per EVENT)
+// are copied instead and a kernel writes the column back out on the device.  A part whose session column does not
+// compress (rows in arbitrary order) is copied raw.
+struct RleTask {
+    const int32_t* session;
+    int64_t rows;
+    u32* out;                 // [2 * cap] (session id, first row) pairs, in page-locked memory
+    int64_t cap;              // runs that fit; beyond that the part is copied raw
+    int64_t n_runs;           // result: -1 = does not compress
+    std::atomic<int> done{0};
+};
+
+static void rle_encode(RleTask* t) {
+    const int32_t* s = t->session;
+    const int64_t n = t->rows, cap = t->cap;
+    u32* o = t->out;
+    int64_t k = 0;
+    if (n > 0) {
+        int32_t cur = s[0];
+        if (cap > 0) { o[0] = (u32)cur; o[1] = 0; }
+        k = 1;
+        for (int64_t i = 1; i < n; ++i) {
+            const int32_t v = s[i];
+            if (v != cur) {
+                if (k >= cap) { k = -1; break; }
+                o[2 * k] = (u32)v; o[2 * k + 1] = (u32)i;
+                ++k;
+                cur = v;
+            }
+        }
+        if (cap == 0) k = -1;
+    }
+    t->n_runs = k;
+    t->done.store(1, std::memory_order_release);
+}
+
+// one thread per run: rows [first row of the run, first row of the next run) get the run's session id
+__global__ void __launch_bounds__(256) rle_expand_kernel(const u32* __restrict__ runs, int64_t n_runs, int64_t rows,
+                                                         int32_t* __restrict__ session) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_runs) return;
+    const int32_t id = (int32_t)runs[2 * r];
+    const int64_t a = runs[2 * r + 1];
+    const int64_t b = (r + 1 < n_runs) ? (int64_t)runs[2 * r + 3] : rows;
+    for (int64_t i = a; i < b; ++i) session[i] = id;
+}
+
 // per-kind state carried over the groups
 struct PartsAccum {
     ottocov_spec spec;
@@ -1014,11 +1067,66 @@ void count_parts_impl(ottocov_ctx* ctx, int n_parts, const int32_t* const* sessi
     cudaEvent_t e0 = new_event();                       // the device blocks may still be in use by earlier work
     CUDA_CHECK(cudaEventRecord(e0, ctx->stream));
     CUDA_CHECK(cudaStreamWaitEvent(cs, e0, 0));
+    // ---- host threads run-length encode the session columns while the first copies are in flight ----------------------
+    // Tasks are row ranges of <= 4 M rows of one part, encoded independently (a run that continues across two ranges is
+    // simply two runs with the same id), handed to the threads in order so that the first groups are ready first.
+    static int rle_on = -1;
+    if (rle_on < 0) { const char* e = getenv("OTTOCOV_NO_SESSION_RLE"); rle_on = (e && atoi(e)) ? 0 : 1; }
+    constexpr int64_t RLE_TASK_ROWS = 4 << 20;
+    std::vector<std::unique_ptr<RleTask>> rle;
+    std::vector<int64_t> task_row0, task_slot;              // first row (global) and staging slot (in runs) of each task
+    std::vector<int> part_task0(n_parts + 1, 0);
+    int64_t slot = 0;
+    if (rle_on)
+        for (int p = 0; p < n_parts; ++p) {
+            part_task0[p] = (int)rle.size();
+            for (int64_t a = 0; a < rows[p]; a += RLE_TASK_ROWS) {
+                const int64_t m = imin64(RLE_TASK_ROWS, rows[p] - a);
+                rle.emplace_back(new RleTask());
+                rle.back()->session = session[p] + a; rle.back()->rows = m; rle.back()->cap = m / 8 + 16; rle.back()->n_runs = -1;
+                task_row0.push_back(off[p] + a);
+                task_slot.push_back(slot);
+                slot += m / 8 + 16;
+            }
+        }
+    part_task0[n_parts] = (int)rle.size();
+    const size_t stage_bytes = (size_t)slot * 8;
+    if (rle_on && stage_bytes > ctx->host_stage_bytes) {
+        if (ctx->host_stage) cudaFreeHost(ctx->host_stage);
+        ctx->host_stage = nullptr; ctx->host_stage_bytes = 0;
+        CUDA_CHECK(cudaHostAlloc(&ctx->host_stage, stage_bytes + stage_bytes / 8, cudaHostAllocDefault));
+        ctx->host_stage_bytes = stage_bytes + stage_bytes / 8;
+    }
+    DevBuf<u32> d_runs(ctx, rle_on ? (size_t)slot * 2 + 2 : 1);
+    std::atomic<int> next_task{0};
+    std::vector<std::thread> workers;
+    struct JoinWorkers {                                    // never leave with a thread still reading the caller's buffers
+        std::vector<std::thread>& w;
+        ~JoinWorkers() { for (auto& t : w) if (t.joinable()) t.join(); }
+    } join_workers{workers};
+    if (rle_on && !rle.empty()) {
+        const int n_tasks = (int)rle.size();
+        for (int k = 0; k < n_tasks; ++k) rle[k]->out = reinterpret_cast<u32*>(ctx->host_stage) + task_slot[k] * 2;
+        unsigned hw = std::thread::hardware_concurrency();
+        int n_thr = (int)(hw ? hw : 4);
+        if (n_thr > 32) n_thr = 32;
+        if (n_thr > n_tasks) n_thr = n_tasks;
+        for (int t = 0; t < n_thr; ++t)
+            workers.emplace_back([&, n_tasks]() {
+                for (;;) {
+                    const int k = next_task.fetch_add(1);
+                    if (k >= n_tasks) return;
+                    rle_encode(rle[k].get());
+                }
+            });
+    }
+    int64_t h2d = 0;
     ctx->begin(OTTOCOV_K_LOAD);
     for (int p = 0; p < n_parts; ++p)                   // aid and type of every part first: the key width is global
         if (rows[p]) {
             CUDA_CHECK(cudaMemcpyAsync(d_aid.p + off[p], aid[p], rows[p] * 4, cudaMemcpyHostToDevice, cs));
             CUDA_CHECK(cudaMemcpyAsync(d_type.p + off[p], type[p], rows[p], cudaMemcpyHostToDevice, cs));
+            h2d += rows[p] * 5;
         }
     cudaEvent_t e_aid = new_event();
     CUDA_CHECK(cudaEventRecord(e_aid, cs));
@@ -1026,13 +1134,32 @@ void count_parts_impl(ottocov_ctx* ctx, int n_parts, const int32_t* const* sessi
     for (int g = 0; g < n_groups; ++g) {
         for (int p = g_first[g]; p < g_first[g + 1]; ++p)
             if (rows[p]) {
-                CUDA_CHECK(cudaMemcpyAsync(d_session.p + off[p], session[p], rows[p] * 4, cudaMemcpyHostToDevice, cs));
                 CUDA_CHECK(cudaMemcpyAsync(d_ts.p + off[p], ts[p], rows[p] * 4, cudaMemcpyHostToDevice, cs));
+                h2d += rows[p] * 4;
+                for (int k = part_task0[p]; k < part_task0[p + 1]; ++k) {       // session column: runs where they compress
+                    while (!rle[k]->done.load(std::memory_order_acquire)) std::this_thread::yield();
+                    if (rle[k]->n_runs < 0) continue;
+                    CUDA_CHECK(cudaMemcpyAsync(d_runs.p + task_slot[k] * 2, rle[k]->out, (size_t)rle[k]->n_runs * 8,
+                                               cudaMemcpyHostToDevice, cs));
+                    h2d += rle[k]->n_runs * 8;
+                }
+                if (!rle_on) {
+                    CUDA_CHECK(cudaMemcpyAsync(d_session.p + off[p], session[p], rows[p] * 4, cudaMemcpyHostToDevice, cs));
+                    h2d += rows[p] * 4;
+                } else {
+                    for (int k = part_task0[p]; k < part_task0[p + 1]; ++k)
+                        if (rle[k]->n_runs < 0) {                               // this range does not compress: raw
+                            CUDA_CHECK(cudaMemcpyAsync(d_session.p + task_row0[k], rle[k]->session, rle[k]->rows * 4,
+                                                       cudaMemcpyHostToDevice, cs));
+                            h2d += rle[k]->rows * 4;
+                        }
+                }
             }
         e_grp[g] = new_event();
         CUDA_CHECK(cudaEventRecord(e_grp[g], cs));
     }
-    ctx->end(OTTOCOV_K_LOAD, 13.0 * N);
+    ctx->h2d_bytes_last = h2d;
+    ctx->end(OTTOCOV_K_LOAD, (double)h2d);
     ctx->stats[OTTOCOV_K_LOAD].launches -= 1;           // copies, not kernels
     // no exit path may return while a copy still reads the caller's host buffers, or leave the main stream ahead of them
     struct JoinCopies {
@@ -1068,6 +1195,12 @@ void count_parts_impl(ottocov_ctx* ctx, int n_parts, const int32_t* const* sessi
         g_rows[g] = r1 - r0;
         CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, e_grp[g], 0));
         if (r1 == r0) continue;
+        if (rle_on)
+            for (int k = part_task0[g_first[g]]; k < part_task0[g_first[g + 1]]; ++k)
+                if (rle[k]->n_runs > 0)
+                    COV_LAUNCH(ctx, OTTOCOV_K_LOAD, 4.0 * rle[k]->rows + 8.0 * rle[k]->n_runs, rle_expand_kernel,
+                               (unsigned)ceil_div64(rle[k]->n_runs, 256), 256, 0, d_runs.p + task_slot[k] * 2, rle[k]->n_runs,
+                               rle[k]->rows, d_session.p + task_row0[k]);
         load_events_impl(ctx, d_session.p + r0, d_aid.p + r0, d_ts.p + r0, d_type.p + r0, r1 - r0, OTTOCOV_DEVICE);
         const ottocov_events_info gi = ctx->info;
         total.n_rows_in += gi.n_rows_in; total.n_events += gi.n_events;
@@ -1164,6 +1297,7 @@ void count_parts_impl(ottocov_ctx* ctx, int n_parts, const int32_t* const* sessi
             ctx->last_count.sort_passes = passes;
             ctx->last_count.n_chunks = n_groups;
             ctx->last_count.fused = 1;
+            ctx->last_count.h2d_bytes = ctx->h2d_bytes_last;
             ctx->last_count.n_unique = tables_out[k]->n;
             for (u64*& b : a.bufs) { dev_free(ctx, b); b = nullptr; }
         }
@@ -1174,11 +1308,18 @@ void count_parts_impl(ottocov_ctx* ctx, int n_parts, const int32_t* const* sessi
             if (tables_out[k]) { dev_free(ctx, tables_out[k]->keys); dev_free(ctx, tables_out[k]->count); delete tables_out[k]; tables_out[k] = nullptr; }
         for (auto& a : acc) for (u64*& b : a.bufs) { dev_free(ctx, b); b = nullptr; }
         CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, e_grp[n_groups - 1], 0));
+        if (rle_on)                                     // (re-)materialise every run-length encoded session column
+            for (size_t k = 0; k < rle.size(); ++k)
+                if (rle[k]->n_runs > 0)
+                    COV_LAUNCH(ctx, OTTOCOV_K_LOAD, 4.0 * rle[k]->rows + 8.0 * rle[k]->n_runs, rle_expand_kernel,
+                               (unsigned)ceil_div64(rle[k]->n_runs, 256), 256, 0, d_runs.p + task_slot[k] * 2, rle[k]->n_runs,
+                               rle[k]->rows, d_session.p + task_row0[k]);
         load_events_impl(ctx, d_session.p, d_aid.p, d_ts.p, d_type.p, N, OTTOCOV_DEVICE);
         total = ctx->info;
         for (int k = 0; k < n_specs; ++k) tables_out[k] = count_impl(ctx, &specs[k]);
     }
     free_events(ctx);
+    ctx->last_count.h2d_bytes = ctx->h2d_bytes_last;
     ctx->info = total;
     ctx->info_only = true;
 }

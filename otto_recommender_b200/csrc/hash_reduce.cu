@@ -34,10 +34,22 @@
 #include "internal.cuh"
 #include "scan.cuh"
 
-constexpr int HR_THREADS = 512;
+// CTA shape.  Measured on the headline run (742 M keys): 512 threads / 8192 slots / 3 CTAs per SM 5.47 ms,
+// 256 threads / 4096 slots / 6 CTAs per SM 5.15 ms -- the same 48 warps per SM, but the CTA barriers (the largest stall
+// reason in ncu: profiles/r02_top_ncu_details.txt) wait for half as many warps.
+#ifndef OTTOCOV_HR_THREADS
+#define OTTOCOV_HR_THREADS 256
+#endif
+#ifndef OTTOCOV_HR_CAP_LOG2
+#define OTTOCOV_HR_CAP_LOG2 12
+#endif
+#ifndef OTTOCOV_HR_MINB
+#define OTTOCOV_HR_MINB 6
+#endif
+constexpr int HR_THREADS = OTTOCOV_HR_THREADS;
 constexpr int HR_IPT = 8;
-constexpr int HR_TILE = HR_THREADS * HR_IPT;     // 4096 keys per CTA (+ the tail of its last bucket)
-constexpr int HR_CAP_LOG2 = 13;
+constexpr int HR_TILE = HR_THREADS * HR_IPT;     // 2048 keys per CTA (+ the tail of its last bucket)
+constexpr int HR_CAP_LOG2 = OTTOCOV_HR_CAP_LOG2;
 constexpr int HR_CAP = 1 << HR_CAP_LOG2;         // 8192 slots
 constexpr int HR_SPT = HR_CAP / HR_THREADS;      // slots per thread in the table scan
 constexpr int HR_XT = 4;                         // keys per thread per slice of a long bucket tail
@@ -185,7 +197,7 @@ __device__ __forceinline__ void hr_clear(u64* s_key, u32* s_cnt) {
 }
 
 template <bool SYM, bool PACKED>
-__global__ void __launch_bounds__(HR_THREADS, PACKED ? 3 : 2)
+__global__ void __launch_bounds__(HR_THREADS, PACKED ? OTTOCOV_HR_MINB : 2)
 hash_reduce_kernel(const u64* __restrict__ keys, int64_t n, int rem_bits, KeyMix mix, u32 min_count, int mirror,
                    u64* __restrict__ out_keys, u32* __restrict__ out_count, unsigned long long* __restrict__ out_n,
                    u64 out_cap, u32* __restrict__ flags) {

@@ -92,6 +92,9 @@ struct ottocov_ctx {
     u32 scan_epoch = 0;
     u32* scan_ticket = nullptr;
     u64* scan_totals = nullptr;        // [8] grand totals of the last scan launch
+    void* host_stage = nullptr;        // page-locked staging for data the library prepares on the host (session runs)
+    size_t host_stage_bytes = 0;
+    int64_t h2d_bytes_last = 0;        // bytes the last ottocov_count_parts copied host -> device
     void* pinned = nullptr;            // 4 KB page-locked landing pad for small device -> host read-backs
     cudaStream_t copy_stream = nullptr;        // host -> device column copies overlapped with the loader (events.cu)
     std::vector<cudaEvent_t> sync_events;      // pool of timing-less events for cross-stream ordering

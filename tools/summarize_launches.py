@@ -20,7 +20,7 @@ for row in csv.DictReader(lines):
     a[1] += 1
     total += ms
     n += 1
-OURS = ("rs_", "scan_onepass", "expand_kernel", "hash_reduce", "rle_kernel", "ev_", "window", "tile_search", "topk",
+OURS = ("rs_", "scan_onepass", "expand_kernel", "expand_scatter", "region_table", "publish_", "mirror_push", "rle_expand", "aid_max", "feat_", "sum_hist", "stripe_off", "init_minmax", "pop_", "hash_reduce", "rle_kernel", "ev_", "window", "tile_search", "topk",
         "mix_", "unmix", "unpack", "order_keys", "table_stats", "pack_keys", "stamp", "strip", "unstamp")
 ours = sum(v[0] for k, v in agg.items() if any(o in k for o in OURS))
 print(f"# ncu launch list summary of: {title}")

@@ -9,7 +9,7 @@
 //   2. radix_sort.cu sorts on the top `bb` bits of the mixed key only (3 passes instead of 6 at the
 //      headline size) -- the keys are now grouped into 2^bb buckets of a few hundred keys each, and
 //      every copy of a key lies in one bucket;
-//   3. hash_reduce_kernel: a CTA owns the buckets that START inside its 4096-key tile (it skips the
+//   3. hash_reduce_kernel: a CTA owns the buckets that START inside its 2048-key tile (it skips the
 //      head of the tile that continues the previous CTA's bucket and reads past the tile end to finish
 //      its last bucket), counts their keys in a shared-memory open-addressing table of packed words
 //      tag(42) | count(22) -- one 64-bit CAS claims AND counts a new key, one 32-bit add counts a
@@ -50,7 +50,7 @@ constexpr int HR_THREADS = OTTOCOV_HR_THREADS;
 constexpr int HR_IPT = 8;
 constexpr int HR_TILE = HR_THREADS * HR_IPT;     // 2048 keys per CTA (+ the tail of its last bucket)
 constexpr int HR_CAP_LOG2 = OTTOCOV_HR_CAP_LOG2;
-constexpr int HR_CAP = 1 << HR_CAP_LOG2;         // 8192 slots
+constexpr int HR_CAP = 1 << HR_CAP_LOG2;         // 4096 slots
 constexpr int HR_SPT = HR_CAP / HR_THREADS;      // slots per thread in the table scan
 constexpr int HR_XT = 4;                         // keys per thread per slice of a long bucket tail
 constexpr int HR_MAX_TAIL_ROUNDS = 1000;         // ~2 M keys: beyond that one CTA would serialise the reduce
@@ -66,8 +66,8 @@ constexpr u64 HR_CMASK = (1ull << HR_CB) - 1ull;
 static_assert(2 * HR_SPT <= 32, "two flag bits per scanned slot must fit one register");
 static_assert((u64)HR_TILE + ((u64)HR_MAX_TAIL_ROUNDS * HR_XT + 1) * HR_THREADS < HR_CMASK, "count field too narrow");
 
-// PACKED: s_key[slot] = tag << 22 | count (64 KB, 3 CTAs / SM).  Otherwise (keys too wide for a 42-bit tag):
-// s_key[slot] = mixed key, s_cnt[slot] = count (96 KB, 2 CTAs / SM, two atomics for a new key).
+// PACKED: s_key[slot] = tag << 22 | count (32 KB, 6 CTAs / SM).  Otherwise (keys too wide for a 42-bit tag):
+// s_key[slot] = mixed key, s_cnt[slot] = count (48 KB, 2+ CTAs / SM, two atomics for a new key).
 template <bool PACKED>
 __device__ __forceinline__ void hr_insert(u64* s_key, u32* s_cnt, u64 h, u64 base, u32 times, u32* flags) {
     const u64 tag = h - base;

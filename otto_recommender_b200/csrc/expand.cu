@@ -224,10 +224,20 @@ __device__ __forceinline__ u32 stage_tile_records(const u32* __restrict__ rec_sr
 
 // Thread t produces the EX_PER consecutive outputs [EX_PER t, EX_PER t + EX_PER) of the tile: one binary search
 // for the first, a linear walk over the record offsets for the rest.  Only outputs k < n_out are defined.
-template <bool SELF, bool CANON, bool MIX>
+// MODE: how a record (its owner event) and the events of its range make a key
+//   EXM_CROSS  owner = source event, range = target events of another type:  key (owner aid, range aid)
+//   EXM_SELF   the same with source type == target type: the owner itself lies inside its range and is skipped
+//   EXM_CANON  symmetric kind, each unordered event pair once:                key (min aid, max aid)
+//   EXM_SWAP   owner = TARGET event, range = source events (taken when the target type is much rarer than the source
+//              type -- carts and orders against clicks -- so the window pass walks the few, not the many):
+//                                                                             key (range aid, owner aid)
+enum { EXM_CROSS = 0, EXM_SELF = 1, EXM_CANON = 2, EXM_SWAP = 3 };
+
+template <int MODE, bool MIX>
 __device__ __forceinline__ void make_tile_keys(const u32* s_off, const u32* s_lo, const u32* s_aid, const u32* s_src,
                                                u32 n_rec, u32 n_out, const u32* __restrict__ aid_tgt, u32 n_dest,
                                                const KeyMix& mix, u64 (&key)[EX_PER]) {
+    constexpr bool SELF = MODE == EXM_SELF, CANON = MODE == EXM_CANON, SWAP = MODE == EXM_SWAP;
     const u32 k0 = (u32)EX_PER * threadIdx.x;
     if (k0 >= n_out) return;
     u32 lo = 0, hi = n_rec;                       // last record with s_off <= k0
@@ -253,7 +263,8 @@ __device__ __forceinline__ void make_tile_keys(const u32* s_off, const u32* s_lo
             }
             u32 tgt = tb + k;
             if (SELF) tgt += (tgt >= src);
-            key[q] = make_pair_key<CANON, MIX>(a, aid_tgt[tgt], n_dest, mix);
+            const u32 other = aid_tgt[tgt];
+            key[q] = SWAP ? make_pair_key<false, MIX>(other, a, n_dest, mix) : make_pair_key<CANON, MIX>(a, other, n_dest, mix);
         }
     }
 }
@@ -264,13 +275,14 @@ __device__ __forceinline__ void make_tile_keys(const u32* s_off, const u32* s_lo
 // ghist != nullptr: the digit histograms of the distribution passes that will sort these keys (pl) are
 // accumulated here, in shared memory while the keys are still in registers, and flushed once per CTA -- the
 // sort's own histogram kernel (one more read of every key) is not needed.
-template <bool SELF, bool CANON, bool MIX>
+template <int MODE, bool MIX>
 __global__ void __launch_bounds__(EX_THREADS)
 expand_kernel(const u32* __restrict__ rec_src, const u32* __restrict__ rec_lo,
               const u64* __restrict__ rec_off, const u32* __restrict__ tile_rec,
               const u32* __restrict__ aid_src, const u32* __restrict__ aid_tgt, u64 out_begin,
               u64 out_end, u64* __restrict__ dst, u32 n_dest, KeyMix mix, int64_t n_tiles, PassList pl,
               u64* __restrict__ ghist) {
+    constexpr bool SELF = MODE == EXM_SELF;
     __shared__ __align__(16) u32 s_buf[3 * EX_PITCH];
     __shared__ u32 s_src[SELF ? EX_TILE + 1 : 1];
     extern __shared__ u32 s_hist[];                   // [pl.n][RS_RADIX] when ghist
@@ -289,7 +301,7 @@ expand_kernel(const u32* __restrict__ rec_src, const u32* __restrict__ rec_lo,
                                                    s_off, s_lo, s_aid, s_src, &n_out);
         u64 key[EX_PER];
         const u32 k0 = (u32)EX_PER * threadIdx.x;
-        make_tile_keys<SELF, CANON, MIX>(s_off, s_lo, s_aid, s_src, n_rec, n_out, aid_tgt, n_dest, mix, key);
+        make_tile_keys<MODE, MIX>(s_off, s_lo, s_aid, s_src, n_rec, n_out, aid_tgt, n_dest, mix, key);
         if (hist && k0 < n_out) {
             for (int p = 0; p < pl.n; ++p) {              // pass parameters are read once per pass, not per key
                 const int sh = pl.shift[p];
@@ -363,12 +375,13 @@ struct ScatterArgs {
     u32 n_dest;
 };
 
-template <bool SELF, bool CANON, bool DIST>
+template <int MODE, bool DIST>
 __global__ void __launch_bounds__(EX_THREADS, OTTOCOV_EXS_MINB)
 expand_scatter_kernel(const u32* __restrict__ rec_src, const u32* __restrict__ rec_lo,
                       const u64* __restrict__ rec_off, const u32* __restrict__ tile_rec,
                       const u32* __restrict__ aid_src, const u32* __restrict__ aid_tgt, u64 out_begin,
                       u64 out_end, KeyMix mix, int64_t n_tiles, PassList pl, u64* __restrict__ ghist, ScatterArgs sa) {
+    constexpr bool SELF = MODE == EXM_SELF;
     __shared__ __align__(16) u32 s_buf[3 * EX_PITCH];
     __shared__ u32 s_src[SELF ? EX_TILE + 1 : 1];
     __shared__ u32 s_cnt[RS_RADIX];                   // keys of the tile per digit, then their first staging slot
@@ -395,8 +408,8 @@ expand_scatter_kernel(const u32* __restrict__ rec_src, const u32* __restrict__ r
         u64 key[EX_PER];
         const u32 k0 = (u32)EX_PER * tid;
         // DIST: plain keys first -- the owner rank is a function of the plain aid -- mixed right below
-        if (DIST) make_tile_keys<SELF, CANON, false>(s_off, s_lo, s_aid, s_src, n_rec, n_out, aid_tgt, 0u, mix, key);
-        else make_tile_keys<SELF, CANON, true>(s_off, s_lo, s_aid, s_src, n_rec, n_out, aid_tgt, 0u, mix, key);
+        if (DIST) make_tile_keys<MODE, false>(s_off, s_lo, s_aid, s_src, n_rec, n_out, aid_tgt, 0u, mix, key);
+        else make_tile_keys<MODE, true>(s_off, s_lo, s_aid, s_src, n_rec, n_out, aid_tgt, 0u, mix, key);
         u32 dig[(EX_PER + 3) / 4];                    // digits, 8 bits each
         u32 rnk[EX_PER / 2];                          // ranks inside (tile, digit), 16 bits each
 #pragma unroll
@@ -494,8 +507,10 @@ expand_scatter_kernel(const u32* __restrict__ rec_src, const u32* __restrict__ r
 }
 
 struct Segment {
-    int tgt_type;
+    int tgt_type;            // type of the events in a record's range
+    int own_type;            // type of the record owners (the kind's source type, or its target type when swapped)
     bool self;
+    bool swap = false;       // EXM_SWAP: owners are the kind's TARGET events
     u64 n_pairs = 0;
     u64 n_rec = 0;
     DevBuf<u32> rec_src, rec_lo;
@@ -561,27 +576,37 @@ static ExpandPlan* make_plan(ottocov_ctx* ctx, const ottocov_spec* spec, bool di
             if (src.n == 0 || tgt.n == 0) continue;
             Segment* sg = new Segment();
             pl->segs.push_back(sg);
-            sg->tgt_type = B;
             const bool self_in = (pl->A == B) && pl->dt_lo <= 0 && pl->dt_hi >= 0;
             sg->self = pl->general ? self_in : (pl->A == B);
+            // walk the rarer side: carts / orders are ~10x / ~40x rarer than clicks, so for click -> cart-or-buy the
+            // window pass runs over the target events and looks for their sources
+            sg->swap = (pl->A != B) && !pl->sym && tgt.n * 2 < src.n;
+            const TypeArray& own = sg->swap ? tgt : src;                 // record owners
+            const TypeArray& rng = sg->swap ? src : tgt;                 // events of their ranges
+            sg->own_type = sg->swap ? B : pl->A;
+            sg->tgt_type = sg->swap ? pl->A : B;
+            const int ot = sg->own_type, rt = sg->tgt_type;
             const u32* xr = nullptr;
-            if (!sg->self) xr = (B == (pl->A + 1) % 3) ? src.xrank[0] : src.xrank[1];
-            DevBuf<u32> lo(ctx, src.n), cnt(ctx, src.n);
+            if (!sg->self) xr = (rt == (ot + 1) % 3) ? own.xrank[0] : own.xrank[1];
+            // owner at t, range event at t': the kind asks dt_lo <= t_tgt - t_src <= dt_hi; seen from a target owner the
+            // range is -dt_hi <= t_src - t_tgt <= -dt_lo
+            const int64_t r_lo = sg->swap ? -pl->dt_hi : pl->dt_lo, r_hi = sg->swap ? -pl->dt_lo : pl->dt_hi;
+            DevBuf<u32> lo(ctx, own.n), cnt(ctx, own.n);
             if (pl->general)
-                COV_LAUNCH(ctx, OTTOCOV_K_WINDOW, 20.0 * src.n, window_range_kernel, (unsigned)ceil_div64(src.n, 256), 256, 0,
-                           src.skey, src.n, tgt.skey, (u32)tgt.n, pl->dt_lo, pl->dt_hi, self_in ? 1 : 0, lo.p, cnt.p);
+                COV_LAUNCH(ctx, OTTOCOV_K_WINDOW, 20.0 * own.n, window_range_kernel, (unsigned)ceil_div64(own.n, 256), 256, 0,
+                           own.skey, own.n, rng.skey, (u32)rng.n, r_lo, r_hi, self_in ? 1 : 0, lo.p, cnt.p);
             else if (pl->sym)
-                COV_LAUNCH(ctx, OTTOCOV_K_WINDOW, 16.0 * src.n, window_fwd_kernel, (unsigned)ceil_div64(src.n, 256), 256, 0,
-                           src.skey, src.n, pl->W, lo.p, cnt.p);
+                COV_LAUNCH(ctx, OTTOCOV_K_WINDOW, 16.0 * own.n, window_fwd_kernel, (unsigned)ceil_div64(own.n, 256), 256, 0,
+                           own.skey, own.n, pl->W, lo.p, cnt.p);
             else
-                COV_LAUNCH(ctx, OTTOCOV_K_WINDOW, 20.0 * src.n, window_kernel, (unsigned)ceil_div64(src.n, 256), 256, 0,
-                           src.skey, xr, src.n, tgt.skey, (u32)tgt.n, pl->W, lo.p, cnt.p);
-            sg->rec_src.alloc(ctx, src.n); sg->rec_lo.alloc(ctx, src.n); sg->rec_off.alloc(ctx, src.n);
+                COV_LAUNCH(ctx, OTTOCOV_K_WINDOW, 20.0 * own.n, window_kernel, (unsigned)ceil_div64(own.n, 256), 256, 0,
+                           own.skey, xr, own.n, rng.skey, (u32)rng.n, pl->W, lo.p, cnt.p);
+            sg->rec_src.alloc(ctx, own.n); sg->rec_lo.alloc(ctx, own.n); sg->rec_off.alloc(ctx, own.n);
             WindowRecords f;
             f.lo = lo.p; f.cnt = cnt.p;
             f.rec_src = sg->rec_src.p; f.rec_lo = sg->rec_lo.p; f.rec_off = sg->rec_off.p;
             u64 tot[2];
-            scan_apply(ctx, OTTOCOV_K_WINDOW, f, src.n, tot, 2.0 * 4.0 * src.n + 8.0 * src.n + 16.0 * src.n);
+            scan_apply(ctx, OTTOCOV_K_WINDOW, f, own.n, tot, 2.0 * 4.0 * own.n + 8.0 * own.n + 16.0 * own.n);
             sg->n_pairs = tot[0];
             sg->n_rec = tot[1];
             pl->P += tot[0];
@@ -600,7 +625,6 @@ static ExpandPlan* make_plan(ottocov_ctx* ctx, const ottocov_spec* spec, bool di
 // of those distribution passes over the emitted keys.
 static void expand_range(ottocov_ctx* ctx, const ExpandPlan* pl, u64 c0, u64 c1, u64* dst_base, u32 n_dest,
                          const KeyMix* mix = nullptr, const PassList* hist_passes = nullptr, u64* ghist = nullptr) {
-    const TypeArray& src = ctx->ta[pl->A];
     const KeyMix mx = mix ? *mix : KeyMix();
     PassList hp;
     hp.n = 0;
@@ -617,22 +641,25 @@ static void expand_range(ottocov_ctx* ctx, const ExpandPlan* pl, u64 c0, u64 c1,
             DevBuf<u32> tile_rec(ctx, n_tiles + 1);
             COV_LAUNCH(ctx, OTTOCOV_K_EXPAND, 0, tile_search_kernel, (unsigned)ceil_div64(n_tiles + 1, 256), 256, 0,
                        sg->rec_off.p, (int64_t)sg->n_rec, ob, oe, n_tiles, tile_rec.p);
+            const TypeArray& own = ctx->ta[sg->own_type];
             const TypeArray& tgt = ctx->ta[sg->tgt_type];
             u64* dst = dst_base + (a - c0);
             const double bytes = 8.0 * (double)(oe - ob);
             const unsigned grid = (unsigned)imin64(n_tiles, (int64_t)ctx->num_sms * 5);     // 5 CTAs / SM at 48 registers
-#define EX_LAUNCH(SELF_, CANON_, MIX_)                                                                              \
-            COV_LAUNCH(ctx, OTTOCOV_K_EXPAND, bytes, (expand_kernel<SELF_, CANON_, MIX_>), grid, EX_THREADS, hist_smem,  \
-                       sg->rec_src.p, sg->rec_lo.p, sg->rec_off.p, tile_rec.p, src.aid, tgt.aid, ob, oe, dst, n_dest, mx, \
+#define EX_LAUNCH(MODE_, MIX_)                                                                                      \
+            COV_LAUNCH(ctx, OTTOCOV_K_EXPAND, bytes, (expand_kernel<MODE_, MIX_>), grid, EX_THREADS, hist_smem,          \
+                       sg->rec_src.p, sg->rec_lo.p, sg->rec_off.p, tile_rec.p, own.aid, tgt.aid, ob, oe, dst, n_dest, mx, \
                        n_tiles, hp, ghist)
             if (mix) {
-                if (pl->sym) EX_LAUNCH(false, true, true);
-                else if (sg->self) EX_LAUNCH(true, false, true);
-                else EX_LAUNCH(false, false, true);
+                if (pl->sym) EX_LAUNCH(EXM_CANON, true);
+                else if (sg->self) EX_LAUNCH(EXM_SELF, true);
+                else if (sg->swap) EX_LAUNCH(EXM_SWAP, true);
+                else EX_LAUNCH(EXM_CROSS, true);
             } else {
-                if (pl->sym) EX_LAUNCH(false, true, false);
-                else if (sg->self) EX_LAUNCH(true, false, false);
-                else EX_LAUNCH(false, false, false);
+                if (pl->sym) EX_LAUNCH(EXM_CANON, false);
+                else if (sg->self) EX_LAUNCH(EXM_SELF, false);
+                else if (sg->swap) EX_LAUNCH(EXM_SWAP, false);
+                else EX_LAUNCH(EXM_CROSS, false);
             }
 #undef EX_LAUNCH
         }
@@ -644,7 +671,6 @@ static void expand_range(ottocov_ctx* ctx, const ExpandPlan* pl, u64 c0, u64 c1,
 // ghist: device [n_dest][rest.n][RS_RADIX], zeroed by the caller.
 static void expand_scatter_all(ottocov_ctx* ctx, const ExpandPlan* pl, const KeyMix& mix, const PassList& rest, u64* ghist,
                                const ScatterArgs& sa) {
-    const TypeArray& src = ctx->ta[pl->A];
     const u32 nd = sa.n_dest > 1 ? sa.n_dest : 1u;
     const size_t hist_smem = (size_t)nd * rest.n * RS_RADIX * sizeof(u32);
     for (Segment* sg : pl->segs) {
@@ -653,21 +679,23 @@ static void expand_scatter_all(ottocov_ctx* ctx, const ExpandPlan* pl, const Key
         DevBuf<u32> tile_rec(ctx, n_tiles + 1);
         COV_LAUNCH(ctx, OTTOCOV_K_EXPAND, 0, tile_search_kernel, (unsigned)ceil_div64(n_tiles + 1, 256), 256, 0,
                    sg->rec_off.p, (int64_t)sg->n_rec, (u64)0, (u64)sg->n_pairs, n_tiles, tile_rec.p);
+        const TypeArray& own = ctx->ta[sg->own_type];
         const TypeArray& tgt = ctx->ta[sg->tgt_type];
         const double bytes = 8.0 * (double)sg->n_pairs;
-#define EXS_LAUNCH(SELF_, CANON_)                                                                                       \
+#define EXS_LAUNCH(MODE_)                                                                                       \
         do {                                                                                                            \
-            auto kern = sa.n_dest > 1 ? expand_scatter_kernel<SELF_, CANON_, true> : expand_scatter_kernel<SELF_, CANON_, false>; \
+            auto kern = sa.n_dest > 1 ? expand_scatter_kernel<MODE_, true> : expand_scatter_kernel<MODE_, false>;       \
             if (hist_smem > 8192) cov_func_smem(ctx, (const void*)kern, hist_smem);                                     \
             int per_sm = 0;                                                                                             \
             CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, EX_THREADS, hist_smem));            \
             const unsigned grid = (unsigned)imin64(n_tiles, (int64_t)ctx->num_sms * (per_sm > 0 ? per_sm : 1));          \
             COV_LAUNCH(ctx, OTTOCOV_K_EXPAND, bytes, kern, grid, EX_THREADS, hist_smem, sg->rec_src.p, sg->rec_lo.p,    \
-                       sg->rec_off.p, tile_rec.p, src.aid, tgt.aid, (u64)0, (u64)sg->n_pairs, mix, n_tiles, rest, ghist, sa); \
+                       sg->rec_off.p, tile_rec.p, own.aid, tgt.aid, (u64)0, (u64)sg->n_pairs, mix, n_tiles, rest, ghist, sa); \
         } while (0)
-        if (pl->sym) EXS_LAUNCH(false, true);
-        else if (sg->self) EXS_LAUNCH(true, false);
-        else EXS_LAUNCH(false, false);
+        if (pl->sym) EXS_LAUNCH(EXM_CANON);
+        else if (sg->self) EXS_LAUNCH(EXM_SELF);
+        else if (sg->swap) EXS_LAUNCH(EXM_SWAP);
+        else EXS_LAUNCH(EXM_CROSS);
 #undef EXS_LAUNCH
     }
 }

@@ -227,7 +227,28 @@ struct RsSegs {
     const u32* tile_start;     // [n_segs + 1] first tile of each segment (tiles never straddle segments)
     const u64* in_off;         // [n_segs] offset of the segment in keys_in
     const u64* cnt;            // [n_segs] keys in the segment
+    const u64* tile_in;        // [launch grid] per tile: offset of its first key in keys_in ...
+    const u32* tile_n;         // [launch grid] ... and its key count (0 for tickets beyond the last tile)
 };
+
+// Per-tile table of a segmented launch (one thread per ticket of the launch grid): the pass kernel then needs one
+// load per tile instead of a search over the segment table on its critical path.
+__global__ void __launch_bounds__(256) rs_seg_tiles_kernel(const RsSegs* __restrict__ segs, u32 tile_keys, u32 grid_tiles,
+                                                           u64* __restrict__ tile_in, u32* __restrict__ tile_n) {
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= grid_tiles) return;
+    if (t >= segs->total_tiles) { tile_in[t] = 0; tile_n[t] = 0; return; }
+    const u32* ts = segs->tile_start;
+    u32 lo = 0, hi = segs->n_segs;                 // last segment whose first tile is <= t
+    while (hi - lo > 1) {
+        const u32 mid = (lo + hi) >> 1;
+        if (ts[mid] <= t) lo = mid; else hi = mid;
+    }
+    const u64 within = (u64)(t - ts[lo]) * tile_keys;
+    const u64 left = segs->cnt[lo] - within;
+    tile_in[t] = segs->in_off[lo] + within;
+    tile_n[t] = (u32)(left < tile_keys ? left : tile_keys);
+}
 
 // One block.  Segment s = b * n_a + a (b-major: b is the digit the keys were partitioned on, a the writer
 // that filled the region) lives at slot a * n_b + b: key offset off_src[slot], count cnt_src[slot].
@@ -269,6 +290,11 @@ __global__ void __launch_bounds__(256) rs_seg_build_kernel(const u64* __restrict
         hdr->in_off = in_off;
         hdr->cnt = cnt;
     }
+}
+
+__global__ void rs_seg_attach_kernel(RsSegs* hdr, const u64* tile_in, const u32* tile_n) {
+    hdr->tile_in = tile_in;
+    hdr->tile_n = tile_n;
 }
 
 #ifndef OTTOCOV_RS_MINB
@@ -316,24 +342,8 @@ rs_onesweep_kernel(const u64* __restrict__ keys_in, u64* __restrict__ keys_out,
         u64 in_base = (u64)t * RS_TILE;
         int64_t left = n - (int64_t)in_base;
         if (segs) {
-            if (t >= segs->total_tiles) left = 0;
-            else {
-                // last segment whose first tile is <= t (empty segments share their successor's first tile)
-                const u32* ts = segs->tile_start;
-                u32 lo = 0, hi = segs->n_segs;
-                while (hi - lo > 1) {
-                    const u32 step = (hi - lo + 31) / 32;
-                    const u32 idx = lo + lane * step;
-                    const u32 v = idx < hi ? ts[idx] : 0xFFFFFFFFu;
-                    const u32 m = __ballot_sync(0xffffffffu, v <= t);
-                    const u32 j = 31 - __clz(m);
-                    lo += j * step;
-                    hi = min(hi, lo + step);
-                }
-                const u64 within = (u64)(t - ts[lo]) * RS_TILE;
-                in_base = segs->in_off[lo] + within;
-                left = (int64_t)(segs->cnt[lo] - within);
-            }
+            in_base = segs->tile_in[t];
+            left = (int64_t)segs->tile_n[t];
         }
         if (lane == 0) {
             s_tile[0] = t;
@@ -563,7 +573,7 @@ int radix_sort_passes(ottocov_ctx* ctx, u64*& keys, u64*& alt, u32*& vals, u32*&
     ensure_sweep_state(ctx, (size_t)(n_tiles_first > n_tiles ? n_tiles_first : n_tiles) * RS_RADIX);
     CUDA_CHECK(cudaMemsetAsync(ctx->sweep_ticket, 0, RS_MAX_PASSES * sizeof(u32), ctx->stream));
 
-    DevBuf<unsigned char> segbuf;
+    DevBuf<unsigned char> segbuf, seg_tiles;
     const RsSegs* segs = nullptr;
     if (seg_cnt) {
         const size_t o_ts = 64, o_in = o_ts + (((size_t)n_segs + 1) * 4 + 7) / 8 * 8, o_cn = o_in + (size_t)n_segs * 8;
@@ -572,6 +582,13 @@ int radix_sort_passes(ottocov_ctx* ctx, u64*& keys, u64*& alt, u32*& vals, u32*&
                    reinterpret_cast<RsSegs*>(segbuf.p), reinterpret_cast<u32*>(segbuf.p + o_ts),
                    reinterpret_cast<u64*>(segbuf.p + o_in), reinterpret_cast<u64*>(segbuf.p + o_cn));
         segs = reinterpret_cast<const RsSegs*>(segbuf.p);
+        seg_tiles.alloc(ctx, (size_t)n_tiles_first * 12 + 16);
+        u64* t_in = reinterpret_cast<u64*>(seg_tiles.p);
+        u32* t_n = reinterpret_cast<u32*>(seg_tiles.p + (size_t)n_tiles_first * 8);
+        COV_LAUNCH(ctx, OTTOCOV_K_MISC, 0, rs_seg_tiles_kernel, (unsigned)ceil_div64(n_tiles_first, 256), 256, 0, segs, (u32)tile,
+                   (u32)n_tiles_first, t_in, t_n);
+        COV_LAUNCH(ctx, OTTOCOV_K_MISC, 0, rs_seg_attach_kernel, 1, 1, 0, reinterpret_cast<RsSegs*>(segbuf.p), (const u64*)t_in,
+                   (const u32*)t_n);
     }
     for (int p = 0; p < pl.n; ++p) {
         const bool first_seg = (p == 0 && segs);

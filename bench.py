@@ -417,7 +417,7 @@ def run_ours(args):
     # ---- e2e: host (pinned) columns in, results back on the host, through the public API ------------
     host_cols = [c.cpu().pin_memory() for c in cols]
 
-    host_parts = Engine.split_at_sessions(*host_cols, 12) if world == 1 else None
+    host_parts = Engine.split_at_sessions(*host_cols, 64) if world == 1 else None
 
     def step_e2e():
         if world == 1 and not args.no_streamed_e2e:

@@ -1060,15 +1060,19 @@ void count_parts_impl(ottocov_ctx* ctx, int n_parts, const int32_t* const* sessi
         ctx->info = total; ctx->info.session_min = ctx->info.session_max = ctx->info.ts_min = ctx->info.ts_max = 0;
         return;
     }
-    // ---- groups of consecutive parts, ~equal rows: big enough to amortise the per-group host round trips, small
-    //      enough that the work on a group hides behind the copy of the next one
-    int n_groups = n_parts < 10 ? n_parts : 10;
+    // ---- groups of consecutive parts: big enough to amortise the per-group host round trips, small enough that the
+    //      work on a group hides behind the copy of the next one -- and SHRINKING towards the end, because the work on
+    //      the last group is the one part of the per-group work that nothing hides (cumulative row shares below)
+    static const double kShare[] = {0.10, 0.20, 0.30, 0.40, 0.50, 0.60, 0.70, 0.80, 0.88, 0.94, 0.975, 1.0};
+    const int max_groups = (int)(sizeof(kShare) / sizeof(kShare[0]));
+    int n_groups = n_parts < max_groups ? n_parts : max_groups;
     std::vector<int> g_first(n_groups + 1, 0);
     {
         int64_t acc = 0; int g = 1;
         for (int p = 0; p < n_parts && g < n_groups; ++p) {
             acc += rows[p];
-            if (acc * n_groups >= N * g) { g_first[g++] = p + 1; }
+            const double share = n_parts < max_groups ? (double)g / n_groups : kShare[g - 1];
+            if ((double)acc >= share * (double)N) { g_first[g++] = p + 1; }
         }
         for (; g <= n_groups; ++g) g_first[g] = n_parts;
         g_first[n_groups] = n_parts;

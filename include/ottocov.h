@@ -283,7 +283,8 @@ int ottocov_table_mirror(ottocov_ctx* ctx, const ottocov_table* t, int transpose
  *   ottocov_reduce_received after the ranks synchronised: reads the published status; *need_cap > 0 (and no table)
  *                           when some rank overflowed a stripe -- every rank sees the same value, grows the plan
  *                           and repeats -- else the remaining passes + hash reduce over this rank's stripes.
- *                           symmetric: keys are canonical half pairs; the table then holds rows a <= b only.
+ *                           symmetric: keys are canonical half pairs; the table then holds rows a <= b only, in NO
+ *                           particular order: it is the input of ottocov_mirror_push / _collect (which sorts).
  *   ottocov_mirror_push     half table -> its transposed off-diagonal rows (b, a, c) stored into the stripes of
  *                           their owners hash(b) (+ status as above); ottocov_mirror_collect merges what this rank
  *                           received with its own half rows into the full sorted table (*need_rows > 0: grow). */

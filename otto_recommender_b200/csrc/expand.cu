@@ -26,9 +26,6 @@
 #include <thread>
 #include <memory>
 
-#ifndef OTTOCOV_EXS_ABLATE
-#define OTTOCOV_EXS_ABLATE 0      // timing experiments on expand_scatter_kernel (results are WRONG when non-zero):
-#endif                            // 1 no pass histograms, 2 no global stores, 3 no shared-memory ranking atomics
 #ifndef OTTOCOV_EXS_MINB
 #define OTTOCOV_EXS_MINB 6        // 40 registers without spills; measured 5.84 (4 CTAs/SM) -> 5.40 (5) -> 5.27 ms (6) on 742 M keys
 #endif
@@ -430,17 +427,13 @@ expand_scatter_kernel(const u32* __restrict__ rec_src, const u32* __restrict__ r
                     const u32 d = (dest << sa.sub_bits) | ((u32)(key[q] >> sa.sh1) & sub_mask);
                     if (d >= sa.d_lo && d < sa.d_hi) {
                         keep |= 1u << q;
-#if OTTOCOV_EXS_ABLATE == 3
-                        const u32 r = (k0 + q) & 15u; if (q == 0) atomicAdd(&s_cnt[d], 8u);
-#else
                         const u32 r = atomicAdd(&s_cnt[d], 1u);
-#endif
                         dig[q >> 2] |= d << (8 * (q & 3));
                         rnk[q >> 1] |= r << (16 * (q & 1));
                     }
                 }
             }
-            for (int p = 0; p < (OTTOCOV_EXS_ABLATE == 1 ? 0 : pl.n); ++p) {   // histograms of the remaining passes, kept keys only
+            for (int p = 0; p < pl.n; ++p) {              // histograms of the remaining passes, kept keys only
                 const int sh = pl.shift[p];
                 const u32 msk = (1u << pl.bits[p]) - 1u;
 #pragma unroll
@@ -493,7 +486,7 @@ expand_scatter_kernel(const u32* __restrict__ rec_src, const u32* __restrict__ r
                 const u64 k = s_out[j];
                 const u32 d = DIST ? (u32)s_dig[j] : ((u32)(k >> sa.sh1) & sub_mask);
                 const u64 gp = s_gptr[d];
-                if (gp && OTTOCOV_EXS_ABLATE != 2) __stcs(reinterpret_cast<u64*>(gp + 8ull * j), k);
+                if (gp) __stcs(reinterpret_cast<u64*>(gp + 8ull * j), k);
             }
         }
         __syncthreads();                                  // s_buf is re-staged by the next tile
@@ -1511,6 +1504,7 @@ ottocov_table* reduce_received_impl(ottocov_ctx* ctx, const ottocov_xplan* plan,
     pre.bb = plan->bucket_bits; pre.first_bits = plan->sub_bits;
     pre.seg_cnt = reinterpret_cast<const u64*>(recv_area + plan->off_counts); pre.seg_off = seg_off.p;
     pre.n_a = R; pre.n_b = n_sub; pre.ctr = nullptr;
+    pre.skip_sort = sym != 0;          // a symmetric kind's half table goes through ottocov_mirror_collect, which sorts
     int passes = 0;
     out = hashed_reduce(ctx, reinterpret_cast<u64*>(recv_area + plan->off_keys), alt.p, n, mix, min_count > 1 ? min_count : 1,
                         sym != 0, false, &passes, ghist.p, &pre);

@@ -413,6 +413,14 @@ ottocov_table* hashed_reduce(ottocov_ctx* ctx, u64* keys, u64* alt, int64_t n, c
         ctx->stats[OTTOCOV_K_RLE].algo_bytes += 12.0 * (double)rows;
         if (rows == 0) return out;
 
+        if (pre && pre->skip_sort) {     // e.g. a half table on its way into ottocov_mirror_collect, which sorts the union
+            DevBuf<u64> tk(ctx, rows);
+            DevBuf<u32> tc(ctx, rows);
+            CUDA_CHECK(cudaMemcpyAsync(tk.p, ok.p, rows * sizeof(u64), cudaMemcpyDeviceToDevice, ctx->stream));
+            CUDA_CHECK(cudaMemcpyAsync(tc.p, oc.p, rows * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->stream));
+            out->keys = tk.take(); out->count = tc.take(); out->n = rows;
+            return out;
+        }
         // ---- the survivors arrive in bucket order: sort them by plain key -----------------------------------
         DevBuf<u64> ok2(ctx, rows);
         DevBuf<u32> oc2(ctx, rows);

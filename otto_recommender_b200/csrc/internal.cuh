@@ -324,6 +324,7 @@ struct HashPre {
     const u64* seg_off;      // [n_a * n_b] key offset of each region inside `keys` (device)
     int n_a, n_b;
     unsigned long long* ctr;
+    bool skip_sort = false;  // leave the surviving rows in bucket order (the caller sorts them later anyway)
 };
 ottocov_table* hashed_reduce(ottocov_ctx* ctx, u64* keys, u64* alt, int64_t n, const KeyMix& mix, u32 min_count,
                              bool sym, bool mirror, int* passes_out, u64* pre_hist = nullptr, const HashPre* pre = nullptr);

@@ -232,10 +232,10 @@ class ScatterExchange:
     identically (the status words each source publishes to ALL ranks), so the ranks never diverge and a step needs
     no NCCL call; the only collective outside the first step of a kind is re-allocating a larger receive area."""
 
-    def __init__(self, engine, group=None):
+    def __init__(self, engine, group=None, device=None):
         self.engine, self.group = engine, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        self.dev = torch.device("cuda", engine.device)
+        self.dev = device if device is not None else torch.device("cuda", engine.device)
         self.plans = {}              # name -> (plan, total_keys it was made for)
         self.capacity = 0
         self.regrows = 0
@@ -243,12 +243,20 @@ class ScatterExchange:
     def _ensure(self, nbytes: int):
         if nbytes <= self.capacity:
             return
-        import torch.distributed._symmetric_memory as symm_mem
         self.capacity = int(nbytes * 1.1) + (1 << 20)           # the same arithmetic on every rank
-        self.buf = symm_mem.empty(self.capacity, dtype=torch.uint8, device=self.dev)
+        self._alloc(self.capacity)
+
+    def _alloc(self, nbytes: int):
+        """Receive area of `nbytes` on every rank, each mapped into every other rank (collective).  Sets peer_ptrs."""
+        import torch.distributed._symmetric_memory as symm_mem
+        self.buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=self.dev)
         gname = self.group.group_name if self.group is not None else dist.group.WORLD.group_name
         self.handle = symm_mem.rendezvous(self.buf, gname)
         self.peer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
+
+    def _barrier(self, channel: int):
+        """Stream-ordered barrier over the ranks: work enqueued before it on any rank is visible after it on all."""
+        self.handle.barrier(channel=channel)
 
     def _agree(self, n_keys: int):
         """max and sum of the ranks' key counts (first step of a kind only: one small collective + host read-back)"""
@@ -268,9 +276,9 @@ class ScatterExchange:
         plan, tot = entry
         while True:
             self._ensure(plan.total_bytes)
-            self.handle.barrier(channel=0)                    # nobody still works in its receive area
+            self._barrier(0)                                  # nobody still works in its receive area
             eng.expand_scatter(plan, self.rank, self.peer_ptrs)
-            self.handle.barrier(channel=1)                    # every key and every status word has landed
+            self._barrier(1)                                  # every key and every status word has landed
             half, need = eng.reduce_received(plan, self.peer_ptrs[self.rank], min_count, sym)
             if half is not None:
                 break
@@ -281,14 +289,14 @@ class ScatterExchange:
         if sym:
             while True:
                 eng.mirror_push(plan, self.rank, half, self.peer_ptrs)
-                self.handle.barrier(channel=2)
+                self._barrier(2)
                 full, need = eng.mirror_collect(plan, self.rank, half, self.peer_ptrs[self.rank])
                 if full is not None:
                     break
                 self.regrows += 1
                 plan = eng.make_xplan(self.world, aid_bits, 0, tot, stripe_cap=plan.stripe_cap, mirror_cap=int(need * 1.25) + 4096)
                 self._ensure(plan.total_bytes)
-                self.handle.barrier(channel=0)                # the layout moved: nobody may still read the old stripes
+                self._barrier(0)                              # the layout moved: nobody may still read the old stripes
             half.free()
             half = full
         self.plans[name] = (plan, tot)

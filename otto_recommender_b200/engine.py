@@ -459,14 +459,17 @@ class Engine:
         return Table(self, h.value)
 
     # ---- (4) segmented top-K --------------------------------------------------------------------------------
-    def topk(self, table: Table, k: Optional[int] = None, device: bool = False, pinned: bool = False):
-        """-> aid_x [A], n_valid [A], aid_y [A, k], cnt [A, k]  (retrieve.py:41-47; canonical ties)."""
+    def topk(self, table: Table, k: Optional[int] = None, device: bool = False, pinned: bool = False, fetch: bool = True):
+        """-> aid_x [A], n_valid [A], aid_y [A, k], cnt [A, k]  (retrieve.py:41-47; canonical ties).
+        fetch=False leaves the result in the engine's device buffers (for topk_lookup) and returns the number of aids."""
         k = self.config.TOP_K if k is None else int(k)
         n = ctypes.c_int64()
         self._sync_stream()
         self._check(self._lib.ottocov_table_topk(self._ctx, table._h, k, ctypes.byref(n)))
         self._last_topk_k = k
         A = int(n.value)
+        if not fetch:
+            return A
         if device:
             import torch
             dev = torch.device("cuda", self.device)

@@ -303,6 +303,28 @@ int ottocov_mirror_push(ottocov_ctx* ctx, const ottocov_xplan* plan, int rank, c
 int ottocov_mirror_collect(ottocov_ctx* ctx, const ottocov_xplan* plan, int rank, const ottocov_table* half,
                            uint64_t recv_area_dev, ottocov_table** out, int64_t* need_rows);
 
+/* ---- EXTENSION: time-decay weighted co-event scores (north_star config 4) ------------------------------------------
+ * The reference has NO weighting in its counts (every in-window pair counts 1, model/count_co_events.py:70-71; SURVEY 0,
+ * App. A.6), so this mode has no reference counterpart and its parity is pinned only by this repo's float64 oracle
+ * (oracle/cov_oracle.c::cov_oracle_score).  Every pair the integer path counts contributes
+ *     w = max(0.10, 1 - |ts_next - ts| / window)        (the decay-with-floor shape of model/kmeans_sessions.py:59)
+ * to score(aid, aid_next).  Weights are quantised to 24 fractional bits (|error| <= 3e-8 per pair, <= 3e-7 relative)
+ * and summed as integers, so the result is exact in fixed point and independent of the summation order; it agrees
+ * with a float64 evaluation to well under the 1e-5 relative error north_star asks for.  Rows keep the integer count
+ * too; spec->min_count thresholds that count exactly as in ottocov_count.  At most 2^20 pairs per (aid, aid_next) and
+ * 2^32-2 pairs per call (OTTOCOV_ERR_CAPACITY otherwise).  Single GPU. */
+typedef struct ottocov_wtable ottocov_wtable;
+int ottocov_count_weighted(ottocov_ctx* ctx, const ottocov_spec* spec, ottocov_wtable** out);
+int ottocov_wtable_rows(const ottocov_wtable* t, int64_t* n_rows);
+int ottocov_wtable_free(ottocov_ctx* ctx, ottocov_wtable* t);
+/* rows in (aid, aid_next) order */
+int ottocov_wtable_fetch(ottocov_ctx* ctx, const ottocov_wtable* t, int32_t* aid, int32_t* aid_next, double* score,
+                         int32_t* count, int64_t cap, int where, int64_t* n_out);
+/* per-aid top-k by (score desc, aid_next asc), long format ordered by (aid, rank); rank is 1-based.  Two calls:
+ * with cap == 0 only *n_out is set (rows the result has), then with buffers of that size. */
+int ottocov_wtable_topk(ottocov_ctx* ctx, const ottocov_wtable* t, int k, int32_t* aid, int32_t* aid_next, double* score,
+                        int32_t* rank, int64_t cap, int where, int64_t* n_out);
+
 /* ---- building blocks exposed for tests and micro-benchmarks ---------------------------------- */
 /* The bijective key mix of the bucketed hash reduce (host code, needs no GPU): a pair (aid, aid_next), both below
  * 2^aid_bits, <-> a 2*aid_bits-bit mixed key.  ottocov_key_unmix returns aid << 32 | aid_next.  1 <= aid_bits <= 28. */

@@ -52,6 +52,11 @@ def _load():
             ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
             P(ctypes.c_void_p), P(ctypes.c_void_p), P(ctypes.c_void_p),
             P(ctypes.c_int64), P(ctypes.c_int64)]
+        lib.cov_oracle_score.restype = ctypes.c_int64
+        lib.cov_oracle_score.argtypes = [
+            ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+            ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+            P(ctypes.c_void_p), P(ctypes.c_void_p), P(ctypes.c_void_p), P(ctypes.c_void_p)]
         lib.cov_oracle_free.argtypes = [ctypes.c_void_p]
         lib.cov_oracle_free.restype = None
         _lib = lib
@@ -87,6 +92,35 @@ def count(session, aid, ts, type_, type_this: int, next_mask: int, window: int,
         for p in (pa_, pb_, pc_):
             lib.cov_oracle_free(p)
     return oa, ob, oc, int(emitted.value), int(nded.value)
+
+
+def score(session, aid, ts, type_, type_this: int, next_mask: int, window: int, dt_min: int = -86400, dt_max: int = 86400):
+    """EXTENSION oracle (no reference counterpart): time-decay weighted scores in float64,
+    w = max(0.10, 1 - |dt| / window) per counted pair.  -> (aid, aid_next, score f64, count u32) sorted by (aid, aid_next)."""
+    lib = _load()
+    s = np.ascontiguousarray(session, np.int32); a = np.ascontiguousarray(aid, np.int32)
+    t = np.ascontiguousarray(ts, np.int32); y = np.ascontiguousarray(type_, np.int8)
+    pa_, pb_, ps_, pc_ = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+    u = lib.cov_oracle_score(len(s), s.ctypes.data, a.ctypes.data, t.ctypes.data, y.ctypes.data, type_this, next_mask, window,
+                             dt_min, dt_max, ctypes.byref(pa_), ctypes.byref(pb_), ctypes.byref(ps_), ctypes.byref(pc_))
+    if u < 0:
+        raise MemoryError("cov_oracle_score failed")
+    try:
+        def take(p, ct, dt):
+            if u == 0:
+                return np.zeros(0, dt)
+            return np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ct)), shape=(u,)).astype(dt, copy=True)
+        out = (take(pa_, ctypes.c_int32, np.int32), take(pb_, ctypes.c_int32, np.int32), take(ps_, ctypes.c_double, np.float64),
+               take(pc_, ctypes.c_uint32, np.uint32))
+    finally:
+        for p in (pa_, pb_, ps_, pc_):
+            lib.cov_oracle_free(p)
+    return out
+
+
+def score_name(session, aid, ts, type_, name: str):
+    th, mask, w = NAMES[name]
+    return score(session, aid, ts, type_, th, mask, w)
 
 
 def count_name(session, aid, ts, type_, name: str):

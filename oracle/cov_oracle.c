@@ -148,3 +148,74 @@ int64_t cov_oracle_count_range(int64_t n, const int32_t* session, const int32_t*
     *out_aid = oa; *out_aid_next = ob; *out_count = oc;
     return u;
 }
+
+
+/* ---- EXTENSION oracle: time-decay weighted scores (no reference counterpart) -------------------------
+ * Same pair set as cov_oracle_count_range; every pair contributes w = max(0.10, 1 - |dt| / window) (window 0: w = 1),
+ * evaluated and summed in float64 in key order.  Returns U distinct keys sorted by (aid, aid_next) with their float64
+ * score and integer count. */
+typedef struct { uint64_t key; double w; } kw_t;
+static int kw_cmp(const void* pa, const void* pb) {
+    const kw_t* a = (const kw_t*)pa; const kw_t* b = (const kw_t*)pb;
+    return a->key < b->key ? -1 : (a->key > b->key ? 1 : 0);
+}
+
+int64_t cov_oracle_score(int64_t n, const int32_t* session, const int32_t* aid, const int32_t* ts, const int8_t* type,
+                         int type_this, int next_mask, int64_t window, int64_t dt_min, int64_t dt_max,
+                         int32_t** out_aid, int32_t** out_aid_next, double** out_score, uint32_t** out_count) {
+    *out_aid = NULL; *out_aid_next = NULL; *out_score = NULL; *out_count = NULL;
+    ev_t* ev = (ev_t*)malloc((size_t)(n > 0 ? n : 1) * sizeof(ev_t));
+    if (!ev) return -1;
+    for (int64_t i = 0; i < n; ++i) { ev[i].session = session[i]; ev[i].ts = ts[i]; ev[i].aid = aid[i]; ev[i].type = type[i]; }
+    qsort(ev, (size_t)n, sizeof(ev_t), ev_cmp);
+    int64_t m = 0;
+    for (int64_t i = 0; i < n; ++i)
+        if (i == 0 || ev_cmp(&ev[i], &ev[i - 1]) != 0) ev[m++] = ev[i];
+    kw_t* kw = NULL; int64_t nk = 0, cap = 0;
+    for (int64_t s0 = 0; s0 < m;) {
+        int64_t s1 = s0;
+        while (s1 < m && ev[s1].session == ev[s0].session) ++s1;
+        for (int64_t i = s0; i < s1; ++i) {
+            if (ev[i].type != type_this) continue;
+            for (int64_t j = s0; j < s1; ++j) {
+                if (j == i) continue;
+                if (!((next_mask >> ev[j].type) & 1)) continue;
+                int64_t dt = (int64_t)ev[j].ts - (int64_t)ev[i].ts;
+                if (dt < dt_min || dt > dt_max) continue;
+                int64_t adt = dt < 0 ? -dt : dt;
+                if (adt > window) continue;
+                if (nk == cap) {
+                    cap = cap ? cap * 2 : (1 << 16);
+                    kw_t* nv = (kw_t*)realloc(kw, (size_t)cap * sizeof(kw_t));
+                    if (!nv) { free(kw); free(ev); return -1; }
+                    kw = nv;
+                }
+                double w = window > 0 ? 1.0 - (double)adt / (double)window : 1.0;
+                if (w < 0.10) w = 0.10;
+                kw[nk].key = ((uint64_t)(uint32_t)ev[i].aid << 32) | (uint32_t)ev[j].aid;
+                kw[nk].w = w;
+                ++nk;
+            }
+        }
+        s0 = s1;
+    }
+    free(ev);
+    qsort(kw, (size_t)nk, sizeof(kw_t), kw_cmp);
+    int64_t u = 0;
+    for (int64_t i = 0; i < nk; ++i) if (i == 0 || kw[i].key != kw[i - 1].key) ++u;
+    int32_t* oa = (int32_t*)malloc((size_t)(u > 0 ? u : 1) * sizeof(int32_t));
+    int32_t* ob = (int32_t*)malloc((size_t)(u > 0 ? u : 1) * sizeof(int32_t));
+    double* os = (double*)malloc((size_t)(u > 0 ? u : 1) * sizeof(double));
+    uint32_t* oc = (uint32_t*)malloc((size_t)(u > 0 ? u : 1) * sizeof(uint32_t));
+    if (!oa || !ob || !os || !oc) { free(oa); free(ob); free(os); free(oc); free(kw); return -1; }
+    int64_t w = -1;
+    for (int64_t i = 0; i < nk; ++i) {
+        if (i == 0 || kw[i].key != kw[i - 1].key) {
+            ++w; oa[w] = (int32_t)(kw[i].key >> 32); ob[w] = (int32_t)(kw[i].key & 0xFFFFFFFFu); os[w] = 0.0; oc[w] = 0;
+        }
+        os[w] += kw[i].w; oc[w]++;
+    }
+    free(kw);
+    *out_aid = oa; *out_aid_next = ob; *out_score = os; *out_count = oc;
+    return u;
+}

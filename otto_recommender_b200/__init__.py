@@ -8,7 +8,7 @@ device every compute entry point raises.
 """
 from .config import CoEventConfig, DEFAULT_CONFIG  # noqa: F401
 from ._lib import OttocovError, load_library, library_path  # noqa: F401
-from .engine import Engine, Table  # noqa: F401
+from .engine import Engine, Table, WeightedTable  # noqa: F401
 
-__all__ = ["CoEventConfig", "DEFAULT_CONFIG", "Engine", "Table", "OttocovError", "load_library",
+__all__ = ["CoEventConfig", "DEFAULT_CONFIG", "Engine", "Table", "WeightedTable", "OttocovError", "load_library",
            "library_path"]

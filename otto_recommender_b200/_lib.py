@@ -99,6 +99,12 @@ SYMBOLS = {
     "ottocov_count_features": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int64, POINTER(c_int64)]),
     "ottocov_count_features_fetch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                              c_int64, c_int]),
+    "ottocov_count_weighted": (c_int, [c_void_p, POINTER(Spec), POINTER(c_void_p)]),
+    "ottocov_wtable_rows": (c_int, [c_void_p, POINTER(c_int64)]),
+    "ottocov_wtable_free": (c_int, [c_void_p, c_void_p]),
+    "ottocov_wtable_fetch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, POINTER(c_int64)]),
+    "ottocov_wtable_topk": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
+                                    POINTER(c_int64)]),
     "ottocov_count_popularity": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int32, c_int,
                                          POINTER(c_int64)]),
     "ottocov_popularity_fetch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int]),

@@ -538,6 +538,44 @@ int ottocov_count_features_fetch(ottocov_ctx* ctx, int32_t* aid, int32_t* aid_ne
     API_END(ctx)
 }
 
+int ottocov_count_weighted(ottocov_ctx* ctx, const ottocov_spec* spec, ottocov_wtable** out) {
+    API_BEGIN(ctx)
+    if (!spec || !out) COV_THROW(OTTOCOV_ERR_ARG, "NULL argument");
+    *out = nullptr;
+    *out = count_weighted_impl(ctx, spec);
+    API_END(ctx)
+}
+
+int ottocov_wtable_rows(const ottocov_wtable* t, int64_t* n_rows) {
+    if (!t || !n_rows) return OTTOCOV_ERR_ARG;
+    *n_rows = t->n;
+    return OTTOCOV_OK;
+}
+
+int ottocov_wtable_free(ottocov_ctx* ctx, ottocov_wtable* t) {
+    API_BEGIN(ctx)
+    if (t) { dev_free(ctx, t->keys); dev_free(ctx, t->count); dev_free(ctx, t->score_fx); delete t; }
+    API_END(ctx)
+}
+
+int ottocov_wtable_fetch(ottocov_ctx* ctx, const ottocov_wtable* t, int32_t* aid, int32_t* aid_next, double* score,
+                         int32_t* count, int64_t cap, int where, int64_t* n_out) {
+    API_BEGIN(ctx)
+    if (!t) COV_THROW(OTTOCOV_ERR_ARG, "NULL table");
+    if (cap > 0 && (!aid || !aid_next || !score)) COV_THROW(OTTOCOV_ERR_ARG, "NULL output");
+    wtable_fetch_impl(ctx, t, aid, aid_next, score, count, cap, where, n_out);
+    API_END(ctx)
+}
+
+int ottocov_wtable_topk(ottocov_ctx* ctx, const ottocov_wtable* t, int k, int32_t* aid, int32_t* aid_next, double* score,
+                        int32_t* rank, int64_t cap, int where, int64_t* n_out) {
+    API_BEGIN(ctx)
+    if (!t) COV_THROW(OTTOCOV_ERR_ARG, "NULL table");
+    if (cap > 0 && (!aid || !aid_next || !score || !rank)) COV_THROW(OTTOCOV_ERR_ARG, "NULL output");
+    wtable_topk_impl(ctx, t, k, aid, aid_next, score, rank, cap, where, n_out);
+    API_END(ctx)
+}
+
 int ottocov_count_popularity(ottocov_ctx* ctx, const int32_t* cluster, const int32_t* aid, const int32_t* ts,
                              const int8_t* type, int64_t n, int where, int32_t ts_recent, int keep_top_k, int64_t* n_rows) {
     API_BEGIN(ctx)

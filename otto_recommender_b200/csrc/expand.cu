@@ -1616,3 +1616,275 @@ ottocov_table* reduce_pairs_impl(ottocov_ctx* ctx, u64* keys, int64_t n, int aid
     }
     return out;
 }
+
+// =====================================================================================================================
+// EXTENSION: time-decay weighted co-event scores (include/ottocov.h, "EXTENSION"; no reference counterpart)
+// =====================================================================================================================
+// Built from the engine's existing pieces, favouring exactness over speed: the window records of the integer path, a
+// plain expansion that also evaluates the weight of every pair, the (key, index) radix sort, three run-length reduces
+// (count, low and high half of the 24-bit fixed-point weights) and one compaction.
+constexpr int WQ_FRAC = 24;
+constexpr u32 WQ_FLOOR = 1677722u;                 // round(0.10 * 2^24)
+constexpr u32 WQ_MAX_PAIRS_PER_KEY = 1u << 20;     // 2^20 * 4096 < 2^32: the 12-bit halves are summed in 32 bits
+
+__device__ __forceinline__ u32 decay_weight_q(u32 adt, u32 W) {
+    if (W == 0) return 1u << WQ_FRAC;
+    const u64 one = 1ull << WQ_FRAC;
+    const u64 r = (((u64)adt << WQ_FRAC) + (W >> 1)) / W;          // round(|dt| / W * 2^24)
+    const u32 q = r >= one ? 0u : (u32)(one - r);
+    return q > WQ_FLOOR ? q : WQ_FLOOR;
+}
+
+// one thread per output pair of the tile; MODE as in make_tile_keys (never EXM_CANON: weights are kept per ordered pair)
+template <int MODE>
+__global__ void __launch_bounds__(256) expand_weighted_kernel(const u32* __restrict__ rec_src, const u32* __restrict__ rec_lo,
+                                                              const u64* __restrict__ rec_off, const u32* __restrict__ tile_rec,
+                                                              const u32* __restrict__ aid_own, const u32* __restrict__ aid_rng,
+                                                              const u64* __restrict__ skey_own, const u64* __restrict__ skey_rng,
+                                                              u64 n_out_total, u32 W, u64* __restrict__ keys,
+                                                              u32* __restrict__ wq, u32* __restrict__ idx, u64 out_base) {
+    const u64 tile = blockIdx.x;
+    const u64 o0 = tile * EX_TILE;
+    const u32 r0 = tile_rec[tile];
+    u32 r1 = tile_rec[tile + 1];
+    for (int q = 0; q < EX_TILE / 256; ++q) {
+        const u64 o = o0 + (u64)q * 256 + threadIdx.x;
+        if (o >= n_out_total) return;
+        u32 lo = r0, hi = r1 + 1;                            // last record with rec_off <= o (records r0 .. r1 may own it)
+        while (hi - lo > 1) {
+            const u32 mid = lo + ((hi - lo) >> 1);
+            if (rec_off[mid] <= o) lo = mid; else hi = mid;
+        }
+        const u32 src = rec_src[lo];
+        u32 tgt = rec_lo[lo] + (u32)(o - rec_off[lo]);
+        if (MODE == EXM_SELF) tgt += (tgt >= src);
+        const u32 a = aid_own[src], b = aid_rng[tgt];
+        const u32 t0 = (u32)skey_own[src], t1 = (u32)skey_rng[tgt];
+        const u32 adt = t1 > t0 ? t1 - t0 : t0 - t1;
+        keys[out_base + o] = (MODE == EXM_SWAP) ? (((u64)b << 32) | a) : (((u64)a << 32) | b);
+        wq[out_base + o] = decay_weight_q(adt, W);
+        idx[out_base + o] = (u32)(out_base + o);
+    }
+}
+
+__global__ void __launch_bounds__(256) wq_gather_split_kernel(const u32* __restrict__ idx, const u32* __restrict__ wq, int64_t n,
+                                                              u32* __restrict__ lo, u32* __restrict__ hi) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u32 w = wq[idx[i]];
+    lo[i] = w & 0xFFFu;
+    hi[i] = w >> 12;
+}
+
+// count / low sums / high sums of the same distinct keys -> rows with count >= min_count
+struct WeightedRows {
+    static constexpr int NC = 1;
+    const u64* keys; const u32* cnt; const u32* slo; const u32* shi;
+    u32 min_count;
+    u64* o_keys; u32* o_cnt; u64* o_score; u32* flag;
+    __device__ u64 value(int64_t i) const { return cnt[i] >= min_count ? 1ull : 0ull; }
+    __device__ void apply(int64_t i, u64 v, const u64* pre) const {
+        if (cnt[i] > WQ_MAX_PAIRS_PER_KEY) atomicOr(flag, 1u);
+        if (!v) return;
+        o_keys[pre[0]] = keys[i];
+        o_cnt[pre[0]] = cnt[i];
+        o_score[pre[0]] = ((u64)shi[i] << 12) + (u64)slo[i];
+    }
+};
+
+static void wtable_release(ottocov_ctx* ctx, ottocov_wtable* t) {
+    if (!t) return;
+    dev_free(ctx, t->keys); dev_free(ctx, t->count); dev_free(ctx, t->score_fx);
+    delete t;
+}
+
+ottocov_wtable* count_weighted_impl(ottocov_ctx* ctx, const ottocov_spec* spec) {
+    ottocov_spec sp = *spec;
+    sp.flags = (sp.flags & ~(u32)OTTOCOV_SYM_ON) | OTTOCOV_SYM_OFF;          // every ordered pair carries its own weight
+    sp.min_count = 1;
+    ExpandPlan* pl = make_plan(ctx, &sp, false);
+    struct PlanGuard { ExpandPlan* p; ~PlanGuard() { delete p; } } plan_guard{pl};
+    memset(&ctx->last_count, 0, sizeof(ctx->last_count));
+    ctx->last_count.n_pairs = (int64_t)pl->P;
+    ottocov_wtable* out = new ottocov_wtable();
+    out->aid_bits = pl->aid_bits;
+    const int64_t P = (int64_t)pl->P;
+    if (P == 0) return out;
+    try {
+        if (P >= (int64_t)0xFFFFFFFFll) COV_THROW(OTTOCOV_ERR_CAPACITY, "weighted mode: at most 2^32-2 pairs per call (got %lld)", (long long)P);
+        const u32 W = (u32)(spec->window > 0x7FFFFFFFll ? 0x7FFFFFFFll : (spec->window < 0 ? 0 : spec->window));
+        DevBuf<u64> keys(ctx, P), kalt(ctx, P);
+        DevBuf<u32> idx(ctx, P), ialt(ctx, P), wq(ctx, P);
+        u64 base = 0;
+        for (Segment* sg : pl->segs) {
+            if (sg->n_pairs == 0) continue;
+            const int64_t n_tiles = ceil_div64((int64_t)sg->n_pairs, EX_TILE);
+            DevBuf<u32> tile_rec(ctx, n_tiles + 1);
+            COV_LAUNCH(ctx, OTTOCOV_K_EXPAND, 0, tile_search_kernel, (unsigned)ceil_div64(n_tiles + 1, 256), 256, 0,
+                       sg->rec_off.p, (int64_t)sg->n_rec, (u64)0, (u64)sg->n_pairs, n_tiles, tile_rec.p);
+            const TypeArray& own = ctx->ta[sg->own_type];
+            const TypeArray& rng = ctx->ta[sg->tgt_type];
+#define EXW_LAUNCH(MODE_)                                                                                               \
+            COV_LAUNCH(ctx, OTTOCOV_K_EXPAND, 16.0 * (double)sg->n_pairs, expand_weighted_kernel<MODE_>, (unsigned)n_tiles, 256, 0, \
+                       sg->rec_src.p, sg->rec_lo.p, sg->rec_off.p, tile_rec.p, own.aid, rng.aid, own.skey, rng.skey,         \
+                       (u64)sg->n_pairs, W, keys.p, wq.p, idx.p, base)
+            if (sg->self) EXW_LAUNCH(EXM_SELF);
+            else if (sg->swap) EXW_LAUNCH(EXM_SWAP);
+            else EXW_LAUNCH(EXM_CROSS);
+#undef EXW_LAUNCH
+            base += sg->n_pairs;
+        }
+        BitField fields[2] = {{0, pl->aid_bits}, {32, 32 + pl->aid_bits}};
+        u64* k = keys.p; u64* ka = kalt.p; u32* v = idx.p; u32* va = ialt.p;
+        ctx->last_count.sort_passes = radix_sort_pairs(ctx, k, ka, v, va, P, fields, 2);
+        DevBuf<u32> lo(ctx, P), hi(ctx, P);
+        COV_LAUNCH(ctx, OTTOCOV_K_ORDER, 16.0 * P, wq_gather_split_kernel, (unsigned)ceil_div64(P, 256), 256, 0, v, wq.p, P, lo.p, hi.p);
+        u64* uk[3] = {nullptr, nullptr, nullptr};
+        u32* uc[3] = {nullptr, nullptr, nullptr};
+        int64_t un[3] = {0, 0, 0};
+        struct Free3 { ottocov_ctx* c; u64** k; u32** v; ~Free3() { for (int i = 0; i < 3; ++i) { dev_free(c, k[i]); dev_free(c, v[i]); } } } f3{ctx, uk, uc};
+        reduce_sorted(ctx, k, nullptr, P, 1, false, &uk[0], &uc[0], &un[0]);     // pair counts
+        reduce_sorted(ctx, k, lo.p, P, 0, false, &uk[1], &uc[1], &un[1]);        // sums of the low 12 weight bits (a sum may be 0:
+        reduce_sorted(ctx, k, hi.p, P, 0, false, &uk[2], &uc[2], &un[2]);        // threshold 0 keeps every key); sums of the high bits
+        if (un[1] != un[0] || un[2] != un[0]) COV_THROW(OTTOCOV_ERR_CUDA, "weighted reduce: row counts disagree");
+        const int64_t U = un[0];
+        DevBuf<u64> okeys(ctx, U), oscore(ctx, U);
+        DevBuf<u32> ocnt(ctx, U), flag(ctx, 1);
+        CUDA_CHECK(cudaMemsetAsync(flag.p, 0, 4, ctx->stream));
+        WeightedRows f;
+        f.keys = uk[0]; f.cnt = uc[0]; f.slo = uc[1]; f.shi = uc[2];
+        f.min_count = spec->min_count > 1 ? spec->min_count : 1;
+        f.o_keys = okeys.p; f.o_cnt = ocnt.p; f.o_score = oscore.p; f.flag = flag.p;
+        u64 tot[1];
+        scan_apply(ctx, OTTOCOV_K_FILTER, f, U, tot, 28.0 * U);
+        u32 hflag = 0;
+        cov_readback(ctx, &hflag, flag.p, 4);
+        if (hflag) COV_THROW(OTTOCOV_ERR_CAPACITY, "weighted mode: a pair occurs more than 2^20 times");
+        out->n = (int64_t)tot[0];
+        out->keys = okeys.take(); out->count = ocnt.take(); out->score_fx = oscore.take();
+        ctx->last_count.n_chunks = 1;
+        ctx->last_count.n_unique = out->n;
+    } catch (...) {
+        wtable_release(ctx, out);
+        throw;
+    }
+    return out;
+}
+
+__global__ void __launch_bounds__(256) wtable_unpack_kernel(const u64* __restrict__ keys, const u32* __restrict__ cnt,
+                                                            const u64* __restrict__ score_fx, const u32* __restrict__ order,
+                                                            int64_t n, int32_t* __restrict__ aid, int32_t* __restrict__ aid_next,
+                                                            double* __restrict__ score, int32_t* __restrict__ count) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t r = order ? (int64_t)order[i] : i;
+    const u64 k = keys[r];
+    aid[i] = (int32_t)(k >> 32); aid_next[i] = (int32_t)(u32)k;
+    score[i] = (double)score_fx[r] / (double)(1u << WQ_FRAC);
+    if (count) count[i] = (int32_t)cnt[r];
+}
+
+void wtable_fetch_impl(ottocov_ctx* ctx, const ottocov_wtable* t, int32_t* aid, int32_t* aid_next, double* score,
+                       int32_t* count, int64_t cap, int where, int64_t* n_out) {
+    const int64_t n = t->n;
+    if (n_out) *n_out = n;
+    if (cap < n) COV_THROW(OTTOCOV_ERR_CAPACITY, "weighted fetch needs room for %lld rows", (long long)n);
+    if (n == 0) return;
+    DevBuf<int32_t> da, db, dc;
+    DevBuf<double> ds;
+    int32_t *pa = aid, *pb = aid_next, *pc = count;
+    double* ps = score;
+    if (where == OTTOCOV_HOST) { da.alloc(ctx, n); db.alloc(ctx, n); dc.alloc(ctx, n); ds.alloc(ctx, n); pa = da.p; pb = db.p; pc = dc.p; ps = ds.p; }
+    COV_LAUNCH(ctx, OTTOCOV_K_ORDER, 40.0 * n, wtable_unpack_kernel, (unsigned)ceil_div64(n, 256), 256, 0, t->keys, t->count, t->score_fx,
+               (const u32*)nullptr, n, pa, pb, ps, pc);
+    if (where == OTTOCOV_HOST) {
+        CUDA_CHECK(cudaMemcpyAsync(aid, pa, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaMemcpyAsync(aid_next, pb, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaMemcpyAsync(score, ps, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (count) CUDA_CHECK(cudaMemcpyAsync(count, pc, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+
+__global__ void __launch_bounds__(256) wt_inv_score_kernel(const u64* __restrict__ score_fx, int64_t n, u64 mask, u64* __restrict__ sk,
+                                                           u32* __restrict__ idx) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    sk[i] = (~score_fx[i]) & mask;            // ascending order of this = descending score
+    idx[i] = (u32)i;
+}
+
+__global__ void __launch_bounds__(256) wt_aid_of_kernel(const u64* __restrict__ keys, const u32* __restrict__ idx, int64_t n,
+                                                        u64* __restrict__ ak) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ak[i] = keys[idx[i]] >> 32;
+}
+
+// rows in (aid asc, score desc, aid_next asc) order: keep the first k of every aid
+struct WeightedTopRows {
+    static constexpr int NC = 1;
+    const u64* ak;            // aid of row i in that order
+    const u32* order;         // row of the table
+    int64_t n;
+    int k;
+    u32* o_order; int32_t* o_rank;
+    __device__ int64_t seg_start(int64_t i) const {
+        const u64 a = ak[i];
+        int64_t lo = 0, hi = i;                              // first row with ak >= a
+        while (lo < hi) { const int64_t mid = lo + ((hi - lo) >> 1); if (ak[mid] < a) lo = mid + 1; else hi = mid; }
+        return lo;
+    }
+    __device__ u64 value(int64_t i) const { return (i - seg_start(i)) < k ? 1ull : 0ull; }
+    __device__ void apply(int64_t i, u64 v, const u64* pre) const {
+        if (!v) return;
+        o_order[pre[0]] = order[i];
+        o_rank[pre[0]] = (int32_t)(i - seg_start(i)) + 1;
+    }
+};
+
+void wtable_topk_impl(ottocov_ctx* ctx, const ottocov_wtable* t, int k, int32_t* aid, int32_t* aid_next, double* score,
+                      int32_t* rank, int64_t cap, int where, int64_t* n_out) {
+    if (k < 1) COV_THROW(OTTOCOV_ERR_ARG, "k must be >= 1");
+    const int64_t n = t->n;
+    if (n_out) *n_out = 0;
+    if (n == 0) return;
+    // stable sort by descending score, then stable sort by aid: (aid asc, score desc, aid_next asc)
+    DevBuf<u64> sk(ctx, n), ska(ctx, n);
+    DevBuf<u32> idx(ctx, n), ia(ctx, n);
+    const int score_bits = WQ_FRAC + 21;                     // <= 2^20 pairs of weight <= 2^24 per key
+    COV_LAUNCH(ctx, OTTOCOV_K_ORDER, 20.0 * n, wt_inv_score_kernel, (unsigned)ceil_div64(n, 256), 256, 0, t->score_fx, n,
+               (1ull << score_bits) - 1ull, sk.p, idx.p);
+    u64* k1 = sk.p; u64* k1a = ska.p; u32* v1 = idx.p; u32* v1a = ia.p;
+    BitField fs[1] = {{0, score_bits}};
+    radix_sort_pairs(ctx, k1, k1a, v1, v1a, n, fs, 1);
+    COV_LAUNCH(ctx, OTTOCOV_K_ORDER, 20.0 * n, wt_aid_of_kernel, (unsigned)ceil_div64(n, 256), 256, 0, t->keys, v1, n, k1a);
+    u64* k2 = k1a; u64* k2a = k1;                            // the aid keys live in the spare buffer of the first sort
+    u32* v2 = v1; u32* v2a = v1a;
+    BitField fa[1] = {{0, t->aid_bits}};
+    radix_sort_pairs(ctx, k2, k2a, v2, v2a, n, fa, 1);
+    DevBuf<u32> o_order(ctx, n);
+    DevBuf<int32_t> o_rank(ctx, n);
+    WeightedTopRows f;
+    f.ak = k2; f.order = v2; f.n = n; f.k = k; f.o_order = o_order.p; f.o_rank = o_rank.p;
+    u64 tot[1];
+    scan_apply(ctx, OTTOCOV_K_TOPK, f, n, tot, 24.0 * n);
+    const int64_t m = (int64_t)tot[0];
+    if (n_out) *n_out = m;
+    if (cap == 0) return;                                    // size query
+    if (cap < m) COV_THROW(OTTOCOV_ERR_CAPACITY, "weighted top-k needs room for %lld rows", (long long)m);
+    DevBuf<int32_t> da, db;
+    DevBuf<double> ds;
+    int32_t *pa = aid, *pb = aid_next;
+    double* ps = score;
+    if (where == OTTOCOV_HOST) { da.alloc(ctx, m); db.alloc(ctx, m); ds.alloc(ctx, m); pa = da.p; pb = db.p; ps = ds.p; }
+    COV_LAUNCH(ctx, OTTOCOV_K_ORDER, 40.0 * m, wtable_unpack_kernel, (unsigned)ceil_div64(m, 256), 256, 0, t->keys, t->count, t->score_fx,
+               (const u32*)o_order.p, m, pa, pb, ps, (int32_t*)nullptr);
+    const cudaMemcpyKind kind = (where == OTTOCOV_HOST) ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    if (where == OTTOCOV_HOST) {
+        CUDA_CHECK(cudaMemcpyAsync(aid, pa, m * 4, kind, ctx->stream));
+        CUDA_CHECK(cudaMemcpyAsync(aid_next, pb, m * 4, kind, ctx->stream));
+        CUDA_CHECK(cudaMemcpyAsync(score, ps, m * 8, kind, ctx->stream));
+    }
+    CUDA_CHECK(cudaMemcpyAsync(rank, o_rank.p, m * 4, kind, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}

@@ -60,6 +60,14 @@ struct ottocov_table {
     int aid_bits = 32;       // significant bits of both key halves (bounds the radix passes)
 };
 
+struct ottocov_wtable {      // EXTENSION: time-decay weighted scores (expand.cu, "weighted")
+    u64* keys = nullptr;     // [n] sorted, distinct
+    u32* count = nullptr;    // [n] integer pair counts
+    u64* score_fx = nullptr; // [n] sum of weights, 24 fractional bits
+    int64_t n = 0;
+    int aid_bits = 32;
+};
+
 struct ottocov_ctx {
     int device = 0;
     int num_sms = 148;
@@ -266,6 +274,13 @@ void expand_run_impl(ottocov_ctx* ctx, int n_ranks, u64* buf_a, u64* buf_b, int*
 void push_keys_impl(ottocov_ctx* ctx, const u64* keys, int64_t n, int n_ranks, const u64* dest_ptrs_host);
 ottocov_table* reduce_pairs_impl(ottocov_ctx* ctx, u64* keys, int64_t n, int aid_bits, u32 min_count, int sym,
                                  int strip_dest);
+
+// weighted extension (expand.cu)
+ottocov_wtable* count_weighted_impl(ottocov_ctx* ctx, const ottocov_spec* spec);
+void wtable_fetch_impl(ottocov_ctx* ctx, const ottocov_wtable* t, int32_t* aid, int32_t* aid_next, double* score,
+                       int32_t* count, int64_t cap, int where, int64_t* n_out);
+void wtable_topk_impl(ottocov_ctx* ctx, const ottocov_wtable* t, int k, int32_t* aid, int32_t* aid_next, double* score,
+                      int32_t* rank, int64_t cap, int where, int64_t* n_out);
 
 // fused expansion + exchange (expand.cu, exchange.cu)
 void xplan_make_impl(int n_ranks, int aid_bits, int64_t max_local_keys, int64_t total_keys, int64_t stripe_cap,

@@ -863,6 +863,42 @@ def test_properties_at_scale(engine):
     assert int(ac[:, 0].max()) == int(fc.max())
 
 
+def test_weighted_time_decay_extension(engine):
+    """EXTENSION (north_star config 4; NO reference counterpart): every counted pair contributes
+    w = max(0.10, 1 - |dt| / window) to score(aid, aid_next).  Pinned by this repo's float64 oracle
+    (oracle/cov_oracle.c::cov_oracle_score): same keys, same integer counts, scores within 1e-5 relative (the
+    fixed-point sums are in fact within 3e-7); top-k by (score desc, aid_next asc) is checked against the table."""
+    cases = [small_events(71, n_sessions=600, n_aids=60, max_len=40)]
+    d = generate_numpy(SynthSpec(n_sessions=20_000, seed=23, force_long_click_session=465))     # long-tail shape of config 4
+    cases.append((d["session"], d["aid"], d["ts"], d["type"]))
+    for ci, (s, a, t, y) in enumerate(cases):
+        engine.load_events(s, a, t, y)
+        for name in NAMES if ci == 0 else ("click_to_cart_or_buy", "click_to_click"):
+            oa, ob, osc, oc = c_oracle.score_name(s, a, t, y, name)
+            ia, ib, ic = engine.count(name).fetch()
+            assert np.array_equal(ia, oa) and np.array_equal(ib, ob) and np.array_equal(ic.astype(np.uint32), oc)
+            for mc in (1, 3):
+                wt = engine.count_weighted(name, min_count=mc)
+                ga, gb, gs, gc = wt.fetch()
+                keep = oc >= mc
+                assert np.array_equal(ga, oa[keep]) and np.array_equal(gb, ob[keep]) and np.array_equal(gc.astype(np.uint32), oc[keep])
+                if len(gs):
+                    rel = np.abs(gs - osc[keep]) / osc[keep]
+                    assert rel.max() <= 1e-5, (name, mc, rel.max())            # north_star's tolerance
+                    assert rel.max() <= 1e-6                                    # what 24 fractional bits really give
+                    assert np.all(gs >= 0.1 * gc - 1e-9) and np.all(gs <= gc + 1e-9)
+                for k in (1, 5, 20):
+                    ta, tb, ts_, tr = wt.topk(k)
+                    o = np.lexsort((gb, -gs, ga))                               # fixed-point sums are exact in float64
+                    xa, xb, xs = ga[o], gb[o], gs[o]
+                    start = np.r_[True, xa[1:] != xa[:-1]] if len(xa) else np.zeros(0, bool)
+                    seg = np.maximum.accumulate(np.where(start, np.arange(len(xa)), 0)) if len(xa) else np.zeros(0, np.int64)
+                    rank = np.arange(len(xa)) - seg + 1
+                    kk = rank <= k
+                    assert np.array_equal(ta, xa[kk]) and np.array_equal(tb, xb[kk]) and np.array_equal(ts_, xs[kk]) and np.array_equal(tr, rank[kk])
+                wt.free()
+
+
 def test_reference_run_fixtures_gpu(engine):
     """The CUDA path against the reference's OWN output (tests/golden/ref_*.json, tools/gen_reference_fixtures.py);
     skipped loudly while the fixtures cannot be generated (polars absent)."""

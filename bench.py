@@ -6,7 +6,8 @@
 Workloads (BASELINE.json configs; synthetic OTTO shape from otto_recommender_b200/synth.py):
     cooc      configs[1] (default): click_to_click 12 h, top-20, min_count 10 on 12.9 M sessions / 220 M events / 1.8 M aids
     all5      configs[2]: all five co-event kinds of config.CO_EVENTS_TO_COUNT with their MIN_COUNT_TO_SAVE thresholds
-    longtail  configs[3]: click_to_cart_or_buy 24 h with one 465-click session forced in (README.md:18)
+    longtail  configs[3]: click_to_cart_or_buy 24 h with one 465-click session forced in (README.md:18), integer counts
+    decay     configs[3] with the float time-decay EXTENSION (w = max(0.10, 1 - |dt|/W) per pair; no reference counterpart), N = 1
     scale4    configs[4]: 4x scale, 51.6 M sessions / 880 M events / 7.2 M aids (46-bit keys), click_to_click
     popularity  SURVEY 8(f) rank 3 (count_popularity), one GPU, its own JSON line
 One "step" = one pass of the hot path over that batch:
@@ -54,6 +55,9 @@ WORKLOADS = {
     "longtail": ("co-event pairs/sec (click-to-cart-or-buy 24h, long-tail sessions, top-20)", ["click_to_cart_or_buy"],
                  FULL_SESSIONS, 1_800_000, {"force_long_click_session": 465}, 3),
     "scale4": ("co-event pairs/sec (click-to-click 12h, 4x scale, top-20)", ["click_to_click"], 4 * FULL_SESSIONS, 7_200_000, {}, 4),
+    # EXTENSION (the reference has no weighting): configs[3] with float time-decay scores, own f64 oracle
+    "decay": ("co-event pairs/sec (time-decay weighted click-to-cart-or-buy 24h, long-tail sessions, top-20)",
+              ["click_to_cart_or_buy"], FULL_SESSIONS, 1_800_000, {"force_long_click_session": 465}, 3),
 }
 
 
@@ -267,6 +271,40 @@ def cpu_baseline_port(host_cols, n_sessions_sample, names):
     return cpu, cols, want
 
 
+def cpu_baseline_weighted(eng, host_cols, n_sessions_sample, names):
+    """EXTENSION: float64 oracle (oracle/cov_oracle.c::cov_oracle_score) on a sample + the GPU's fixed-point scores on it."""
+    import numpy as np
+    from oracle import c_oracle
+    s = host_cols[0]
+    cut = int(np.searchsorted(s, s[0] + n_sessions_sample, "left"))
+    cols = [c[:cut] for c in host_cols]
+    t0 = time.perf_counter()
+    want, pairs = {}, 0
+    for name in names:
+        want[name] = c_oracle.score_name(*cols, name)
+        pairs += int(want[name][3].sum())
+    dt = time.perf_counter() - t0
+    eng.load_events(*cols)
+    worst = 0.0
+    verdict = None
+    for name, (oa, ob, osc, oc) in want.items():
+        mc = MIN_COUNT_TO_SAVE[name]
+        ga, gb, gs, gc = eng.count_weighted(name, min_count=mc).fetch()
+        keep = oc >= mc
+        if not (np.array_equal(ga, oa[keep]) and np.array_equal(gb, ob[keep]) and np.array_equal(gc.astype(np.uint32), oc[keep])):
+            verdict = f"MISMATCH: {name} keys / counts"
+            break
+        if len(gs):
+            worst = max(worst, float((np.abs(gs - osc[keep]) / osc[keep]).max()))
+    if verdict is None:
+        verdict = f"keys and counts identical, scores within {worst:.1e} relative of the float64 oracle (tolerance 1e-5)" if worst <= 1e-5 \
+            else f"MISMATCH: score relative error {worst:.2e} > 1e-5"
+    cpu = {"value": pairs / dt, "unit": UNIT, "cores": 1, "kind": "port",
+           "sample": f"first {n_sessions_sample:,} sessions ({cut:,} events, {pairs:,} pairs), {', '.join(names)}: float64 weighted "
+                     f"oracle oracle/cov_oracle.c::cov_oracle_score, {dt:.1f} s"}
+    return cpu, verdict
+
+
 def parity_on_sample(eng, cols, want):
     """The GPU path on the CPU baseline's sample, compared with the oracle's tables and top-20 (outside any timed region)."""
     import numpy as np
@@ -336,6 +374,9 @@ def run_ours(args):
     torch.cuda.empty_cache()
 
     eng = Engine(device=local_rank)
+    weighted = args.workload == "decay"
+    if weighted and world > 1:
+        raise SystemExit("--workload decay (float time-decay extension) is single-GPU")
     exchange = {"nccl": covdist.count_exchange_first, "push": covdist.count_exchange_push,
                 "scatter": covdist.count_exchange_scatter}[args.exchange]
     state = {"tables": []}
@@ -348,6 +389,12 @@ def run_ours(args):
         pairs, infos = 0, {}
         for name in names:
             mc = MIN_COUNT_TO_SAVE[name]
+            if weighted:
+                f = eng.count_weighted(name, min_count=mc)
+                ci = eng.count_info()
+                pairs += ci["n_pairs"]; infos[name] = ci
+                state["tables"].append(f)
+                continue
             if world > 1:                                     # raw keys cross NVLink once, reduced where they land
                 f = exchange(eng, name, mc, aid_bits=aid_bits)
             else:                                             # threshold fused into the reduce
@@ -362,7 +409,10 @@ def run_ours(args):
         eng.load_events(*cols)
         pairs, infos = count_all(args.pair_budget)
         for f in state["tables"]:
-            eng.topk(f, TOP_K, fetch=False)               # the per-aid top-20 stays in HBM (the e2e arm copies it out)
+            if weighted:
+                f.topk_rows(TOP_K)
+            else:
+                eng.topk(f, TOP_K, fetch=False)           # the per-aid top-20 stays in HBM (the e2e arm copies it out)
         return pairs, infos
 
     def barrier():
@@ -401,7 +451,8 @@ def run_ours(args):
     mem = eng.memory_info()
 
     # ---- fingerprint of the global thresholded tables (outside the timed region) --------------------------
-    fp = torch.stack([table_fingerprint(t, dev) for t in state["tables"]]).sum(0)
+    fp = (torch.stack([table_fingerprint(t, dev) for t in state["tables"]]).sum(0) if not weighted
+          else torch.tensor([sum(t.rows for t in state["tables"]), 0, 0, 0], dtype=torch.int64, device=dev))
     t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
     p_all = torch.tensor([pairs_local, n_rows], dtype=torch.int64, device=dev)
     if world > 1:
@@ -420,6 +471,15 @@ def run_ours(args):
     host_parts = Engine.split_at_sessions(*host_cols, 64) if world == 1 else None
 
     def step_e2e():
+        if weighted:
+            eng.load_events(*host_cols)                   # H2D inside
+            count_all()
+            d2h = 0
+            for f in state["tables"]:
+                ta, tb, ts_, tr = f.topk(TOP_K)           # D2H inside
+                fa, fb, fs, fc = f.fetch()
+                d2h += ta.size * 20 + fa.size * 20
+            return d2h
         if world == 1 and not args.no_streamed_e2e:
             # the public ingest call: the population as parts in host memory (what reading the ETL's parquet parts
             # gives), copied on a second stream and counted group by group behind the copies
@@ -467,7 +527,7 @@ def run_ours(args):
     sp = stats["sort_pass"]
     achieved = sp["algo_bytes"] / (sp["ms"] * 1e-3) / 1e9 if sp["ms"] > 0 else 0.0
     first = infos[names[0]]
-    keys_sorted = first["n_pairs"] // 2 if names[0] in ("click_to_click", "cart_to_cart", "buy_to_buy") else first["n_pairs"]
+    keys_sorted = first["n_pairs"] // 2 if (names[0] in ("click_to_click", "cart_to_cart", "buy_to_buy") and not weighted) else first["n_pairs"]
     per_launch_bytes = 16.0 * keys_sorted       # the big launches: bucket passes over this rank's keys of the first kind
     per_launch_ms = per_launch_bytes / (achieved * 1e9) * 1e3 if achieved > 0 else 0.0
     traffic = None
@@ -487,8 +547,11 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         hc = [c.numpy() for c in host_cols]
         sample_sessions = min(args.cpu_sample_sessions if len(names) == 1 else args.cpu_sample_sessions // 3, sessions)
-        cpu, sample_cols, want = cpu_baseline_port(hc, sample_sessions, names)
-        parity = parity_on_sample(eng, sample_cols, want)
+        if weighted:
+            cpu, parity = cpu_baseline_weighted(eng, hc, min(300_000, sessions), names)
+        else:
+            cpu, sample_cols, want = cpu_baseline_port(hc, sample_sessions, names)
+            parity = parity_on_sample(eng, sample_cols, want)
 
     out = {
         "metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -530,7 +593,7 @@ def run_ours(args):
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
-    if parity is not None and parity != "identical":
+    if parity is not None and "MISMATCH" in parity:
         raise SystemExit(f"parity check on the CPU sample failed: {parity}")
 
 
@@ -605,6 +668,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cooc", choices=list(WORKLOADS) + ["popularity"],
                     help="cooc = the BASELINE.json metric on configs[1] (default); all5 / longtail / scale4 = configs[2..4]; "
+                         "decay = configs[3] with the float time-decay extension (N=1); "
                          "popularity = the popularity stage, N=1, its own JSON line")
     ap.add_argument("--sessions", type=int, default=0, help="sessions of the synthetic workload (0 = the workload's own size)")
     ap.add_argument("--pair-budget", type=int, default=None, help="co-event keys expanded at once (HBM footprint); default: from free HBM")

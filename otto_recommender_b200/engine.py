@@ -146,6 +146,14 @@ class WeightedTable:
         m = int(got.value)
         return a[:m], b[:m], s[:m], r[:m]
 
+    def topk_rows(self, k: int = 20) -> int:
+        """Runs the per-aid top-k on the device without copying it out; -> rows it has."""
+        got = ctypes.c_int64()
+        self._e._sync_stream()
+        self._e._check(self._e._lib.ottocov_wtable_topk(self._e._ctx, self._h, int(k), None, None, None, None, 0, _lib.HOST,
+                                                        ctypes.byref(got)))
+        return int(got.value)
+
     def free(self):
         if self._h is not None and self._e._ctx is not None:
             self._e._lib.ottocov_wtable_free(self._e._ctx, self._h)

@@ -947,23 +947,6 @@ ottocov_table* count_impl(ottocov_ctx* ctx, const ottocov_spec* spec) {
 }
 
 // ---- streamed ingest + count (include/ottocov.h, ottocov_count_parts) ----------------------------------------------
-__global__ void __launch_bounds__(256) aid_max_kernel(const int32_t* __restrict__ aid, int64_t n, int* __restrict__ out) {
-    int mx = -2147483647 - 1, mn = 2147483647;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const int a = aid[i];
-        mx = max(mx, a); mn = min(mn, a);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-    }
-    if ((threadIdx.x & 31) == 0) { atomicMax(&out[0], mx); atomicMin(&out[1], mn); }
-}
-
-__global__ void init_minmax_kernel(int* out) { out[0] = -2147483647 - 1; out[1] = 2147483647; }
-
 // ---- the session column crosses PCIe run-length encoded ---------------------------------------------------------------
 // The ETL writes each part ordered by session (etl/jsonl_to_parquet.py:59-84), so the 4-byte session column -- 31 % of
 // the 13 B/event the loader needs -- is ~17 equal values in a row.  Host threads turn it into (session id, first row)
@@ -979,25 +962,31 @@ struct RleTask {
     std::atomic<int> done{0};
 };
 
+// Branch-free in the common case (1.2 ns per value on one core against 2.6 for the obvious loop): the candidate run
+// is always written at slot k and k only advances when the value changed.
 static void rle_encode(RleTask* t) {
     const int32_t* s = t->session;
     const int64_t n = t->rows, cap = t->cap;
     u32* o = t->out;
     int64_t k = 0;
     if (n > 0) {
-        int32_t cur = s[0];
-        if (cap > 0) { o[0] = (u32)cur; o[1] = 0; }
-        k = 1;
-        for (int64_t i = 1; i < n; ++i) {
-            const int32_t v = s[i];
-            if (v != cur) {
-                if (k >= cap) { k = -1; break; }
-                o[2 * k] = (u32)v; o[2 * k + 1] = (u32)i;
-                ++k;
-                cur = v;
+        if (cap < 2) k = -1;
+        else {
+            o[0] = (u32)s[0]; o[1] = 0; k = 1;
+            int64_t i = 1;
+            while (i < n && k >= 0) {
+                const int64_t e = i + 1024 < n ? i + 1024 : n;
+                if (k + (e - i) >= cap) {                      // close to the capacity: the careful loop
+                    for (; i < e; ++i)
+                        if (s[i] != s[i - 1]) {
+                            if (k >= cap) { k = -1; break; }
+                            o[2 * k] = (u32)s[i]; o[2 * k + 1] = (u32)i; ++k;
+                        }
+                } else {
+                    for (; i < e; ++i) { o[2 * k] = (u32)s[i]; o[2 * k + 1] = (u32)i; k += (s[i] != s[i - 1]); }
+                }
             }
         }
-        if (cap == 0) k = -1;
     }
     t->n_runs = k;
     t->done.store(1, std::memory_order_release);
@@ -1024,11 +1013,15 @@ struct PartsAccum {
     PassList full, rest;
     u32 n_digits = 0;
     u64 P_total = 0, n_pairs = 0;
-    std::vector<u64*> bufs;                    // one region buffer per group (cov_alloc)
-    std::vector<u64> cap;                      // region capacity of each group
+    std::vector<u64*> bufs;                    // one region buffer per group (cov_alloc); after the group's passes its
+    std::vector<u64*> sorted;                  //   first P_g slots hold the group's keys sorted by bucket (`sorted`)
+    std::vector<u32*> bounds;                  // per group: first key of every bucket range (hash_reduce.cu)
+    std::vector<u64> n_g;                      // keys of each group
+    u32 rb = 1;                                // buckets per reduce CTA
+    int64_t n_ranges = 0;
     DevBuf<unsigned long long> cursor;         // [groups][RS_RADIX] fill counters
-    DevBuf<u64> reg;                           // [groups][2][RS_RADIX] byte addresses | capacities
-    DevBuf<u64> ghist;
+    DevBuf<u64> reg;                           // [groups][3][RS_RADIX] byte addresses | capacities | key offsets
+    DevBuf<u64> ghist;                         // [groups][passes][RS_RADIX]
     DevBuf<unsigned long long> ctr;
 };
 
@@ -1093,11 +1086,11 @@ void count_parts_impl(ottocov_ctx* ctx, int n_parts, const int32_t* const* sessi
     CUDA_CHECK(cudaEventRecord(e0, ctx->stream));
     CUDA_CHECK(cudaStreamWaitEvent(cs, e0, 0));
     // ---- host threads run-length encode the session columns while the first copies are in flight ----------------------
-    // Tasks are row ranges of <= 4 M rows of one part, encoded independently (a run that continues across two ranges is
+    // Tasks are row ranges of <= 1 M rows of one part, encoded independently (a run that continues across two ranges is
     // simply two runs with the same id), handed to the threads in order so that the first groups are ready first.
     static int rle_on = -1;
     if (rle_on < 0) { const char* e = getenv("OTTOCOV_NO_SESSION_RLE"); rle_on = (e && atoi(e)) ? 0 : 1; }
-    constexpr int64_t RLE_TASK_ROWS = 4 << 20;
+    constexpr int64_t RLE_TASK_ROWS = 1 << 20;          // ~1.5 ms of one core: the first group is ready almost at once
     std::vector<std::unique_ptr<RleTask>> rle;
     std::vector<int64_t> task_row0, task_slot;              // first row (global) and staging slot (in runs) of each task
     std::vector<int> part_task0(n_parts + 1, 0);
@@ -1119,10 +1112,9 @@ void count_parts_impl(ottocov_ctx* ctx, int n_parts, const int32_t* const* sessi
     if (rle_on && stage_bytes > ctx->host_stage_bytes) {
         if (ctx->host_stage) cudaFreeHost(ctx->host_stage);
         ctx->host_stage = nullptr; ctx->host_stage_bytes = 0;
-        CUDA_CHECK(cudaHostAlloc(&ctx->host_stage, stage_bytes + stage_bytes / 8, cudaHostAllocDefault));
+        CUDA_CHECK(cudaHostAlloc(&ctx->host_stage, stage_bytes + stage_bytes / 8, cudaHostAllocMapped | cudaHostAllocPortable));
         ctx->host_stage_bytes = stage_bytes + stage_bytes / 8;
     }
-    DevBuf<u32> d_runs(ctx, rle_on ? (size_t)slot * 2 + 2 : 1);
     std::atomic<int> next_task{0};
     std::vector<std::thread> workers;
     struct JoinWorkers {                                    // never leave with a thread still reading the caller's buffers
@@ -1138,7 +1130,7 @@ void count_parts_impl(ottocov_ctx* ctx, int n_parts, const int32_t* const* sessi
         if (n_thr > n_tasks) n_thr = n_tasks;
         for (int t = 0; t < n_thr; ++t)
             workers.emplace_back([&, n_tasks]() {
-                for (;;) {
+                for (;;) {                                  // in order: the first groups' runs are needed first
                     const int k = next_task.fetch_add(1);
                     if (k >= n_tasks) return;
                     rle_encode(rle[k].get());
@@ -1146,87 +1138,92 @@ void count_parts_impl(ottocov_ctx* ctx, int n_parts, const int32_t* const* sessi
             });
     }
     int64_t h2d = 0;
+    static int trace_on = -1;
+    if (trace_on < 0) { const char* e = getenv("OTTOCOV_TRACE"); trace_on = (e && atoi(e)) ? 1 : 0; }
+    cudaEvent_t tr_a = nullptr, tr_b = nullptr;
+    if (trace_on) { cudaEventCreate(&tr_a); cudaEventCreate(&tr_b); cudaEventRecord(tr_a, cs); }
     ctx->begin(OTTOCOV_K_LOAD);
-    for (int p = 0; p < n_parts; ++p)                   // aid and type of every part first: the key width is global
-        if (rows[p]) {
-            CUDA_CHECK(cudaMemcpyAsync(d_aid.p + off[p], aid[p], rows[p] * 4, cudaMemcpyHostToDevice, cs));
-            CUDA_CHECK(cudaMemcpyAsync(d_type.p + off[p], type[p], rows[p], cudaMemcpyHostToDevice, cs));
-            h2d += rows[p] * 5;
-        }
-    cudaEvent_t e_aid = new_event();
-    CUDA_CHECK(cudaEventRecord(e_aid, cs));
-    std::vector<cudaEvent_t> e_grp(n_groups);
+    // raw columns (type, aid, ts -- and session where the runs are switched off) of every group, enqueued at once: the DMA
+    // engine starts at t = 0 and never waits for the host.  The session runs (small) follow on a second stream as the
+    // encoder threads deliver them, group by group, while the main stream already works on the earlier groups.
+    std::vector<cudaEvent_t> e_grp(n_groups), e_run(n_groups, nullptr);      // e_run[g] != null: group g's session column is on its way
     for (int g = 0; g < n_groups; ++g) {
         for (int p = g_first[g]; p < g_first[g + 1]; ++p)
             if (rows[p]) {
+                CUDA_CHECK(cudaMemcpyAsync(d_type.p + off[p], type[p], rows[p], cudaMemcpyHostToDevice, cs));
+                CUDA_CHECK(cudaMemcpyAsync(d_aid.p + off[p], aid[p], rows[p] * 4, cudaMemcpyHostToDevice, cs));
                 CUDA_CHECK(cudaMemcpyAsync(d_ts.p + off[p], ts[p], rows[p] * 4, cudaMemcpyHostToDevice, cs));
-                h2d += rows[p] * 4;
-                for (int k = part_task0[p]; k < part_task0[p + 1]; ++k) {       // session column: runs where they compress
-                    while (!rle[k]->done.load(std::memory_order_acquire)) std::this_thread::yield();
-                    if (rle[k]->n_runs < 0) continue;
-                    CUDA_CHECK(cudaMemcpyAsync(d_runs.p + task_slot[k] * 2, rle[k]->out, (size_t)rle[k]->n_runs * 8,
-                                               cudaMemcpyHostToDevice, cs));
-                    h2d += rle[k]->n_runs * 8;
-                }
+                h2d += rows[p] * 9;
                 if (!rle_on) {
                     CUDA_CHECK(cudaMemcpyAsync(d_session.p + off[p], session[p], rows[p] * 4, cudaMemcpyHostToDevice, cs));
                     h2d += rows[p] * 4;
-                } else {
-                    for (int k = part_task0[p]; k < part_task0[p + 1]; ++k)
-                        if (rle[k]->n_runs < 0) {                               // this range does not compress: raw
-                            CUDA_CHECK(cudaMemcpyAsync(d_session.p + task_row0[k], rle[k]->session, rle[k]->rows * 4,
-                                                       cudaMemcpyHostToDevice, cs));
-                            h2d += rle[k]->rows * 4;
-                        }
                 }
             }
         e_grp[g] = new_event();
         CUDA_CHECK(cudaEventRecord(e_grp[g], cs));
     }
-    ctx->h2d_bytes_last = h2d;
+    if (trace_on) cudaEventRecord(tr_b, cs);
+    // The runs are NOT copied: a second stream's copies queue behind the big ones on the same DMA engine (measured: the
+    // first group then waited for the whole 38 ms copy).  The staging buffer is page-locked memory, which the device can
+    // read directly: rle_expand_kernel pulls the runs over PCIe itself, next to the DMA traffic.  Only a range that
+    // does not compress needs a copy of its raw session column (main stream; rare: rows in arbitrary order).
+    auto enqueue_runs = [&](int g) {
+        if (!rle_on) return;
+        for (int p = g_first[g]; p < g_first[g + 1]; ++p)
+            for (int k = part_task0[p]; k < part_task0[p + 1]; ++k) {
+                while (!rle[k]->done.load(std::memory_order_acquire)) std::this_thread::yield();
+                if (rle[k]->n_runs >= 0) {
+                    h2d += rle[k]->n_runs * 8;
+                } else {
+                    CUDA_CHECK(cudaMemcpyAsync(d_session.p + task_row0[k], rle[k]->session, rle[k]->rows * 4,
+                                               cudaMemcpyHostToDevice, ctx->stream));
+                    h2d += rle[k]->rows * 4;
+                }
+            }
+        e_run[g] = e_grp[g];            // marks the group as handled
+    };
     ctx->end(OTTOCOV_K_LOAD, (double)h2d);
     ctx->stats[OTTOCOV_K_LOAD].launches -= 1;           // copies, not kernels
     // no exit path may return while a copy still reads the caller's host buffers, or leave the main stream ahead of them
     struct JoinCopies {
         ottocov_ctx* c; cudaEvent_t last; bool done = false;
-        ~JoinCopies() { cudaStreamWaitEvent(c->stream, last, 0); if (!done) cudaStreamSynchronize(c->copy_stream); }
+        ~JoinCopies() {
+            cudaStreamWaitEvent(c->stream, last, 0);
+            if (!done) cudaStreamSynchronize(c->copy_stream);
+        }
     } join_copies{ctx, e_grp[n_groups - 1]};
 
-    // ---- global key width ------------------------------------------------------------------------------------------
-    CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, e_aid, 0));
-    DevBuf<int> d_mm(ctx, 2);
-    COV_LAUNCH(ctx, OTTOCOV_K_MISC, 0, init_minmax_kernel, 1, 1, 0, d_mm.p);
-    COV_LAUNCH(ctx, OTTOCOV_K_LOAD, 4.0 * N, aid_max_kernel, (int)imin64(ceil_div64(N, 1024), (int64_t)ctx->num_sms * 8), 256, 0,
-               d_aid.p, N, d_mm.p);
-    int mm[2];
-    cov_readback(ctx, mm, d_mm.p, sizeof(mm));
-    if (mm[1] < 0) COV_THROW(OTTOCOV_ERR_DATA, "negative aid %d", mm[1]);
-    int aid_bits = 0;
-    for (u32 v = (u32)mm[0]; v; v >>= 1) ++aid_bits;
-    if (aid_bits == 0) aid_bits = 1;
-    const bool hashable = hashed_reduce_supported(aid_bits);
-    const KeyMix mix = make_key_mix(aid_bits);
+    // The key width (bits of the largest aid) must be fixed before the first key is mixed.  It is taken from the FIRST
+    // group (the loader finds it anyway) and checked on every later one: an aid that needs more bits sends the call to
+    // the plain path below.  (Waiting for every aid column to land first would hold the first group back by a third of
+    // the copy; scanning them on the host costs more than it saves.)
+    int aid_bits = 0, aid_max = 0;
+    KeyMix mix = make_key_mix(1);
 
     std::vector<PartsAccum> acc(n_specs);
     struct AccGuard {
         ottocov_ctx* c; std::vector<PartsAccum>& v;
-        ~AccGuard() { for (auto& a : v) for (u64* b : a.bufs) dev_free(c, b); }
+        ~AccGuard() { for (auto& a : v) { for (u64* b : a.bufs) dev_free(c, b); for (u32* b : a.bounds) dev_free(c, b); } }
     } acc_guard{ctx, acc};
-    bool fallback = !hashable;                          // keys too wide for the hash path: plain load + count below
+    bool fallback = false;
     std::vector<int64_t> g_rows(n_groups);
 
+    cov_trace(ctx, "parts: copies enqueued, key width known");
     for (int g = 0; g < n_groups && !fallback; ++g) {
         const int64_t r0 = off[g_first[g]], r1 = off[g_first[g + 1]];
         g_rows[g] = r1 - r0;
         CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, e_grp[g], 0));
+        enqueue_runs(g);
         if (r1 == r0) continue;
         if (rle_on)
             for (int k = part_task0[g_first[g]]; k < part_task0[g_first[g + 1]]; ++k)
                 if (rle[k]->n_runs > 0)
                     COV_LAUNCH(ctx, OTTOCOV_K_LOAD, 4.0 * rle[k]->rows + 8.0 * rle[k]->n_runs, rle_expand_kernel,
-                               (unsigned)ceil_div64(rle[k]->n_runs, 256), 256, 0, d_runs.p + task_slot[k] * 2, rle[k]->n_runs,
+                               (unsigned)ceil_div64(rle[k]->n_runs, 256), 256, 0, (const u32*)rle[k]->out, rle[k]->n_runs,
                                rle[k]->rows, d_session.p + task_row0[k]);
+        cov_trace(ctx, "parts:   group's columns have landed");
         load_events_impl(ctx, d_session.p + r0, d_aid.p + r0, d_ts.p + r0, d_type.p + r0, r1 - r0, OTTOCOV_DEVICE);
+        cov_trace(ctx, "parts:   loader");
         const ottocov_events_info gi = ctx->info;
         total.n_rows_in += gi.n_rows_in; total.n_events += gi.n_events;
         for (int t = 0; t < 3; ++t) total.n_by_type[t] += gi.n_by_type[t];
@@ -1235,10 +1232,17 @@ void count_parts_impl(ottocov_ctx* ctx, int n_parts, const int32_t* const* sessi
         total.ts_min = gi.ts_min < total.ts_min ? gi.ts_min : total.ts_min;
         total.ts_max = gi.ts_max > total.ts_max ? gi.ts_max : total.ts_max;
         total.was_sorted = total.was_sorted && gi.was_sorted;
-        ctx->info.aid_bits = aid_bits;                  // keys of every group are made with the global width
+        aid_max = gi.aid_max > aid_max ? gi.aid_max : aid_max;
+        if (aid_bits == 0) {                            // first group with rows: it fixes the key width
+            aid_bits = gi.aid_bits;
+            if (!hashed_reduce_supported(aid_bits)) { fallback = true; break; }      // keys too wide for the hash path
+            mix = make_key_mix(aid_bits);
+        } else if (gi.aid_bits > aid_bits) { fallback = true; break; }
+        ctx->info.aid_bits = aid_bits;                  // keys of every group are made with that width
         for (int k = 0; k < n_specs; ++k) {
             PartsAccum& a = acc[k];
             ExpandPlan* pl = make_plan(ctx, &specs[k], false);
+            cov_trace(ctx, "parts:   window");
             struct PlanGuard { ExpandPlan* p; ~PlanGuard() { delete p; } } plan_guard{pl};
             if (!a.started) {
                 a.started = true;
@@ -1255,37 +1259,60 @@ void count_parts_impl(ottocov_ctx* ctx, int n_parts, const int32_t* const* sessi
                 BitField rf[1] = {{mix.kb - a.bb + a.full.bits[0], mix.kb}};
                 a.rest = make_pass_list(rf, 1);
                 a.n_digits = 1u << a.full.bits[0];
+                a.rb = hashed_range_buckets((int64_t)P_est, a.bb);
+                a.n_ranges = hashed_n_ranges(a.bb, a.rb);
                 a.cursor.alloc(ctx, (size_t)n_groups * RS_RADIX);
-                a.reg.alloc(ctx, (size_t)n_groups * 2 * RS_RADIX);
-                a.ghist.alloc(ctx, (size_t)a.rest.n * RS_RADIX);
+                a.reg.alloc(ctx, (size_t)n_groups * 3 * RS_RADIX);
+                a.ghist.alloc(ctx, (size_t)n_groups * a.rest.n * RS_RADIX);
                 a.ctr.alloc(ctx, 2);
                 CUDA_CHECK(cudaMemsetAsync(a.cursor.p, 0, (size_t)n_groups * RS_RADIX * sizeof(unsigned long long), ctx->stream));
-                CUDA_CHECK(cudaMemsetAsync(a.ghist.p, 0, (size_t)a.rest.n * RS_RADIX * sizeof(u64), ctx->stream));
+                CUDA_CHECK(cudaMemsetAsync(a.ghist.p, 0, (size_t)n_groups * a.rest.n * RS_RADIX * sizeof(u64), ctx->stream));
                 CUDA_CHECK(cudaMemsetAsync(a.ctr.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
+                a.bufs.assign(n_groups, nullptr); a.sorted.assign(n_groups, nullptr); a.bounds.assign(n_groups, nullptr);
+                a.n_g.assign(n_groups, 0);
             }
             if (pl->sym != a.sym) COV_THROW(OTTOCOV_ERR_CUDA, "inconsistent symmetric choice across groups");
             a.n_pairs += pl->sym ? 2 * pl->P : pl->P;
             const u64 capg = ((((u64)((double)pl->P / a.n_digits * (1.0 + fuse_slack_pct() / 100.0)) + 4096) + 1) & ~1ull);
-            a.cap.resize(n_groups, 0);
-            a.bufs.resize(n_groups, nullptr);
             if (pl->P == 0) continue;
-            a.cap[g] = capg;
             a.bufs[g] = (u64*)cov_alloc(ctx, (size_t)a.n_digits * capg * 8);
+            a.n_g[g] = pl->P;
             a.P_total += pl->P;
-            u64* reg_base = a.reg.p + (size_t)g * 2 * RS_RADIX;
-            DevBuf<u64> tmp_off(ctx, RS_RADIX);
-            COV_LAUNCH(ctx, OTTOCOV_K_MISC, 0, region_table_kernel, 1, RS_RADIX, 0, reg_base, reg_base + RS_RADIX, tmp_off.p,
+            u64* reg_base = a.reg.p + (size_t)g * 3 * RS_RADIX;
+            u64* reg_off = reg_base + 2 * RS_RADIX;
+            COV_LAUNCH(ctx, OTTOCOV_K_MISC, 0, region_table_kernel, 1, RS_RADIX, 0, reg_base, reg_base + RS_RADIX, reg_off,
                        reinterpret_cast<u64>(a.bufs[g]), capg, (const unsigned long long*)nullptr, (u64)0, 0u, a.n_digits);
+            u64* ghist_g = a.ghist.p + (size_t)g * a.rest.n * RS_RADIX;
             ScatterArgs sa;
             sa.reg_base = reg_base; sa.reg_cap = reg_base + RS_RADIX; sa.cursor = a.cursor.p + (size_t)g * RS_RADIX;
             sa.flags = reinterpret_cast<u32*>(a.ctr.p + 1);
             sa.sh1 = a.full.shift[0]; sa.sub_bits = a.full.bits[0]; sa.n_digits = a.n_digits; sa.d_lo = 0; sa.d_hi = a.n_digits;
             sa.n_dest = 0;
-            expand_scatter_all(ctx, pl, mix, a.rest, a.ghist.p, sa);
+            expand_scatter_all(ctx, pl, mix, a.rest, ghist_g, sa);
+            cov_trace(ctx, "parts:   expansion + first pass");
+            // the group's remaining passes right away, behind the copy of the next groups: afterwards its keys sit sorted
+            // by bucket at the start of its region buffer, with the table of bucket-range boundaries next to them
+            const u32* abort_flag = reinterpret_cast<const u32*>(a.ctr.p + 1);
+            u64* sk = a.bufs[g];
+            u64* ska = (u64*)cov_alloc(ctx, (size_t)pl->P * 8);
+            u32* v = nullptr; u32* va = nullptr;
+            try {
+                radix_sort_passes(ctx, sk, ska, v, va, (int64_t)pl->P, a.rest, ghist_g,
+                                  reinterpret_cast<const u64*>(a.cursor.p + (size_t)g * RS_RADIX), reg_off, 1, (int)a.n_digits, abort_flag);
+            } catch (...) { dev_free(ctx, sk == a.bufs[g] ? ska : sk); throw; }
+            if (sk == a.bufs[g]) dev_free(ctx, ska);
+            else { dev_free(ctx, a.bufs[g]); a.bufs[g] = sk; }            // result landed in the second buffer: keep that one
+            a.sorted[g] = sk;
+            a.bounds[g] = (u32*)cov_alloc(ctx, (size_t)(a.n_ranges + 1) * 4);
+            hashed_range_bounds(ctx, sk, (int64_t)pl->P, mix.kb - a.bb, a.rb, a.n_ranges, a.bounds[g], abort_flag);
         }
+        cov_trace(ctx, "parts: group done (load, window, expansion, passes, bounds)");
     }
-    total.aid_max = mm[0];
-    total.aid_bits = aid_bits;
+    for (int g = 0; g < n_groups; ++g)                  // a group skipped by a fallback: its runs must still be on their way
+        if (!e_run[g]) enqueue_runs(g);
+    ctx->h2d_bytes_last = h2d;
+    total.aid_max = aid_max;
+    total.aid_bits = aid_bits ? aid_bits : 1;
 
     // ---- remaining passes + hash reduce per kind, over the regions of all groups -------------------------------------------
     if (!fallback) {
@@ -1294,56 +1321,53 @@ void count_parts_impl(ottocov_ctx* ctx, int n_parts, const int32_t* const* sessi
             memset(&ctx->last_count, 0, sizeof(ctx->last_count));
             ctx->last_count.n_pairs = (int64_t)a.n_pairs;
             if (!a.started || a.P_total == 0) { tables_out[k] = make_empty_table(aid_bits); continue; }
-            // one array of n keys for the ping-pong of the passes; region offsets are taken relative to it (mod 2^64)
-            DevBuf<u64> base(ctx, (size_t)a.P_total), alt(ctx, (size_t)a.P_total);
-            std::vector<u64> h_off((size_t)n_groups * a.n_digits);
+            // every group is bucket-sorted already: count the bucket ranges over all of them
+            std::vector<const u64*> kp;
+            std::vector<const u32*> bp;
             for (int g = 0; g < n_groups; ++g)
-                for (u32 d = 0; d < a.n_digits; ++d)
-                    h_off[(size_t)g * a.n_digits + d] =
-                        a.bufs[g] ? (u64)((reinterpret_cast<int64_t>(a.bufs[g]) - reinterpret_cast<int64_t>(base.p)) / 8 +
-                                          (int64_t)((u64)d * a.cap[g])) : 0ull;      // signed distance, stored mod 2^64
-            DevBuf<u64> seg_off(ctx, h_off.size()), seg_cnt(ctx, h_off.size());
-            CUDA_CHECK(cudaMemcpyAsync(seg_off.p, h_off.data(), h_off.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-            CUDA_CHECK(cudaStreamSynchronize(ctx->stream));          // h_off is a local vector
-            for (int g = 0; g < n_groups; ++g)                        // [g][RS_RADIX] counters -> dense [g][n_digits]
-                CUDA_CHECK(cudaMemcpyAsync(seg_cnt.p + (size_t)g * a.n_digits, a.cursor.p + (size_t)g * RS_RADIX,
-                                           a.n_digits * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-            HashPre pre;
-            pre.bb = a.bb; pre.first_bits = a.full.bits[0]; pre.seg_cnt = seg_cnt.p; pre.seg_off = seg_off.p;
-            pre.n_a = n_groups; pre.n_b = (int)a.n_digits; pre.ctr = a.ctr.p;
-            int passes = 0;
+                if (a.sorted[g]) { kp.push_back(a.sorted[g]); bp.push_back(a.bounds[g]); }
+            const int passes = 1 + a.rest.n;
             try {
-                tables_out[k] = hashed_reduce(ctx, base.p, alt.p, (int64_t)a.P_total, mix, a.user_min, a.sym, a.sym, &passes,
-                                              a.ghist.p, &pre);
+                tables_out[k] = hashed_reduce_groups(ctx, kp.data(), bp.data(), (int)kp.size(), (int64_t)a.P_total, a.bb, a.rb, mix,
+                                                     a.user_min, a.sym, a.sym, a.ctr.p);
             } catch (const FusedOverflow&) {
-                fallback = true;                                      // a hot pair outgrew a region: plain path below
+                fallback = true;                                      // a hot pair outgrew a region or a table: plain path below
                 break;
             }
+            cov_trace(ctx, "parts: reduce over all groups + survivors' sort");
             ctx->last_count.sort_passes = passes;
             ctx->last_count.n_chunks = n_groups;
             ctx->last_count.fused = 1;
             ctx->last_count.h2d_bytes = ctx->h2d_bytes_last;
             ctx->last_count.n_unique = tables_out[k]->n;
             for (u64*& b : a.bufs) { dev_free(ctx, b); b = nullptr; }
+            for (u32*& b : a.bounds) { dev_free(ctx, b); b = nullptr; }
         }
     }
     if (fallback) {
         // the columns are all on the device by now (or will be: the main stream waits for the last copy)
         for (int k = 0; k < n_specs; ++k)
             if (tables_out[k]) { dev_free(ctx, tables_out[k]->keys); dev_free(ctx, tables_out[k]->count); delete tables_out[k]; tables_out[k] = nullptr; }
-        for (auto& a : acc) for (u64*& b : a.bufs) { dev_free(ctx, b); b = nullptr; }
+        for (auto& a : acc) { for (u64*& b : a.bufs) { dev_free(ctx, b); b = nullptr; } for (u32*& b : a.bounds) { dev_free(ctx, b); b = nullptr; } }
         CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, e_grp[n_groups - 1], 0));
         if (rle_on)                                     // (re-)materialise every run-length encoded session column
             for (size_t k = 0; k < rle.size(); ++k)
                 if (rle[k]->n_runs > 0)
                     COV_LAUNCH(ctx, OTTOCOV_K_LOAD, 4.0 * rle[k]->rows + 8.0 * rle[k]->n_runs, rle_expand_kernel,
-                               (unsigned)ceil_div64(rle[k]->n_runs, 256), 256, 0, d_runs.p + task_slot[k] * 2, rle[k]->n_runs,
+                               (unsigned)ceil_div64(rle[k]->n_runs, 256), 256, 0, (const u32*)rle[k]->out, rle[k]->n_runs,
                                rle[k]->rows, d_session.p + task_row0[k]);
         load_events_impl(ctx, d_session.p, d_aid.p, d_ts.p, d_type.p, N, OTTOCOV_DEVICE);
         total = ctx->info;
         for (int k = 0; k < n_specs; ++k) tables_out[k] = count_impl(ctx, &specs[k]);
     }
     free_events(ctx);
+    if (trace_on) {
+        float ms = 0.f;
+        cudaEventSynchronize(tr_b);
+        cudaEventElapsedTime(&ms, tr_a, tr_b);
+        fprintf(stderr, "[trace] parts: the copy stream was busy for %.3f ms (%.1f GB/s)\n", ms, (double)h2d / ms / 1e6);
+        cudaEventDestroy(tr_a); cudaEventDestroy(tr_b);
+    }
     ctx->last_count.h2d_bytes = ctx->h2d_bytes_last;
     ctx->info = total;
     ctx->info_only = true;

@@ -271,6 +271,66 @@ hash_reduce_kernel(const u64* __restrict__ keys, int64_t n, int rem_bits, KeyMix
                          out_cap, flags);
 }
 
+// ---- the same reduce over SEVERAL bucket-sorted arrays (streamed ingest, expand.cu::count_parts_impl) ----------------
+// ottocov_count_parts buckets every group of parts on its own while the next group is still crossing PCIe, so when
+// the last byte has arrived there are G arrays, each sorted by the 21-bit bucket id, and all that is left is the
+// counting.  A CTA owns a RANGE of `rb` consecutive buckets (~2048 keys in total over the groups); a per-group table
+// of range boundaries (hr_range_bounds_kernel, built right after the group's last pass) tells it which slice of every
+// array is its own, so every bucket it counts is complete and the tile-edge logic of hash_reduce_kernel is not needed.
+constexpr int HR_MAX_GROUPS = 16;
+struct HrGroups {
+    const u64* keys[HR_MAX_GROUPS];       // bucket-sorted keys of group g
+    const u32* bounds[HR_MAX_GROUPS];     // [n_ranges + 1] first key of every bucket range in that array
+    int n_groups;
+};
+
+__global__ void __launch_bounds__(256) hr_fill_u32_kernel(u32* p, int64_t n, u32 v) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// bounds[r] = first index whose bucket range is >= r (bounds pre-filled with n); empty ranges get their successor's start
+__global__ void __launch_bounds__(256) hr_range_bounds_kernel(const u64* __restrict__ keys, int64_t n, int rem_bits, u32 rb,
+                                                              u32* __restrict__ bounds, const u32* __restrict__ abort_flag) {
+    if (abort_flag && (*abort_flag & HR_FLAG_FUSED_OVERFLOW)) return;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u32 r = (u32)((keys[i] >> rem_bits) / rb);
+    const int64_t first = (i == 0) ? 0 : (int64_t)((keys[i - 1] >> rem_bits) / rb) + 1;
+    for (int64_t q = first; q <= (int64_t)r; ++q) bounds[q] = (u32)i;       // usually one iteration, none inside a range
+}
+
+template <bool SYM, bool PACKED>
+__global__ void __launch_bounds__(HR_THREADS, PACKED ? OTTOCOV_HR_MINB : 2)
+hash_reduce_ranges_kernel(HrGroups grp, int rem_bits, u32 rb, KeyMix mix, u32 min_count, int mirror,
+                          u64* __restrict__ out_keys, u32* __restrict__ out_count, unsigned long long* __restrict__ out_n,
+                          u64 out_cap, u32* __restrict__ flags) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    u64* s_key = reinterpret_cast<u64*>(s_raw);                              // [HR_CAP]
+    u32* s_cnt = reinterpret_cast<u32*>(s_key + HR_CAP);                     // [HR_CAP] (!PACKED)
+    u32* s_scan = s_cnt + (PACKED ? 0 : HR_CAP);                             // [HR_THREADS / 32 + 1]
+    __shared__ unsigned long long s_base;
+    __shared__ u32 s_over;
+    if (*flags & HR_FLAG_FUSED_OVERFLOW) return;
+    const int tid = threadIdx.x;
+    const u64 r = blockIdx.x;
+    const u64 base = PACKED ? ((r * rb) << rem_bits) : 0ull;               // every key of the range is >= its first bucket
+    hr_clear<PACKED>(s_key, s_cnt);
+    if (tid == 0) s_over = 0;
+    __syncthreads();
+    u32 total = 0;
+    for (int g = 0; g < grp.n_groups; ++g) {
+        const u32 lo = grp.bounds[g][r], hi = grp.bounds[g][r + 1];
+        total += hi - lo;
+        const u64* __restrict__ k = grp.keys[g];
+        for (u32 i = lo + tid; i < hi; i += HR_THREADS) hr_insert<PACKED>(s_key, s_cnt, __ldcs(k + i), base, 1u, flags);
+    }
+    if (total > (u32)HR_CMASK / 2) { if (tid == 0) atomicOr(flags, 4u); return; }     // count field of the packed word (block-uniform)
+    __syncthreads();
+    hr_emit<SYM, PACKED>(s_key, s_cnt, s_scan, &s_base, &s_over, base, mix, min_count, mirror, out_keys, out_count, out_n,
+                         out_cap, flags);
+}
+
 __global__ void __launch_bounds__(256) unmix_kernel(u64* __restrict__ keys, int64_t n, KeyMix mix) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) keys[i] = key_mix_inv(mix, keys[i]);
@@ -433,6 +493,89 @@ ottocov_table* hashed_reduce(ottocov_ctx* ctx, u64* keys, u64* alt, int64_t n, c
         out->keys = ok2.take();
         out->count = oc2.take();
         out->n = rows;
+    } catch (...) {
+        dev_free(ctx, out->keys); dev_free(ctx, out->count);
+        delete out;
+        throw;
+    }
+    return out;
+}
+
+
+// ---- host side of the multi-array reduce ----------------------------------------------------------------------------------
+u32 hashed_range_buckets(int64_t n_est, int bb) {
+    const double per_bucket = (double)n_est / (double)((u64)1 << bb);
+    double rb = (double)HR_TILE / (per_bucket > 1e-9 ? per_bucket : 1e-9);
+    if (rb < 1.0) rb = 1.0;
+    if (rb > 4096.0) rb = 4096.0;
+    return (u32)(rb + 0.5);
+}
+
+int64_t hashed_n_ranges(int bb, u32 rb) { return (int64_t)((((u64)1 << bb) + rb - 1) / rb); }
+
+void hashed_range_bounds(ottocov_ctx* ctx, const u64* keys, int64_t n, int rem_bits, u32 rb, int64_t n_ranges, u32* bounds,
+                         const u32* abort_flag) {
+    COV_LAUNCH(ctx, OTTOCOV_K_MISC, 0, hr_fill_u32_kernel, (unsigned)ceil_div64(n_ranges + 1, 256), 256, 0, bounds, n_ranges + 1, (u32)n);
+    if (n > 0)
+        COV_LAUNCH(ctx, OTTOCOV_K_RLE, 8.0 * n, hr_range_bounds_kernel, (unsigned)ceil_div64(n, 256), 256, 0, keys, n, rem_bits, rb,
+                   bounds, abort_flag);
+}
+
+// keys[g]: n[g] mixed keys sorted by their bucket field [kb - bb, kb); bounds[g]: hashed_range_bounds of that array.
+// ctr: device [2] (rows, flags) zeroed before the keys were made (HR_FLAG_FUSED_OVERFLOW may be set by their writer).
+// Throws FusedOverflow when any flag is raised (the caller owns the fallback: it still has the events).
+ottocov_table* hashed_reduce_groups(ottocov_ctx* ctx, const u64* const* keys, const u32* const* bounds, int n_groups,
+                                    int64_t n_total, int bb, u32 rb, const KeyMix& mix, u32 min_count, bool sym, bool mirror,
+                                    unsigned long long* ctr) {
+    if (n_groups < 1 || n_groups > HR_MAX_GROUPS) COV_THROW(OTTOCOV_ERR_ARG, "1..%d bucket-sorted arrays", HR_MAX_GROUPS);
+    ottocov_table* out = new ottocov_table();
+    out->aid_bits = mix.ab;
+    if (min_count < 1) min_count = 1;
+    try {
+        static int no_packed = -1;
+        if (no_packed < 0) { const char* g = getenv("OTTOCOV_HR_NO_PACKED"); no_packed = (g && atoi(g)) ? 1 : 0; }
+        const int rem_bits = mix.kb - bb;
+        int span_bits = 0;
+        while (((u64)1 << span_bits) < rb) ++span_bits;
+        const bool packed = (mix.kb <= HR_TAG_BITS || rem_bits + span_bits <= HR_TAG_BITS) && !no_packed;
+        const int64_t n_ranges = hashed_n_ranges(bb, rb);
+        const u64 cap = (u64)(sym ? 2 : 1) * ((u64)n_total / min_count) + 1024;
+        DevBuf<u64> ok(ctx, cap);
+        DevBuf<u32> oc(ctx, cap);
+        HrGroups grp;
+        memset(&grp, 0, sizeof(grp));
+        grp.n_groups = n_groups;
+        for (int g = 0; g < n_groups; ++g) { grp.keys[g] = keys[g]; grp.bounds[g] = bounds[g]; }
+        u32* flags = reinterpret_cast<u32*>(ctr + 1);
+#define HRG_LAUNCH(SYM_, PACKED_)                                                                                      \
+        do {                                                                                                           \
+            auto kern = hash_reduce_ranges_kernel<SYM_, PACKED_>;                                                      \
+            cov_func_smem(ctx, (const void*)kern, hr_smem_bytes(PACKED_));                                             \
+            COV_LAUNCH(ctx, OTTOCOV_K_RLE, 8.0 * n_total, kern, (unsigned)n_ranges, HR_THREADS, hr_smem_bytes(PACKED_), grp, \
+                       rem_bits, rb, mix, min_count, (SYM_ && mirror) ? 1 : 0, ok.p, oc.p, ctr, cap, flags);           \
+        } while (0)
+        if (sym) { if (packed) HRG_LAUNCH(true, true); else HRG_LAUNCH(true, false); }
+        else { if (packed) HRG_LAUNCH(false, true); else HRG_LAUNCH(false, false); }
+#undef HRG_LAUNCH
+        unsigned long long h[2];
+        cov_readback(ctx, h, ctr, sizeof(h));
+        if ((h[1] & 0xFFFFFFFFull) != 0) {
+            if (getenv("OTTOCOV_TRACE")) fprintf(stderr, "[trace] hashed_reduce_groups: flags 0x%llx -> fallback\n", h[1] & 0xFFFFFFFFull);
+            throw FusedOverflow{};
+        }
+        const int64_t rows = (int64_t)h[0];
+        ctx->stats[OTTOCOV_K_RLE].algo_bytes += 12.0 * (double)rows;
+        if (rows == 0) return out;
+        BitField full[2] = {{0, mix.ab}, {32, 32 + mix.ab}};
+        DevBuf<u64> ok2(ctx, rows);
+        DevBuf<u32> oc2(ctx, rows);
+        u64* sk = ok.p; u64* ska = ok2.p; u32* sv = oc.p; u32* sva = oc2.p;
+        radix_sort_pairs(ctx, sk, ska, sv, sva, rows, full, 2);
+        if (sk != ok2.p) {
+            CUDA_CHECK(cudaMemcpyAsync(ok2.p, sk, rows * sizeof(u64), cudaMemcpyDeviceToDevice, ctx->stream));
+            CUDA_CHECK(cudaMemcpyAsync(oc2.p, sv, rows * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        out->keys = ok2.take(); out->count = oc2.take(); out->n = rows;
     } catch (...) {
         dev_free(ctx, out->keys); dev_free(ctx, out->count);
         delete out;

@@ -343,6 +343,14 @@ struct HashPre {
 };
 ottocov_table* hashed_reduce(ottocov_ctx* ctx, u64* keys, u64* alt, int64_t n, const KeyMix& mix, u32 min_count,
                              bool sym, bool mirror, int* passes_out, u64* pre_hist = nullptr, const HashPre* pre = nullptr);
+// Reduce over several bucket-sorted arrays (streamed ingest): see hash_reduce.cu, "the same reduce over SEVERAL ...".
+u32 hashed_range_buckets(int64_t n_est, int bb);                 // buckets per CTA so that a CTA counts ~2048 keys
+int64_t hashed_n_ranges(int bb, u32 rb);
+void hashed_range_bounds(ottocov_ctx* ctx, const u64* keys, int64_t n, int rem_bits, u32 rb, int64_t n_ranges, u32* bounds,
+                         const u32* abort_flag);
+ottocov_table* hashed_reduce_groups(ottocov_ctx* ctx, const u64* const* keys, const u32* const* bounds, int n_groups,
+                                    int64_t n_total, int bb, u32 rb, const KeyMix& mix, u32 min_count, bool sym, bool mirror,
+                                    unsigned long long* ctr);
 // plain keys (optionally with a destination stamp in bits 56..63) -> mixed keys, in place; also fills ghist
 // (device, [pl.n][RS_RADIX]) with the digit counts of the passes in pl (hashed_reduce's pre_hist)
 void mix_keys_inplace(ottocov_ctx* ctx, u64* keys, int64_t n, const KeyMix& mix, bool strip_dest, const PassList& pl,

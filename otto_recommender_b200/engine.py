@@ -24,6 +24,13 @@ def _as_col(x, np_dtype, torch_dtype_name):
     """-> (pointer, where, keepalive).  A column wider than its target type is range-checked before it is narrowed:
     the C side only ever sees int32 / int8 values, so raw OTTO millisecond timestamps (~1.66e12) or 64-bit session
     ids would otherwise wrap silently.  `ts` must be in SECONDS, as etl/jsonl_to_parquet.py:28 writes it."""
+    if _is_torch(x):
+        import torch
+        dt = getattr(torch, torch_dtype_name)
+        if x.dtype == dt and x.is_contiguous():                 # the common case: nothing to convert, nothing to check
+            return x.data_ptr(), (_lib.DEVICE if x.is_cuda else _lib.HOST), x
+    elif isinstance(x, np.ndarray) and x.dtype == np_dtype and x.flags.c_contiguous:
+        return x.ctypes.data, _lib.HOST, x
     info = np.iinfo(np_dtype)
     if _is_torch(x):
         import torch

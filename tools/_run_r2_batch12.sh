@@ -1,0 +1,21 @@
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_dropin.py -m gpu -q -x --timeout 600 -k "count_parts or fused_population or cli_three" > gpurun_out/r2b12_pytest.log 2>&1; tail -3 gpurun_out/r2b12_pytest.log
+for W in cooc all5; do
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --workload $W > gpurun_out/r2b12_bench_$W.log 2> gpurun_out/r2b12_bench_$W.err; tail -2 gpurun_out/r2b12_bench_$W.err | cut -c1-300; python tools/show_bench.py gpurun_out/r2b12_bench_$W.log > gpurun_out/r2b12_show_$W.txt; head -1 gpurun_out/r2b12_show_$W.txt
+done
+OTTOCOV_TRACE=1 timeout 300 python - <<'PY' 2>&1 | grep -E "trace|e2e" | tail -60
+import sys, time, torch
+sys.path.insert(0, '.')
+from otto_recommender_b200 import Engine
+from otto_recommender_b200.synth import SynthSpec, generate
+d = generate(SynthSpec(n_sessions=12_900_000, n_aids=1_800_000, seed=42), 'cuda')
+host = [d[k].cpu().pin_memory() for k in ('session','aid','ts','type')]
+del d; torch.cuda.empty_cache()
+eng = Engine(0)
+parts = Engine.split_at_sessions(*host, 64)
+for i in range(3):
+    torch.cuda.synchronize(); t0=time.perf_counter()
+    tabs = eng.count_parts(parts, ['click_to_click'], [10])
+    torch.cuda.synchronize(); print('e2e count_parts ms', (time.perf_counter()-t0)*1e3, file=sys.stderr)
+    for t in tabs: t.free()
+PY

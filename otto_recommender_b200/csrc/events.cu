@@ -142,6 +142,41 @@ struct SplitByType {
     }
 };
 
+// The split of rows that are (optimistically) already in (session, ts) order, with the loader's range / order statistics
+// accumulated while the rows are read anyway (scan.cuh, `Acc`): saves the separate statistics pass over all four columns.
+struct EvAcc { int tmin, tmax, amax; unsigned bad; };      // bad: bit 0 = a row out of order, bit 1 = a negative aid
+struct SplitSortedStats : SplitByType<true> {
+    typedef EvAcc Acc;
+    EvStats* st;
+    int64_t n_rows;
+    __device__ void acc_init(Acc& a) const { a.tmin = 2147483647; a.tmax = -2147483647 - 1; a.amax = -2147483647 - 1; a.bad = 0; }
+    __device__ u64 value(int64_t i, Acc& a) const {
+        const int s = session[i], t = ts[i], ai = (int)aid[i];
+        a.tmin = min(a.tmin, t); a.tmax = max(a.tmax, t); a.amax = max(a.amax, ai);
+        if (ai < 0) a.bad |= 2u;
+        if (i > 0) {
+            const int ps = session[i - 1], pt = ts[i - 1];
+            if (ps > s || (ps == s && pt > t)) a.bad |= 1u;
+        } else st->smin = s;                                   // sorted rows: the session range sits at the two ends
+        if (i == n_rows - 1) st->smax = s;
+        return keep(i) ? (1ull << (21 * (int)type[i])) : 0ull;
+    }
+    __device__ void acc_flush(Acc& a) const {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a.tmin = min(a.tmin, __shfl_xor_sync(0xffffffffu, a.tmin, o));
+            a.tmax = max(a.tmax, __shfl_xor_sync(0xffffffffu, a.tmax, o));
+            a.amax = max(a.amax, __shfl_xor_sync(0xffffffffu, a.amax, o));
+            a.bad |= __shfl_xor_sync(0xffffffffu, a.bad, o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(&st->tmin, a.tmin); atomicMax(&st->tmax, a.tmax); atomicMax(&st->amax, a.amax);
+            if (a.bad & 1u) atomicOr(&st->unsorted, 1u);
+            if (a.bad & 2u) atomicMin(&st->amin, -1);
+        }
+    }
+};
+
 static int bit_width_u64(u64 v) {
     int b = 0;
     while (v) { ++b; v >>= 1; }
@@ -367,6 +402,60 @@ void load_events_impl(ottocov_ctx* ctx, const int32_t* session, const int32_t* a
         ctx->end(OTTOCOV_K_LOAD, 13.0 * n);
         ctx->stats[OTTOCOV_K_LOAD].launches -= 1;   // copies, not kernels
         session = d_session.p; aid = d_aid.p; ts = d_ts.p; type = d_type.p;
+    }
+
+    // -- fast path: rows already in (session, ts) order (what the ETL writes).  One tiny pass over the type column gives
+    //    the per-type capacities; then ONE pass validates, finds the ranges, checks the order, removes duplicates and
+    //    splits by type.  If the rows turn out unordered (or an aid is negative) its outputs are dropped and the
+    //    general path below runs (and reports errors).
+    static int no_fused_loader = -1;
+    if (no_fused_loader < 0) { const char* e = getenv("OTTOCOV_NO_FUSED_LOADER"); no_fused_loader = (e && atoi(e)) ? 1 : 0; }
+    if (!no_fused_loader) {
+        DevBuf<unsigned long long> d_tc(ctx, 4);
+        CUDA_CHECK(cudaMemsetAsync(d_tc.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
+        COV_LAUNCH(ctx, OTTOCOV_K_LOAD, 1.0 * n, ev_type_count_kernel, (int)imin64(ceil_div64(n, 1024), (int64_t)ctx->num_sms * 8), 256, 0,
+                   type, n, d_tc.p);
+        unsigned long long tc[4];
+        cov_readback(ctx, tc, d_tc.p, sizeof(tc));
+        if (tc[3]) COV_THROW(OTTOCOV_ERR_DATA, "event type outside {0,1,2}");
+        DevBuf<u64> f_skey[3];
+        DevBuf<u32> f_aid[3], f_x0[3], f_x1[3];
+        DevBuf<EvStats> f_st(ctx, 1);
+        COV_LAUNCH(ctx, OTTOCOV_K_MISC, 0, ev_stats_init_kernel, 1, 1, 0, f_st.p);
+        SplitSortedStats f;
+        f.skey = nullptr; f.session = session; f.ts = ts; f.smin = INT32_MIN; f.tmin = INT32_MIN;
+        f.aid = reinterpret_cast<const u32*>(aid); f.type = type;
+        f.st = f_st.p; f.n_rows = n;
+        for (int t = 0; t < 3; ++t) {
+            const size_t cap = (size_t)tc[t];
+            f_skey[t].alloc(ctx, cap); f_aid[t].alloc(ctx, cap); f_x0[t].alloc(ctx, cap); f_x1[t].alloc(ctx, cap);
+            f.out[t].skey = f_skey[t].p; f.out[t].aid = f_aid[t].p;
+            f.out[t].xrank[0] = f_x0[t].p; f.out[t].xrank[1] = f_x1[t].p;
+            f.out[t].n = 0;
+        }
+        u64 ftot[3];
+        scan_apply(ctx, OTTOCOV_K_LOAD, f, n, ftot, 13.0 * n + 20.0 * n);
+        EvStats fs;
+        cov_readback(ctx, &fs, f_st.p, sizeof(fs));
+        if (!fs.unsorted && fs.amin >= 0) {
+            info.session_min = fs.smin; info.session_max = fs.smax;
+            info.ts_min = fs.tmin; info.ts_max = fs.tmax;
+            info.aid_max = fs.amax;
+            info.aid_bits = bit_width_u64((u64)fs.amax);
+            if (info.aid_bits == 0) info.aid_bits = 1;
+            info.was_sorted = 1;
+            for (int t = 0; t < 3; ++t) {
+                ctx->ta[t].skey = f_skey[t].take();
+                ctx->ta[t].aid = f_aid[t].take();
+                ctx->ta[t].xrank[0] = f_x0[t].take();
+                ctx->ta[t].xrank[1] = f_x1[t].take();
+                ctx->ta[t].n = (int64_t)ftot[t];
+                info.n_by_type[t] = (int64_t)ftot[t];
+            }
+            info.n_events = (int64_t)(ftot[0] + ftot[1] + ftot[2]);
+            ctx->loaded = true;
+            return;
+        }
     }
 
     // -- validate + ranges + sortedness ------------------------------------------------------------

@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(256) window_fwd_kernel(const u64* __restrict__
     const u32 t = (u32)k;
     const u64 upper = (k & 0xFFFFFFFF00000000ull) | (u64)(t > 0xFFFFFFFFu - window ? 0xFFFFFFFFu : t + window);
     const u32 hi = upper_bound_fwd(key, (u32)n, (u32)j, upper);
-    lo_out[j] = (u32)j + 1u;
+    if (lo_out) lo_out[j] = (u32)j + 1u;          // the canonical expansion knows it: targets start right after the source
     cnt_out[j] = hi - (u32)j - 1u;
 }
 
@@ -145,7 +145,7 @@ struct WindowRecords {
         if (!v) return;
         const u64 r = pre[1];
         rec_src[r] = (u32)j;
-        rec_lo[r] = lo[j];
+        if (rec_lo) rec_lo[r] = lo[j];            // symmetric kinds: lo == src + 1, neither stored nor re-read
         rec_off[r] = pre[0];
     }
 };
@@ -205,7 +205,7 @@ __device__ __forceinline__ u32 stage_tile_records(const u32* __restrict__ rec_sr
         const u32 r = r0 + j;
         const u64 off = rec_off[r];
         const u32 src = rec_src[r];
-        u32 lo = rec_lo[r];
+        u32 lo = rec_lo ? rec_lo[r] : src + 1u;
         u32 rel;
         if (off <= o0) { rel = 0; lo += (u32)(o0 - off); }   // only j == 0: skip outputs of earlier tiles
         else rel = (u32)(off - o0);
@@ -584,22 +584,25 @@ static ExpandPlan* make_plan(ottocov_ctx* ctx, const ottocov_spec* spec, bool di
             // owner at t, range event at t': the kind asks dt_lo <= t_tgt - t_src <= dt_hi; seen from a target owner the
             // range is -dt_hi <= t_src - t_tgt <= -dt_lo
             const int64_t r_lo = sg->swap ? -pl->dt_hi : pl->dt_lo, r_hi = sg->swap ? -pl->dt_lo : pl->dt_hi;
-            DevBuf<u32> lo(ctx, own.n), cnt(ctx, own.n);
+            DevBuf<u32> lo, cnt(ctx, own.n);
+            if (!pl->sym || pl->general) lo.alloc(ctx, own.n);
             if (pl->general)
                 COV_LAUNCH(ctx, OTTOCOV_K_WINDOW, 20.0 * own.n, window_range_kernel, (unsigned)ceil_div64(own.n, 256), 256, 0,
                            own.skey, own.n, rng.skey, (u32)rng.n, r_lo, r_hi, self_in ? 1 : 0, lo.p, cnt.p);
             else if (pl->sym)
-                COV_LAUNCH(ctx, OTTOCOV_K_WINDOW, 16.0 * own.n, window_fwd_kernel, (unsigned)ceil_div64(own.n, 256), 256, 0,
-                           own.skey, own.n, pl->W, lo.p, cnt.p);
+                COV_LAUNCH(ctx, OTTOCOV_K_WINDOW, 12.0 * own.n, window_fwd_kernel, (unsigned)ceil_div64(own.n, 256), 256, 0,
+                           own.skey, own.n, pl->W, (u32*)nullptr, cnt.p);
             else
                 COV_LAUNCH(ctx, OTTOCOV_K_WINDOW, 20.0 * own.n, window_kernel, (unsigned)ceil_div64(own.n, 256), 256, 0,
                            own.skey, xr, own.n, rng.skey, (u32)rng.n, pl->W, lo.p, cnt.p);
-            sg->rec_src.alloc(ctx, own.n); sg->rec_lo.alloc(ctx, own.n); sg->rec_off.alloc(ctx, own.n);
+            const bool implicit_lo = pl->sym && !pl->general;
+            sg->rec_src.alloc(ctx, own.n); sg->rec_off.alloc(ctx, own.n);
+            if (!implicit_lo) sg->rec_lo.alloc(ctx, own.n);
             WindowRecords f;
-            f.lo = lo.p; f.cnt = cnt.p;
-            f.rec_src = sg->rec_src.p; f.rec_lo = sg->rec_lo.p; f.rec_off = sg->rec_off.p;
+            f.lo = implicit_lo ? nullptr : lo.p; f.cnt = cnt.p;
+            f.rec_src = sg->rec_src.p; f.rec_lo = implicit_lo ? nullptr : sg->rec_lo.p; f.rec_off = sg->rec_off.p;
             u64 tot[2];
-            scan_apply(ctx, OTTOCOV_K_WINDOW, f, own.n, tot, 2.0 * 4.0 * own.n + 8.0 * own.n + 16.0 * own.n);
+            scan_apply(ctx, OTTOCOV_K_WINDOW, f, own.n, tot, (implicit_lo ? 4.0 : 8.0) * own.n + 8.0 * own.n + (implicit_lo ? 12.0 : 16.0) * own.n);
             sg->n_pairs = tot[0];
             sg->n_rec = tot[1];
             pl->P += tot[0];

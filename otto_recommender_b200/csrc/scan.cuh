@@ -39,6 +39,13 @@ constexpr u64 SC_VALUE_MASK = (1ull << 56) - 1;
 constexpr u64 SC_FLAG_AGG = 1ull << 62;
 constexpr u64 SC_FLAG_PREFIX = 2ull << 62;
 
+// Optional per-thread side accumulation while the elements are read (e.g. the loader's range / order statistics, which
+// would otherwise cost a pass of their own): a functor with a member type `Acc` supplies
+//     __device__ void acc_init(Acc&) const;   __device__ u64 value(int64_t i, Acc&) const;   __device__ void acc_flush(Acc&) const;
+// acc_flush is called by every thread right after its last value() (warp-reduce + a few atomics).
+template <class F, class = void> struct scan_has_acc { static constexpr bool value = false; };
+template <class F> struct scan_has_acc<F, decltype((void)sizeof(typename F::Acc))> { static constexpr bool value = true; };
+
 template <int NC>
 __device__ __forceinline__ void scan_unpack(u64 p, u64* c) {
     if (NC == 1) {
@@ -110,10 +117,21 @@ __global__ void __launch_bounds__(SCAN_THREADS, OTTOCOV_SCAN_MINB) scan_onepass_
     const int64_t base = tile * SCAN_TILE + (int64_t)warp * 32 * SCAN_ITEMS + lane;
     u64 v[SCAN_ITEMS], ex[SCAN_ITEMS];
     u64 carry = 0;      // packed running total of this warp's earlier rounds
+    if constexpr (scan_has_acc<F>::value) {
+        typename F::Acc acc;
+        f.acc_init(acc);
 #pragma unroll
-    for (int r = 0; r < SCAN_ITEMS; ++r) {
-        const int64_t i = base + r * 32;
-        v[r] = (i < n) ? f.value(i) : 0;
+        for (int r = 0; r < SCAN_ITEMS; ++r) {
+            const int64_t i = base + r * 32;
+            v[r] = (i < n) ? f.value(i, acc) : 0;
+        }
+        f.acc_flush(acc);
+    } else {
+#pragma unroll
+        for (int r = 0; r < SCAN_ITEMS; ++r) {
+            const int64_t i = base + r * 32;
+            v[r] = (i < n) ? f.value(i) : 0;
+        }
     }
 #pragma unroll
     for (int r = 0; r < SCAN_ITEMS; ++r) {

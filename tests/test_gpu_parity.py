@@ -630,12 +630,16 @@ def test_fused_first_pass_overflow_and_unfused_children():
     Both knobs are read once per process, so the cases run in child processes; same tables as the oracle."""
     import subprocess
     import sys
-    if os.environ.get("OTTOCOV_FUSE_SLACK_PCT") or os.environ.get("OTTOCOV_NO_FUSED_PASS"):
+    if os.environ.get("OTTOCOV_FUSE_SLACK_PCT") or os.environ.get("OTTOCOV_NO_FUSED_PASS") or os.environ.get("OTTOCOV_NO_FUSED_LOADER"):
         pytest.skip("already inside the child run")
-    for extra in ({"OTTOCOV_FUSE_SLACK_PCT": "-60"}, {"OTTOCOV_NO_FUSED_PASS": "1"}):
+    # (3) OTTOCOV_NO_FUSED_LOADER=1: the loader's general path (separate statistics pass) on inputs the fused
+    # validate+dedup+split pass would otherwise take.
+    for extra, sel in (({"OTTOCOV_FUSE_SLACK_PCT": "-60"}, "fused_child or hash_reduce_hot or hash_reduce_many"),
+                       ({"OTTOCOV_NO_FUSED_PASS": "1"}, "fused_child or hash_reduce_hot or hash_reduce_many"),
+                       ({"OTTOCOV_NO_FUSED_LOADER": "1"}, "golden_b1 or random_vs_oracle or edge_cases or errors_are_loud")):
         env = dict(os.environ, **extra)
         r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
-                            "-k", "fused_child or hash_reduce_hot or hash_reduce_many"],
+                            "-k", sel],
                            env=env, capture_output=True, text=True, timeout=900)
         assert r.returncode == 0, str(extra) + r.stdout[-3000:] + r.stderr[-2000:]
 

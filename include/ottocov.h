@@ -98,7 +98,8 @@ typedef struct {
     int64_t n_unique;        /* rows of the table it produced                                      */
     int32_t n_chunks;        /* pair-budget chunks it ran                                          */
     int32_t sort_passes;     /* distribution passes per chunk (a pass fused into the expansion counts) */
-    int32_t fused;           /* 1 = the first pass of the bucketed hash reduce ran inside the expansion     */
+    int32_t fused;           /* 1 = the first pass of the bucketed hash reduce ran inside the expansion;
+                              * 2 = likewise, and whole buckets were counted per CTA (one pass fewer)     */
     int32_t reserved;
     int64_t h2d_bytes;       /* ottocov_count_parts: bytes copied host -> device (the session column travels  */
                              /* run-length encoded when it compresses); 0 for the other calls                */

@@ -732,7 +732,9 @@ static bool fuse_enabled() {
 static void count_fused(ottocov_ctx* ctx, const ExpandPlan* pl, const KeyMix& mix, u64 budget, u32 min_count,
                         std::vector<ottocov_table*>& partials, ottocov_count_info& ci) {
     const u64 P = pl->P;
-    const int bb = hashed_bucket_bits((int64_t)P, mix.kb);
+    const int bb_big = hashed_big_bucket_bits((int64_t)P, mix.kb);      // whole-bucket reduce when it saves a pass
+    const bool big = bb_big > 0;
+    const int bb = big ? bb_big : hashed_bucket_bits((int64_t)P, mix.kb);
     BitField bucket_field[1] = {{mix.kb - bb, mix.kb}};
     const PassList full = make_pass_list(bucket_field, 1);
     BitField rest_field[1] = {{mix.kb - bb + full.bits[0], mix.kb}};
@@ -795,7 +797,7 @@ static void count_fused(ottocov_ctx* ctx, const ExpandPlan* pl, const KeyMix& mi
         if (!overflow && n_c > 0) {
             DevBuf<u64> alt(ctx, (size_t)n_c);
             HashPre pre;
-            pre.bb = bb; pre.first_bits = full.bits[0];
+            pre.bb = bb; pre.first_bits = full.bits[0]; pre.big = big;
             pre.seg_cnt = reinterpret_cast<const u64*>(cursor.p + d0); pre.n_a = 1; pre.n_b = (int)dc;
             pre.seg_off = reg_off + d0; pre.ctr = ctr.p;
             int passes = 0;
@@ -816,7 +818,7 @@ static void count_fused(ottocov_ctx* ctx, const ExpandPlan* pl, const KeyMix& mi
         exact = false;
         if (part) partials.push_back(part);
         ci.n_chunks += 1;
-        ci.fused = 1;
+        ci.fused = big ? 2 : 1;
         d0 += dc;
         cov_trace(ctx, "count: bucket passes + hash reduce");
     }

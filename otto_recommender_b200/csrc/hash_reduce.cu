@@ -51,7 +51,6 @@ constexpr int HR_IPT = 8;
 constexpr int HR_TILE = HR_THREADS * HR_IPT;     // 2048 keys per CTA (+ the tail of its last bucket)
 constexpr int HR_CAP_LOG2 = OTTOCOV_HR_CAP_LOG2;
 constexpr int HR_CAP = 1 << HR_CAP_LOG2;         // 4096 slots
-constexpr int HR_SPT = HR_CAP / HR_THREADS;      // slots per thread in the table scan
 constexpr int HR_XT = 4;                         // keys per thread per slice of a long bucket tail
 constexpr int HR_MAX_TAIL_ROUNDS = 1000;         // ~2 M keys: beyond that one CTA would serialise the reduce
 constexpr u64 HR_NONE = ~0ull;                   // empty slot / no key (mixed keys have <= 56 bits)
@@ -63,46 +62,45 @@ constexpr u64 HR_NONE = ~0ull;                   // empty slot / no key (mixed k
 constexpr int HR_CB = 22;
 constexpr int HR_TAG_BITS = 64 - HR_CB;
 constexpr u64 HR_CMASK = (1ull << HR_CB) - 1ull;
-static_assert(2 * HR_SPT <= 32, "two flag bits per scanned slot must fit one register");
 static_assert((u64)HR_TILE + ((u64)HR_MAX_TAIL_ROUNDS * HR_XT + 1) * HR_THREADS < HR_CMASK, "count field too narrow");
 
 // PACKED: s_key[slot] = tag << 22 | count (32 KB, 6 CTAs / SM).  Otherwise (keys too wide for a 42-bit tag):
 // s_key[slot] = mixed key, s_cnt[slot] = count (48 KB, 2+ CTAs / SM, two atomics for a new key).
-template <bool PACKED>
+template <bool PACKED, int CL2 = HR_CAP_LOG2>
 __device__ __forceinline__ void hr_insert(u64* s_key, u32* s_cnt, u64 h, u64 base, u32 times, u32* flags) {
     const u64 tag = h - base;
     if (PACKED && (tag >> HR_TAG_BITS)) { atomicOr(flags, 8u); return; }     // bucket span wider than the tag
-    u32 slot = (((u32)tag ^ (u32)(tag >> 32)) * 0x9E3779B1u) >> (32 - HR_CAP_LOG2);
+    u32 slot = (((u32)tag ^ (u32)(tag >> 32)) * 0x9E3779B1u) >> (32 - CL2);
 #pragma unroll 1
-    for (int probes = 0; probes < HR_CAP; ++probes) {
-        u64 cur = *reinterpret_cast<volatile u64*>(s_key + slot);
+    for (int probes = 0; probes < (1 << CL2); ++probes) {
         if (PACKED) {
-            if (cur == HR_NONE) {
-                cur = atomicCAS(reinterpret_cast<unsigned long long*>(s_key + slot), HR_NONE, (tag << HR_CB) | (u64)times);
-                if (cur == HR_NONE) return;                     // claimed and counted in one step
-            }
+            // CAS first, no look: most keys are new, and the shared-memory atomic unit is far from busy (23 % in ncu)
+            // while issue slots are what the kernel runs out of
+            const u64 cur = atomicCAS(reinterpret_cast<unsigned long long*>(s_key + slot), HR_NONE, (tag << HR_CB) | (u64)times);
+            if (cur == HR_NONE) return;                         // claimed and counted in one step
             if ((cur >> HR_CB) == tag) { atomicAdd(reinterpret_cast<u32*>(s_key + slot), times); return; }
         } else {
+            u64 cur = *reinterpret_cast<volatile u64*>(s_key + slot);
             if (cur == HR_NONE) {
                 cur = atomicCAS(reinterpret_cast<unsigned long long*>(s_key + slot), HR_NONE, tag);
                 if (cur == HR_NONE) cur = tag;                  // this thread claimed the slot
             }
             if (cur == tag) { atomicAdd(s_cnt + slot, times); return; }
         }
-        slot = (slot + 1) & (HR_CAP - 1);
+        slot = (slot + 1) & ((1 << CL2) - 1);
     }
     atomicOr(flags, 1u);                                   // table full: the host falls back to the full sort
 }
 
 // Keys past the tile end (the rest of the CTA's last bucket).  A long tail means a hot pair repeated many
 // times: when a whole warp holds one key, one lane adds 32 instead of 32 lanes queueing on one counter.
-template <bool PACKED>
+template <bool PACKED, int CL2 = HR_CAP_LOG2>
 __device__ __forceinline__ void hr_insert_tail(u64* s_key, u32* s_cnt, u64 h, u64 base, bool mine, u32* flags) {
     const u64 h0 = __shfl_sync(0xffffffffu, h, 0);
     if (__all_sync(0xffffffffu, mine && h == h0)) {
-        if ((threadIdx.x & 31) == 0) hr_insert<PACKED>(s_key, s_cnt, h0, base, 32u, flags);
+        if ((threadIdx.x & 31) == 0) hr_insert<PACKED, CL2>(s_key, s_cnt, h0, base, 32u, flags);
     } else if (mine) {
-        hr_insert<PACKED>(s_key, s_cnt, h, base, 1u, flags);
+        hr_insert<PACKED, CL2>(s_key, s_cnt, h, base, 1u, flags);
     }
 }
 
@@ -122,37 +120,48 @@ __device__ __forceinline__ bool hr_slot(const u64* s_key, const u32* s_cnt, int 
 // compare with the lowest count that could survive (half the threshold for a symmetric kind: a diagonal row
 // counts twice); only candidates are decoded and un-mixed.  Survivors are appended to the output with one global
 // atomic per CTA.  Returns false when the output buffer overflowed (flag raised; the caller gives up).
-template <bool SYM, bool PACKED>
+template <bool SYM, bool PACKED, int CL2 = HR_CAP_LOG2, int NT = HR_THREADS>
 __device__ __forceinline__ bool hr_emit(const u64* s_key, const u32* s_cnt, u32* s_scan, unsigned long long* s_base, u32* s_over,
                                         u64 base, const KeyMix& mix, u32 min_count, int mirror, u64* __restrict__ out_keys,
                                         u32* __restrict__ out_count, unsigned long long* __restrict__ out_n, u64 out_cap,
                                         u32* __restrict__ flags) {
+    constexpr int SPT = (1 << CL2) / NT;                   // slots per thread
+    static_assert(2 * SPT <= 32, "two flag bits per scanned slot must fit one register");
     const int tid = threadIdx.x;
     const u32 cand = SYM ? (min_count + 1u) / 2u : min_count;
-    u32 bits = 0, emit = 0;                                // two flag bits per slot: keep, also emit the mirrored row
+    // Pass 1, branch-free: which of this thread's slots hold a count that could survive.  Pass 2 decodes those only.
+    // (One loop doing both made every warp run the decode + un-mix for every slot index at which ANY of its lanes had
+    // a candidate -- most of them -- and that was the largest block of issued instructions in the kernel: ncu, round 2.)
+    u32 candm = 0;
 #pragma unroll
-    for (int q = 0; q < HR_SPT; ++q) {
-        const int j = tid + q * HR_THREADS;
+    for (int q = 0; q < SPT; ++q) {
+        const int j = tid + q * NT;
         const u32 c = PACKED ? (reinterpret_cast<const u32*>(s_key + j)[0] & (u32)HR_CMASK) : s_cnt[j];
-        if (c >= cand && (!PACKED || c != (u32)HR_CMASK) && c != 0u) {
-            u64 total = c;
-            bool diag = false;
-            if (SYM) {
-                u64 h; u32 c2;
-                hr_slot<PACKED>(s_key, s_cnt, j, base, &h, &c2);
-                const u64 plain = key_mix_inv(mix, h);
-                diag = (u32)(plain >> 32) == (u32)plain;
-                if (diag) total *= 2;                      // (a, a): both orders of each event pair
-            }
+        candm |= ((c >= cand && (!PACKED || c != (u32)HR_CMASK) && c != 0u) ? 1u : 0u) << q;
+    }
+    u32 bits = 0, emit = 0;                                // two flag bits per slot: keep, also emit the mirrored row
+    if (!SYM) {                                            // cand == min_count: every candidate survives
+#pragma unroll
+        for (int q = 0; q < SPT; ++q) bits |= ((candm >> q) & 1u) << (2 * q);
+        emit = __popc(candm);
+    } else {
+        while (candm) {
+            const int q = __ffs(candm) - 1;
+            candm &= candm - 1u;
+            u64 h; u32 c;
+            hr_slot<PACKED>(s_key, s_cnt, tid + q * NT, base, &h, &c);
+            const u64 plain = key_mix_inv(mix, h);
+            const bool diag = (u32)(plain >> 32) == (u32)plain;
+            const u64 total = diag ? 2ull * c : (u64)c;    // (a, a): both orders of each event pair
             if (total >= (u64)min_count) {
-                const bool two = SYM && mirror && !diag;
+                const bool two = mirror && !diag;
                 bits |= (two ? 3u : 1u) << (2 * q);
                 emit += two ? 2u : 1u;
             }
         }
     }
     u32 blk_total;
-    const u32 ex = block_exclusive_scan<u32, HR_THREADS>(emit, s_scan, &blk_total);
+    const u32 ex = block_exclusive_scan<u32, NT>(emit, s_scan, &blk_total);
     if (tid == 0) {
         unsigned long long b = 0;
         if (blk_total) {
@@ -168,7 +177,7 @@ __device__ __forceinline__ bool hr_emit(const u64* s_key, const u32* s_cnt, u32*
         const int q = (__ffs(bits) - 1) >> 1;
         const u32 f = (bits >> (2 * q)) & 3u;
         bits &= ~(3u << (2 * q));
-        const int j = tid + q * HR_THREADS;
+        const int j = tid + q * NT;
         u64 h; u32 c;
         hr_slot<PACKED>(s_key, s_cnt, j, base, &h, &c);
         const u64 plain = key_mix_inv(mix, h);
@@ -181,18 +190,18 @@ __device__ __forceinline__ bool hr_emit(const u64* s_key, const u32* s_cnt, u32*
     return true;
 }
 
-template <bool PACKED>
+template <bool PACKED, int CL2 = HR_CAP_LOG2, int NT = HR_THREADS>
 __device__ __forceinline__ void hr_clear(u64* s_key, u32* s_cnt) {
     const int tid = threadIdx.x;
     uint4* kv = reinterpret_cast<uint4*>(s_key);           // two slots per 128-bit store
     const uint4 ones = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
 #pragma unroll
-    for (int q = 0; q < HR_CAP / 2 / HR_THREADS; ++q) kv[tid + q * HR_THREADS] = ones;
+    for (int q = 0; q < (1 << CL2) / 2 / NT; ++q) kv[tid + q * NT] = ones;
     if (!PACKED) {
         uint4* cv = reinterpret_cast<uint4*>(s_cnt);
         const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-        for (int q = 0; q < HR_CAP / 4 / HR_THREADS; ++q) cv[tid + q * HR_THREADS] = zero;
+        for (int q = 0; q < (1 << CL2) / 4 / NT; ++q) cv[tid + q * NT] = zero;
     }
 }
 
@@ -331,6 +340,148 @@ hash_reduce_ranges_kernel(HrGroups grp, int rem_bits, u32 rb, KeyMix mix, u32 mi
                          out_cap, flags);
 }
 
+// ---- whole buckets (round 2): one distribution pass fewer ------------------------------------------------------------
+// The tile kernel above wants buckets of ~512 keys: 21 bucket bits for the headline's 742 M keys = the fused pass + TWO
+// more passes of 16 B/key each.  Here a CTA takes one WHOLE bucket of ~11 k keys -- 16 bucket bits = the fused pass + ONE
+// more.  The bucket's [lo, hi) comes from the bounds table the last pass wrote (radix_sort.cu, RsSegs), so there is no
+// tile-edge logic.
+//   * The keys are staged once in shared memory as 32-bit tags (the bits below the bucket id), each thread's keys in
+//     its own column: the keys of round 0 from the top of the column, the others from the bottom.
+//   * 2^round_bits rounds (0 or 1 bit): round r clears the 8192-slot table, counts the keys whose top remaining bit is
+//     r, and emits.  Half a bucket per round keeps the table half empty.
+//   * The insert loop is LANE-PERSISTENT: one probe per iteration, and a lane whose key is placed takes its next key in
+//     the same iteration.  (Measured with ncu on the first version, which called hr_insert once per key: 12 of 32 lanes
+//     active on average -- every key cost the warp the LONGEST probe chain among its 32 lanes -- and the kernel was
+//     bound by issued instructions, 236 per 32 keys; experiments/round2_variants/.)  Now the warp runs for the longest
+//     SUM of chains over a lane's ~11 keys, which is close to the average.
+// A bucket that does not fit the staging area (a hot pair repeated thousands of times) streams from HBM once per round.
+constexpr int HRB_THREADS = 512;
+constexpr int HRB_CAP_LOG2 = 13;                     // 8192 slots = 64 KB; + 48 KB of staged tags: 2 CTAs / SM
+constexpr int HRB_CAP = 1 << HRB_CAP_LOG2;
+constexpr int HRB_KPT = 24;
+constexpr int HRB_STAGE_KEYS = HRB_THREADS * HRB_KPT;  // 12288
+constexpr int HRB_MAX_REM_BITS = 31;                 // tags are 32-bit
+constexpr int HRB_MAX_ROUND_BITS = 1;
+
+// bounds[nb] = n; an entry no tile wrote (~0: empty bucket) takes the next written one to its right
+__global__ void __launch_bounds__(1024) hr_bounds_fix_kernel(u64* __restrict__ bounds, u32 nb, u64 n, const u32* __restrict__ flags) {
+    __shared__ u64 s_min[1024];
+    if (*flags & HR_FLAG_FUSED_OVERFLOW) return;
+    const u32 tid = threadIdx.x;
+    const u32 per = (nb + 1 + 1023) / 1024;
+    const u32 b0 = min(nb + 1, tid * per), b1 = min(nb + 1, b0 + per);
+    u64 m = HR_NONE;
+    for (u32 i = b1; i-- > b0;) {
+        const u64 v = (i == nb) ? n : bounds[i];
+        m = v < m ? v : m;
+    }
+    s_min[tid] = m;
+    __syncthreads();
+    if (tid == 0) {
+        u64 c = HR_NONE;
+        for (int t = 1023; t >= 0; --t) { const u64 x = s_min[t]; s_min[t] = c; c = x < c ? x : c; }
+    }
+    __syncthreads();
+    u64 c = s_min[tid];                                    // first written bound to the right of this thread's span
+    for (u32 i = b1; i-- > b0;) {
+        const u64 v = (i == nb) ? n : bounds[i];
+        if (v == HR_NONE) bounds[i] = c;
+        else { c = v; if (i == nb) bounds[i] = n; }
+    }
+}
+
+__device__ __forceinline__ u32 hrb_slot_of(u32 tag) { return (tag * 0x9E3779B1u) >> (32 - HRB_CAP_LOG2); }
+
+template <bool SYM>
+__global__ void __launch_bounds__(HRB_THREADS, 2)
+hash_reduce_buckets_kernel(const u64* __restrict__ keys, const u64* __restrict__ bounds, int rem_bits, int round_bits,
+                           KeyMix mix, u32 min_count, int mirror, u64* __restrict__ out_keys, u32* __restrict__ out_count,
+                           unsigned long long* __restrict__ out_n, u64 out_cap, u32* __restrict__ flags) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    u64* s_key = reinterpret_cast<u64*>(s_raw);                              // [HRB_CAP] packed words tag | count
+    u32* s_tags = reinterpret_cast<u32*>(s_key + HRB_CAP);                   // [HRB_KPT][HRB_THREADS]
+    u32* s_scan = s_tags + HRB_STAGE_KEYS;                                   // [HRB_THREADS / 32 + 1]
+    __shared__ unsigned long long s_base;
+    __shared__ u32 s_over;
+    if (*flags & HR_FLAG_FUSED_OVERFLOW) return;
+    const int tid = threadIdx.x;
+    const u64 lo = bounds[blockIdx.x], hi = bounds[blockIdx.x + 1];
+    if (hi <= lo) return;
+    const u64 nk = hi - lo;
+    if (nk >= (u64)HR_CMASK / 2) { if (tid == 0) atomicOr(flags, 4u); return; }      // count field of the packed word
+    const u64 base = (keys[lo] >> rem_bits) << rem_bits;                     // the bucket id: the same in every key
+    const u32 low_mask = (u32)((1ull << rem_bits) - 1ull);
+    const int rshift = rem_bits - round_bits;
+    const bool staged = nk <= (u64)HRB_STAGE_KEYS;
+    int n_front = 0, n_back = 0;                                             // this thread's keys of round 0 / round 1
+    if (staged) {
+        const u32 n32 = (u32)nk;
+        const u32* kp = reinterpret_cast<const u32*>(keys + lo + tid);      // low words only: the tag has <= 31 bits
+        u32* col = s_tags + tid;
+        u32 t[HRB_KPT];
+#pragma unroll
+        for (int j = 0; j < HRB_KPT; ++j)
+            t[j] = ((u32)(j * HRB_THREADS + tid) < n32) ? (__ldcs(kp + 2 * j * HRB_THREADS) & low_mask) : 0u;
+#pragma unroll
+        for (int j = 0; j < HRB_KPT; ++j) {
+            if ((u32)(j * HRB_THREADS + tid) < n32) {
+                const bool front = (t[j] >> rshift) == 0u;
+                col[(front ? n_front : HRB_KPT - 1 - n_back) * HRB_THREADS] = t[j];
+                n_front += front ? 1 : 0;
+                n_back += front ? 0 : 1;
+            }
+        }
+    }
+    if (tid == 0) s_over = 0;
+    for (int r = 0; r < (1 << round_bits); ++r) {
+        hr_clear<true, HRB_CAP_LOG2, HRB_THREADS>(s_key, nullptr);
+        __syncthreads();
+        if (staged) {
+            int left = r == 0 ? n_front : n_back;
+            int row = r == 0 ? 0 : HRB_KPT - 1;
+            const int step = r == 0 ? 1 : -1;
+            const u32* col = s_tags + tid;
+            bool active = left > 0;
+            u32 tag = active ? col[row * HRB_THREADS] : 0u;
+            u32 slot = hrb_slot_of(tag);
+            int probes = 0;
+            // the vote makes the warp reconverge at every iteration: without it the lanes that took different branches
+            // run the loop in separate groups, and the warp pays the SUM of their iterations
+            while (__any_sync(0xffffffffu, active)) {
+                if (active) {
+                    const u64 cur = atomicCAS(reinterpret_cast<unsigned long long*>(s_key + slot), HR_NONE, ((u64)tag << HR_CB) | 1ull);
+                    const bool match = (cur >> HR_CB) == (u64)tag;       // an empty slot's tag field is all ones: never a tag
+                    if (match) atomicAdd(reinterpret_cast<u32*>(s_key + slot), 1u);
+                    if (match || cur == HR_NONE) {                       // counted (or claimed and counted in one step)
+                        if (--left == 0) active = false;
+                        else {
+                            row += step;
+                            tag = col[row * HRB_THREADS];
+                            slot = hrb_slot_of(tag);
+                            probes = 0;
+                        }
+                    } else {
+                        slot = (slot + 1) & (HRB_CAP - 1);
+                        if (++probes >= HRB_CAP) { atomicOr(flags, 1u); active = false; }      // table full: the host falls back
+                    }
+                }
+            }
+        } else {
+            for (u64 i0 = lo; i0 < hi; i0 += HRB_THREADS) {                  // block-uniform trip count
+                const u64 i = i0 + (u64)tid;
+                const u64 t = (i < hi) ? (u64)((u32)__ldcs(keys + i) & low_mask) : HR_NONE;
+                const bool mine = (i < hi) && ((u32)t >> rshift) == (u32)r;
+                hr_insert_tail<true, HRB_CAP_LOG2>(s_key, nullptr, t, 0ull, mine, flags);
+            }
+        }
+        __syncthreads();
+        if (!hr_emit<SYM, true, HRB_CAP_LOG2, HRB_THREADS>(s_key, nullptr, s_scan, &s_base, &s_over, base, mix, min_count, mirror,
+                                                           out_keys, out_count, out_n, out_cap, flags))
+            return;
+        __syncthreads();                                                      // the next round clears the table
+    }
+}
+
 __global__ void __launch_bounds__(256) unmix_kernel(u64* __restrict__ keys, int64_t n, KeyMix mix) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) keys[i] = key_mix_inv(mix, keys[i]);
@@ -387,6 +538,37 @@ int hashed_bucket_bits(int64_t n, int kb) {
     return bb;
 }
 
+// Whole-bucket reduce: <= OTTOCOV_HRB_AVG (default 11500: the registers of a CTA hold 12288 keys, and a Poisson bucket of
+// 11500 stays below that by five sigma) keys per bucket on average.  Used when that takes fewer distribution passes
+// than the tile kernel's small buckets (OTTOCOV_HRB=0 turns it off, OTTOCOV_HRB=2 uses it wherever it can run: tests).
+static int64_t hrb_avg() {
+    static int64_t v = 0;
+    if (!v) { const char* e = getenv("OTTOCOV_HRB_AVG"); v = e ? atoll(e) : 11500; if (v < 16 || v > 11500) v = 11500; }
+    return v;
+}
+static int hrb_mode() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("OTTOCOV_HRB"); v = e ? atoi(e) : 1; if (v < 0 || v > 2) v = 1; }
+    return v;
+}
+static int hrb_round_bits() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("OTTOCOV_HRB_ROUND_BITS"); v = e ? atoi(e) : 1; if (v < 0 || v > HRB_MAX_ROUND_BITS) v = 1; }
+    return v;
+}
+int hashed_big_bucket_bits(int64_t n, int kb) {
+    const int mode = hrb_mode();
+    if (mode == 0) return 0;
+    int bb = 0;
+    while (bb < kb && (n >> bb) > hrb_avg()) ++bb;
+    if (bb <= RS_MAX_BITS || bb > 2 * RS_MAX_BITS) return 0;           // the fused pass + exactly one more
+    if (kb - bb > HRB_MAX_REM_BITS || kb - bb < hrb_round_bits()) return 0;
+    const int small = hashed_bucket_bits(n, kb);
+    const int p_small = (small + RS_MAX_BITS - 1) / RS_MAX_BITS;
+    if (mode == 1 && p_small <= 2) return 0;                             // no pass saved
+    return bb;
+}
+
 ottocov_table* hashed_reduce(ottocov_ctx* ctx, u64* keys, u64* alt, int64_t n, const KeyMix& mix, u32 min_count,
                              bool sym, bool mirror, int* passes_out, u64* pre_hist, const HashPre* pre) {
     ottocov_table* out = new ottocov_table();
@@ -409,13 +591,23 @@ ottocov_table* hashed_reduce(ottocov_ctx* ctx, u64* keys, u64* alt, int64_t n, c
         PassList pl = make_pass_list(bucket_field, 1);
         u64* k = keys; u64* ka = alt; u32* v = nullptr; u32* va = nullptr;
         int passes;
+        const bool big = pre && pre->big;
+        DevBuf<u64> bucket_bounds;
+        size_t n_buckets = 0;
         if (pre) {                      // pass 0 was done by whoever wrote the keys: they sit in its digit regions
             const int b0 = pre->first_bits > 0 ? pre->first_bits : (pl.n > 0 ? pl.bits[0] : 0);
             BitField rest_field[1] = {{rem_bits + b0, mix.kb}};
             const PassList rest = make_pass_list(rest_field, 1);
             if (rest.n < 1) COV_THROW(OTTOCOV_ERR_ARG, "fused first pass needs at least one more pass");
+            if (big) {
+                if (rest.n != 1 || rem_bits > HRB_MAX_REM_BITS || !pre->ctr)
+                    COV_THROW(OTTOCOV_ERR_ARG, "whole-bucket reduce: one pass after the fused one, <= 31 key bits below the bucket");
+                n_buckets = ((size_t)1 << rest.bits[0]) * (size_t)pre->n_b;
+                bucket_bounds.alloc(ctx, n_buckets + 1);
+                CUDA_CHECK(cudaMemsetAsync(bucket_bounds.p, 0xFF, (n_buckets + 1) * sizeof(u64), ctx->stream));
+            }
             passes = 1 + radix_sort_passes(ctx, k, ka, v, va, n, rest, pre_hist, pre->seg_cnt, pre->seg_off, pre->n_a, pre->n_b,
-                                           pre->ctr ? reinterpret_cast<const u32*>(pre->ctr + 1) : nullptr);
+                                           pre->ctr ? reinterpret_cast<const u32*>(pre->ctr + 1) : nullptr, bucket_bounds.p);
         } else {
             passes = radix_sort_passes(ctx, k, ka, v, va, n, pl, pre_hist);
         }
@@ -437,6 +629,22 @@ ottocov_table* hashed_reduce(ottocov_ctx* ctx, u64* keys, u64* alt, int64_t n, c
         const bool packed = (mix.kb <= HR_TAG_BITS || rem_bits + 8 <= HR_TAG_BITS) && !no_packed;
         const unsigned grid = (unsigned)ceil_div64(n, HR_TILE);
         u32* flags = reinterpret_cast<u32*>(ctr + 1);
+        if (big) {
+            COV_LAUNCH(ctx, OTTOCOV_K_MISC, 0, hr_bounds_fix_kernel, 1, 1024, 0, bucket_bounds.p, (u32)n_buckets, (u64)n,
+                       (const u32*)flags);
+            const size_t smem = (size_t)HRB_CAP * 8 + (size_t)HRB_STAGE_KEYS * 4 + (HRB_THREADS / 32 + 1) * 4 + 12;
+            if (sym) {
+                auto kern = hash_reduce_buckets_kernel<true>;
+                cov_func_smem(ctx, (const void*)kern, smem);
+                COV_LAUNCH(ctx, OTTOCOV_K_RLE, 8.0 * n, kern, (unsigned)n_buckets, HRB_THREADS, smem, k, (const u64*)bucket_bounds.p,
+                           rem_bits, hrb_round_bits(), mix, min_count, mirror ? 1 : 0, ok.p, oc.p, ctr, cap, flags);
+            } else {
+                auto kern = hash_reduce_buckets_kernel<false>;
+                cov_func_smem(ctx, (const void*)kern, smem);
+                COV_LAUNCH(ctx, OTTOCOV_K_RLE, 8.0 * n, kern, (unsigned)n_buckets, HRB_THREADS, smem, k, (const u64*)bucket_bounds.p,
+                           rem_bits, hrb_round_bits(), mix, min_count, 0, ok.p, oc.p, ctr, cap, flags);
+            }
+        } else {
 #define HR_LAUNCH(SYM_, PACKED_)                                                                                      \
         do {                                                                                                          \
             auto kern = hash_reduce_kernel<SYM_, PACKED_>;                                                            \
@@ -450,6 +658,7 @@ ottocov_table* hashed_reduce(ottocov_ctx* ctx, u64* keys, u64* alt, int64_t n, c
             if (packed) HR_LAUNCH(false, true); else HR_LAUNCH(false, false);
         }
 #undef HR_LAUNCH
+        }
         unsigned long long h[2];
         cov_readback(ctx, h, ctr, sizeof(h));
         const int64_t rows = (int64_t)h[0];

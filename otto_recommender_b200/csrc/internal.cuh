@@ -251,7 +251,8 @@ int radix_sort_pairs(ottocov_ctx* ctx, u64*& keys, u64*& alt, u32*& vals, u32*& 
 // a * n_b + b starts at key offset seg_off[.] and holds seg_cnt[.] keys (device arrays); logical order: b-major.
 int radix_sort_passes(ottocov_ctx* ctx, u64*& keys, u64*& alt, u32*& vals, u32*& valt, int64_t n, const PassList& pl,
                       u64* pre_hist = nullptr, const u64* seg_cnt = nullptr, const u64* seg_off = nullptr, int n_a = 1,
-                      int n_b = 1, const u32* abort_flag = nullptr);     // abort_flag: see rs_onesweep_kernel
+                      int n_b = 1, const u32* abort_flag = nullptr,      // abort_flag: see rs_onesweep_kernel
+                      u64* bucket_bounds = nullptr);                     // [2^bits * n_b] pre-set to ~0: see RsSegs (one pass only)
 // cudaFuncAttributeMaxDynamicSharedMemorySize opt-in, once per (context = device, kernel)
 void cov_func_smem(ottocov_ctx* ctx, const void* func, size_t bytes);
 
@@ -340,7 +341,11 @@ struct HashPre {
     int n_a, n_b;
     unsigned long long* ctr;
     bool skip_sort = false;  // leave the surviving rows in bucket order (the caller sorts them later anyway)
+    bool big = false;        // whole-bucket reduce (hash_reduce_buckets_kernel): bb = first_bits + ONE more pass
 };
+// Bucket bits of the whole-bucket reduce for n keys, or 0 when it does not save a distribution pass over
+// hashed_bucket_bits (or cannot serve keys this wide).
+int hashed_big_bucket_bits(int64_t n, int kb);
 ottocov_table* hashed_reduce(ottocov_ctx* ctx, u64* keys, u64* alt, int64_t n, const KeyMix& mix, u32 min_count,
                              bool sym, bool mirror, int* passes_out, u64* pre_hist = nullptr, const HashPre* pre = nullptr);
 // Reduce over several bucket-sorted arrays (streamed ingest): see hash_reduce.cu, "the same reduce over SEVERAL ...".

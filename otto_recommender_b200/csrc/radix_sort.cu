@@ -229,15 +229,24 @@ struct RsSegs {
     const u64* cnt;            // [n_segs] keys in the segment
     const u64* tile_in;        // [launch grid] per tile: offset of its first key in keys_in ...
     const u32* tile_n;         // [launch grid] ... and its key count (0 for tickets beyond the last tile)
+    const u32* tile_first;     // [launch grid] segment index if the tile is the first of its segment, else ~0
+    // Bucket bounds (optional; only when this pass is the LAST one).  Segment s = b * n_a + a holds the keys whose
+    // earlier digit is b, so after this pass the keys with (this digit, earlier digit) = (d, b) are contiguous, and
+    // they start where digit d starts + what the tiles of the segments before s hold of digit d -- exactly the
+    // exclusive prefix the first tile of segment s resolves by look-back.  It records
+    // bounds[d * n_b + b] = min(.., that position); entries of empty buckets stay ~0 (hash_reduce.cu fills them in).
+    u64* bounds;
+    u32 n_a, n_b;
 };
 
 // Per-tile table of a segmented launch (one thread per ticket of the launch grid): the pass kernel then needs one
 // load per tile instead of a search over the segment table on its critical path.
 __global__ void __launch_bounds__(256) rs_seg_tiles_kernel(const RsSegs* __restrict__ segs, u32 tile_keys, u32 grid_tiles,
-                                                           u64* __restrict__ tile_in, u32* __restrict__ tile_n) {
+                                                           u64* __restrict__ tile_in, u32* __restrict__ tile_n,
+                                                           u32* __restrict__ tile_first) {
     const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= grid_tiles) return;
-    if (t >= segs->total_tiles) { tile_in[t] = 0; tile_n[t] = 0; return; }
+    if (t >= segs->total_tiles) { tile_in[t] = 0; tile_n[t] = 0; tile_first[t] = ~0u; return; }
     const u32* ts = segs->tile_start;
     u32 lo = 0, hi = segs->n_segs;                 // last segment whose first tile is <= t
     while (hi - lo > 1) {
@@ -248,6 +257,7 @@ __global__ void __launch_bounds__(256) rs_seg_tiles_kernel(const RsSegs* __restr
     const u64 left = segs->cnt[lo] - within;
     tile_in[t] = segs->in_off[lo] + within;
     tile_n[t] = (u32)(left < tile_keys ? left : tile_keys);
+    tile_first[t] = (t == ts[lo]) ? lo : ~0u;
 }
 
 // One block.  Segment s = b * n_a + a (b-major: b is the digit the keys were partitioned on, a the writer
@@ -292,9 +302,14 @@ __global__ void __launch_bounds__(256) rs_seg_build_kernel(const u64* __restrict
     }
 }
 
-__global__ void rs_seg_attach_kernel(RsSegs* hdr, const u64* tile_in, const u32* tile_n) {
+__global__ void rs_seg_attach_kernel(RsSegs* hdr, const u64* tile_in, const u32* tile_n, const u32* tile_first, u64* bounds,
+                                     u32 n_a, u32 n_b) {
     hdr->tile_in = tile_in;
     hdr->tile_n = tile_n;
+    hdr->tile_first = tile_first;
+    hdr->bounds = bounds;
+    hdr->n_a = n_a;
+    hdr->n_b = n_b;
 }
 
 #ifndef OTTOCOV_RS_MINB
@@ -341,14 +356,17 @@ rs_onesweep_kernel(const u64* __restrict__ keys_in, u64* __restrict__ keys_out,
         t = __shfl_sync(0xffffffffu, t, 0);
         u64 in_base = (u64)t * RS_TILE;
         int64_t left = n - (int64_t)in_base;
+        u32 first_of = ~0u;
         if (segs) {
             in_base = segs->tile_in[t];
             left = (int64_t)segs->tile_n[t];
+            if (segs->bounds) first_of = segs->tile_first[t];
         }
         if (lane == 0) {
             s_tile[0] = t;
             s_tile[1] = (u32)(left <= 0 ? 0 : (left < RS_TILE ? left : RS_TILE));
             *reinterpret_cast<u64*>(s_tile + 2) = in_base;
+            s_tile[4] = first_of;
         }
     }
     for (int j = tid; j < VW * STRIDE; j += RS_THREADS) s_whist[j] = 0;
@@ -436,6 +454,10 @@ rs_onesweep_kernel(const u64* __restrict__ keys_in, u64* __restrict__ keys_out,
         // byte address inside that rank's receive buffer, mapped into this process over NVLink
         s_gptr[tid] = ptr_base ? ptr_base[tid] + (excl - (u64)dstart) * 8u
                                : reinterpret_cast<u64>(keys_out) + (digit_base[tid] + excl - (u64)dstart) * 8u;
+        const u32 first_of = s_tile[4];
+        if (first_of != ~0u)                                  // first tile of a segment: bucket bounds (see RsSegs)
+            atomicMin(reinterpret_cast<unsigned long long*>(segs->bounds + (size_t)tid * segs->n_b + first_of / segs->n_a),
+                      (unsigned long long)(digit_base[tid] + excl));
     }
 
     // -- D: scatter into the digit-ordered staging buffer ---------------------------------------------------
@@ -548,10 +570,12 @@ int radix_sort_pairs(ottocov_ctx* ctx, u64*& keys, u64*& alt, u32*& vals, u32*& 
 }
 
 int radix_sort_passes(ottocov_ctx* ctx, u64*& keys, u64*& alt, u32*& vals, u32*& valt, int64_t n, const PassList& pl,
-                      u64* pre_hist, const u64* seg_cnt, const u64* seg_off, int n_a, int n_b, const u32* abort_flag) {
+                      u64* pre_hist, const u64* seg_cnt, const u64* seg_off, int n_a, int n_b, const u32* abort_flag,
+                      u64* bucket_bounds) {
     if (n <= 0 || pl.n == 0 || (n == 1 && !seg_cnt)) return 0;
     const bool has_vals = vals != nullptr;
     if (seg_cnt && has_vals) COV_THROW(OTTOCOV_ERR_ARG, "segmented radix input is keys-only");
+    if (bucket_bounds && !(seg_cnt && pl.n == 1)) COV_THROW(OTTOCOV_ERR_ARG, "bucket bounds come from a single pass over segments");
 
     DevBuf<u64> ghist;
     u64* gh = pre_hist;
@@ -582,13 +606,14 @@ int radix_sort_passes(ottocov_ctx* ctx, u64*& keys, u64*& alt, u32*& vals, u32*&
                    reinterpret_cast<RsSegs*>(segbuf.p), reinterpret_cast<u32*>(segbuf.p + o_ts),
                    reinterpret_cast<u64*>(segbuf.p + o_in), reinterpret_cast<u64*>(segbuf.p + o_cn));
         segs = reinterpret_cast<const RsSegs*>(segbuf.p);
-        seg_tiles.alloc(ctx, (size_t)n_tiles_first * 12 + 16);
+        seg_tiles.alloc(ctx, (size_t)n_tiles_first * 16 + 16);
         u64* t_in = reinterpret_cast<u64*>(seg_tiles.p);
         u32* t_n = reinterpret_cast<u32*>(seg_tiles.p + (size_t)n_tiles_first * 8);
+        u32* t_first = t_n + n_tiles_first;
         COV_LAUNCH(ctx, OTTOCOV_K_MISC, 0, rs_seg_tiles_kernel, (unsigned)ceil_div64(n_tiles_first, 256), 256, 0, segs, (u32)tile,
-                   (u32)n_tiles_first, t_in, t_n);
+                   (u32)n_tiles_first, t_in, t_n, t_first);
         COV_LAUNCH(ctx, OTTOCOV_K_MISC, 0, rs_seg_attach_kernel, 1, 1, 0, reinterpret_cast<RsSegs*>(segbuf.p), (const u64*)t_in,
-                   (const u32*)t_n);
+                   (const u32*)t_n, (const u32*)t_first, bucket_bounds, (u32)n_a, (u32)n_b);
     }
     for (int p = 0; p < pl.n; ++p) {
         const bool first_seg = (p == 0 && segs);

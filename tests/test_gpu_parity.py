@@ -602,6 +602,7 @@ def _fused_cases(engine, seed=13, n_sessions=40_000):
     s, a, t, y = d["session"], d["aid"], d["ts"], d["type"]
     engine.load_events(s, a, t, y)
     fused_seen = 0
+    big_seen = _fused_cases.big_seen = [0]      # of those, counted by the whole-bucket kernel (count_info "fused" == 2)
     for name in NAMES:
         oa, ob, oc, emitted, _ = c_oracle.count_name(s, a, t, y, name)
         for mc in (1, 2, 3):
@@ -611,7 +612,8 @@ def _fused_cases(engine, seed=13, n_sessions=40_000):
                     got = engine.count(name, min_count=mc, symmetric=sym, hashed=True, pair_budget=budget)
                     ci = engine.count_info()
                     assert ci["n_pairs"] == emitted
-                    fused_seen += ci["fused"]
+                    fused_seen += 1 if ci["fused"] else 0
+                    big_seen[0] += 1 if ci["fused"] == 2 else 0
                     if ci["fused"] and budget is not None:
                         assert ci["n_chunks"] >= 3, ci
                     ga, gb, gc = got.fetch()
@@ -630,13 +632,20 @@ def test_fused_first_pass_overflow_and_unfused_children():
     Both knobs are read once per process, so the cases run in child processes; same tables as the oracle."""
     import subprocess
     import sys
-    if os.environ.get("OTTOCOV_FUSE_SLACK_PCT") or os.environ.get("OTTOCOV_NO_FUSED_PASS") or os.environ.get("OTTOCOV_NO_FUSED_LOADER"):
+    if any(os.environ.get(k) for k in ("OTTOCOV_FUSE_SLACK_PCT", "OTTOCOV_NO_FUSED_PASS", "OTTOCOV_NO_FUSED_LOADER", "OTTOCOV_HRB")):
         pytest.skip("already inside the child run")
     # (3) OTTOCOV_NO_FUSED_LOADER=1: the loader's general path (separate statistics pass) on inputs the fused
     # validate+dedup+split pass would otherwise take.
     for extra, sel in (({"OTTOCOV_FUSE_SLACK_PCT": "-60"}, "fused_child or hash_reduce_hot or hash_reduce_many"),
                        ({"OTTOCOV_NO_FUSED_PASS": "1"}, "fused_child or hash_reduce_hot or hash_reduce_many"),
-                       ({"OTTOCOV_NO_FUSED_LOADER": "1"}, "golden_b1 or random_vs_oracle or edge_cases or errors_are_loud")):
+                       ({"OTTOCOV_NO_FUSED_LOADER": "1"}, "golden_b1 or random_vs_oracle or edge_cases or errors_are_loud"),
+                       # (4) the whole-bucket reduce (one CTA per bucket, keys staged in shared memory, 2^ROUND_BITS table rounds), which
+                       # by default only engages at sizes where it saves a pass (> 33 M keys): forced on small inputs with
+                       # small / medium buckets; the hot-pair test then streams a bucket that does not fit the staging area
+                       ({"OTTOCOV_HRB": "2", "OTTOCOV_HRB_AVG": "64"}, "fused_child or hash_reduce_hot or hash_reduce_many"),
+                       ({"OTTOCOV_HRB": "2", "OTTOCOV_HRB_AVG": "2000"}, "fused_child or hash_reduce_many"),
+                       ({"OTTOCOV_HRB": "2", "OTTOCOV_HRB_AVG": "2000", "OTTOCOV_HRB_ROUND_BITS": "0"}, "fused_child"),
+                       ({"OTTOCOV_HRB": "0"}, "fused_child")):
         env = dict(os.environ, **extra)
         r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
                             "-k", sel],
@@ -649,6 +658,9 @@ def test_fused_child(engine):
         assert _fused_cases(engine, seed=14, n_sessions=30_000) >= 12
     elif os.environ.get("OTTOCOV_NO_FUSED_PASS"):
         assert _fused_cases(engine, seed=14, n_sessions=30_000) == 0
+    elif os.environ.get("OTTOCOV_HRB"):
+        assert _fused_cases(engine, seed=14, n_sessions=30_000) >= 12
+        assert (_fused_cases.big_seen[0] >= 6) == (os.environ["OTTOCOV_HRB"] == "2"), _fused_cases.big_seen
     else:
         pytest.skip("runs inside test_fused_first_pass_overflow_and_unfused_children")
 

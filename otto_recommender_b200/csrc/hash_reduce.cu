@@ -190,6 +190,79 @@ __device__ __forceinline__ bool hr_emit(const u64* s_key, const u32* s_cnt, u32*
     return true;
 }
 
+// The same scan + emit without CTA barriers (packed words only): every WARP reserves room for its survivors with its
+// own global atomic (the rows are sorted afterwards, their order here is free), and every thread resets the slots it
+// scanned, so the table is empty again when the function returns.  Used by the whole-bucket kernel, whose 16-warp
+// CTAs (two per SM) pay dearly for each barrier.  An output overflow raises the flag (the host falls back).
+template <bool SYM, int CL2, int NT>
+__device__ __forceinline__ void hr_emit_warp(u64* s_key, u64 base, const KeyMix& mix, u32 min_count, int mirror,
+                                             u64* __restrict__ out_keys, u32* __restrict__ out_count,
+                                             unsigned long long* __restrict__ out_n, u64 out_cap, u32* __restrict__ flags) {
+    constexpr int SPT = (1 << CL2) / NT;
+    static_assert(2 * SPT <= 32, "two flag bits per scanned slot must fit one register");
+    const int tid = threadIdx.x, lane = tid & 31;
+    const u32 cand = SYM ? (min_count + 1u) / 2u : min_count;
+    u32 candm = 0;
+#pragma unroll
+    for (int q = 0; q < SPT; ++q) {
+        const u32 c = reinterpret_cast<const u32*>(s_key + tid + q * NT)[0] & (u32)HR_CMASK;
+        candm |= ((c >= cand && c != (u32)HR_CMASK && c != 0u) ? 1u : 0u) << q;
+    }
+    u32 bits = 0, emit = 0;
+    if (!SYM) {
+#pragma unroll
+        for (int q = 0; q < SPT; ++q) bits |= ((candm >> q) & 1u) << (2 * q);
+        emit = __popc(candm);
+    } else {
+        while (candm) {
+            const int q = __ffs(candm) - 1;
+            candm &= candm - 1u;
+            u64 h; u32 c;
+            hr_slot<true>(s_key, nullptr, tid + q * NT, base, &h, &c);
+            const u64 plain = key_mix_inv(mix, h);
+            const bool diag = (u32)(plain >> 32) == (u32)plain;
+            const u64 total = diag ? 2ull * c : (u64)c;
+            if (total >= (u64)min_count) {
+                const bool two = mirror && !diag;
+                bits |= (two ? 3u : 1u) << (2 * q);
+                emit += two ? 2u : 1u;
+            }
+        }
+    }
+    u32 inc = emit;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    const u32 wtot = __shfl_sync(0xffffffffu, inc, 31);
+    if (wtot) {                                            // warp-uniform
+        unsigned long long b = 0;
+        if (lane == 31) b = atomicAdd(out_n, (unsigned long long)wtot);
+        b = __shfl_sync(0xffffffffu, b, 31);
+        if (b + wtot > out_cap) {
+            if (lane == 31) atomicOr(flags, 2u);
+        } else {
+            u64 o = b + inc - emit;
+            while (bits) {
+                const int q = (__ffs(bits) - 1) >> 1;
+                const u32 f = (bits >> (2 * q)) & 3u;
+                bits &= ~(3u << (2 * q));
+                u64 h; u32 c;
+                hr_slot<true>(s_key, nullptr, tid + q * NT, base, &h, &c);
+                const u64 plain = key_mix_inv(mix, h);
+                u64 total = c;
+                if (SYM && (u32)(plain >> 32) == (u32)plain) total *= 2;
+                const u32 c32 = (u32)(total > 0xFFFFFFFFull ? 0xFFFFFFFFull : total);
+                out_keys[o] = plain; out_count[o] = c32; ++o;
+                if (f & 2u) { out_keys[o] = (plain << 32) | (plain >> 32); out_count[o] = c32; ++o; }
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < SPT; ++q) s_key[tid + q * NT] = HR_NONE;
+}
+
 template <bool PACKED, int CL2 = HR_CAP_LOG2, int NT = HR_THREADS>
 __device__ __forceinline__ void hr_clear(u64* s_key, u32* s_cnt) {
     const int tid = threadIdx.x;
@@ -362,6 +435,7 @@ constexpr int HRB_KPT = 24;
 constexpr int HRB_STAGE_KEYS = HRB_THREADS * HRB_KPT;  // 12288
 constexpr int HRB_MAX_REM_BITS = 31;                 // tags are 32-bit
 constexpr int HRB_MAX_ROUND_BITS = 1;
+constexpr int HRB_MAX_ITERS = 4 * HRB_CAP;           // probes per lane and round before the CTA gives up (typical: ~16)
 
 // bounds[nb] = n; an entry no tile wrote (~0: empty bucket) takes the next written one to its right
 __global__ void __launch_bounds__(1024) hr_bounds_fix_kernel(u64* __restrict__ bounds, u32 nb, u64 n, const u32* __restrict__ flags) {
@@ -399,10 +473,7 @@ hash_reduce_buckets_kernel(const u64* __restrict__ keys, const u64* __restrict__
                            unsigned long long* __restrict__ out_n, u64 out_cap, u32* __restrict__ flags) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     u64* s_key = reinterpret_cast<u64*>(s_raw);                              // [HRB_CAP] packed words tag | count
-    u32* s_tags = reinterpret_cast<u32*>(s_key + HRB_CAP);                   // [HRB_KPT][HRB_THREADS]
-    u32* s_scan = s_tags + HRB_STAGE_KEYS;                                   // [HRB_THREADS / 32 + 1]
-    __shared__ unsigned long long s_base;
-    __shared__ u32 s_over;
+    u32* s_tags = reinterpret_cast<u32*>(s_key + HRB_CAP);                   // [HRB_THREADS / 32 warps][HRB_KPT * 32]
     if (*flags & HR_FLAG_FUSED_OVERFLOW) return;
     const int tid = threadIdx.x;
     const u64 lo = bounds[blockIdx.x], hi = bounds[blockIdx.x + 1];
@@ -413,59 +484,70 @@ hash_reduce_buckets_kernel(const u64* __restrict__ keys, const u64* __restrict__
     const u32 low_mask = (u32)((1ull << rem_bits) - 1ull);
     const int rshift = rem_bits - round_bits;
     const bool staged = nk <= (u64)HRB_STAGE_KEYS;
-    int n_front = 0, n_back = 0;                                             // this thread's keys of round 0 / round 1
+    // Staging: the warp's keys of round 0 are packed from the front of the warp's queue, the others from its back
+    // (ballot + popc), so lane l's keys of a round are entries l, l + 32, ... : every lane gets the same number +- 1.
+    const int lane = tid & 31;
+    u32* wq = s_tags + (tid >> 5) * (HRB_KPT * 32);
+    u32 n_front = 0, n_back = 0;                                             // warp-uniform
     if (staged) {
         const u32 n32 = (u32)nk;
         const u32* kp = reinterpret_cast<const u32*>(keys + lo + tid);      // low words only: the tag has <= 31 bits
-        u32* col = s_tags + tid;
+        const u32 lt = lanemask_lt();
         u32 t[HRB_KPT];
 #pragma unroll
         for (int j = 0; j < HRB_KPT; ++j)
             t[j] = ((u32)(j * HRB_THREADS + tid) < n32) ? (__ldcs(kp + 2 * j * HRB_THREADS) & low_mask) : 0u;
 #pragma unroll
         for (int j = 0; j < HRB_KPT; ++j) {
-            if ((u32)(j * HRB_THREADS + tid) < n32) {
-                const bool front = (t[j] >> rshift) == 0u;
-                col[(front ? n_front : HRB_KPT - 1 - n_back) * HRB_THREADS] = t[j];
-                n_front += front ? 1 : 0;
-                n_back += front ? 0 : 1;
-            }
+            const bool valid = (u32)(j * HRB_THREADS + tid) < n32;
+            const bool front = valid && (t[j] >> rshift) == 0u;
+            const bool back = valid && !front;
+            const u32 mf = __ballot_sync(0xffffffffu, front), mb = __ballot_sync(0xffffffffu, back);
+            if (front) wq[n_front + __popc(mf & lt)] = t[j];
+            if (back) wq[HRB_KPT * 32 - 1 - (n_back + __popc(mb & lt))] = t[j];
+            n_front += __popc(mf);
+            n_back += __popc(mb);
         }
+        __syncwarp();
     }
-    if (tid == 0) s_over = 0;
+    hr_clear<true, HRB_CAP_LOG2, HRB_THREADS>(s_key, nullptr);
+    __syncthreads();
     for (int r = 0; r < (1 << round_bits); ++r) {
-        hr_clear<true, HRB_CAP_LOG2, HRB_THREADS>(s_key, nullptr);
-        __syncthreads();
         if (staged) {
-            int left = r == 0 ? n_front : n_back;
-            int row = r == 0 ? 0 : HRB_KPT - 1;
-            const int step = r == 0 ? 1 : -1;
-            const u32* col = s_tags + tid;
-            bool active = left > 0;
-            u32 tag = active ? col[row * HRB_THREADS] : 0u;
+            const u32 n_r = r == 0 ? n_front : n_back;                       // the warp's keys of this round
+            const int mine = n_r > (u32)lane ? (int)((n_r - (u32)lane + 31u) >> 5) : 0;
+            const u32* first = r == 0 ? wq + lane : wq + (HRB_KPT * 32 - 1 - lane);
+            const int stride = r == 0 ? 32 : -32;
+            // One probe per iteration; a lane whose key is placed takes its next key in the same iteration.  The vote
+            // makes the warp reconverge every time round (without it the lanes that took different branches ran the
+            // loop in separate groups).  CAS first, no look: an empty slot is claimed AND counted by the one atomic; the
+            // tag field of the word it returns says which of the three cases this was (empty = all ones, never a tag).
+            // The body is kept to ~20 instructions: no per-key probe counter -- a table that fills up (more distinct
+            // keys than slots; needs an adversarial input) shows as a warp that is still busy after HRB_MAX_ITERS.
+            int left = mine;
+            const u32* p = first;
+            u32 tag = left > 0 ? *p : 0u;
             u32 slot = hrb_slot_of(tag);
-            int probes = 0;
-            // the vote makes the warp reconverge at every iteration: without it the lanes that took different branches
-            // run the loop in separate groups, and the warp pays the SUM of their iterations
-            while (__any_sync(0xffffffffu, active)) {
-                if (active) {
-                    const u64 cur = atomicCAS(reinterpret_cast<unsigned long long*>(s_key + slot), HR_NONE, ((u64)tag << HR_CB) | 1ull);
-                    const bool match = (cur >> HR_CB) == (u64)tag;       // an empty slot's tag field is all ones: never a tag
-                    if (match) atomicAdd(reinterpret_cast<u32*>(s_key + slot), 1u);
-                    if (match || cur == HR_NONE) {                       // counted (or claimed and counted in one step)
-                        if (--left == 0) active = false;
-                        else {
-                            row += step;
-                            tag = col[row * HRB_THREADS];
+            int it = 0;
+            while (__any_sync(0xffffffffu, left > 0)) {
+                if (left > 0) {
+                    const u64 cur = atomicCAS(reinterpret_cast<unsigned long long*>(s_key + slot), HR_NONE,
+                                              ((u64)tag << HR_CB) | 1ull);
+                    const u32 ct = (u32)(cur >> HR_CB);
+                    if (ct == tag) atomicAdd(reinterpret_cast<u32*>(s_key + slot), 1u);
+                    if (ct == tag || ct == 0xFFFFFFFFu) {
+                        if (--left > 0) {
+                            p += stride;
+                            tag = *p;
                             slot = hrb_slot_of(tag);
-                            probes = 0;
                         }
                     } else {
                         slot = (slot + 1) & (HRB_CAP - 1);
-                        if (++probes >= HRB_CAP) { atomicOr(flags, 1u); active = false; }      // table full: the host falls back
                     }
                 }
+                if (++it >= HRB_MAX_ITERS) break;              // warp-uniform
             }
+            if (__any_sync(0xffffffffu, left > 0) && lane == 0) atomicOr(flags, 1u);      // the host falls back to the sort
         } else {
             for (u64 i0 = lo; i0 < hi; i0 += HRB_THREADS) {                  // block-uniform trip count
                 const u64 i = i0 + (u64)tid;
@@ -475,10 +557,9 @@ hash_reduce_buckets_kernel(const u64* __restrict__ keys, const u64* __restrict__
             }
         }
         __syncthreads();
-        if (!hr_emit<SYM, true, HRB_CAP_LOG2, HRB_THREADS>(s_key, nullptr, s_scan, &s_base, &s_over, base, mix, min_count, mirror,
-                                                           out_keys, out_count, out_n, out_cap, flags))
-            return;
-        __syncthreads();                                                      // the next round clears the table
+        hr_emit_warp<SYM, HRB_CAP_LOG2, HRB_THREADS>(s_key, base, mix, min_count, mirror, out_keys, out_count, out_n, out_cap,
+                                                     flags);                 // leaves the table empty
+        if (r + 1 < (1 << round_bits)) __syncthreads();
     }
 }
 
@@ -632,18 +713,17 @@ ottocov_table* hashed_reduce(ottocov_ctx* ctx, u64* keys, u64* alt, int64_t n, c
         if (big) {
             COV_LAUNCH(ctx, OTTOCOV_K_MISC, 0, hr_bounds_fix_kernel, 1, 1024, 0, bucket_bounds.p, (u32)n_buckets, (u64)n,
                        (const u32*)flags);
-            const size_t smem = (size_t)HRB_CAP * 8 + (size_t)HRB_STAGE_KEYS * 4 + (HRB_THREADS / 32 + 1) * 4 + 12;
-            if (sym) {
-                auto kern = hash_reduce_buckets_kernel<true>;
-                cov_func_smem(ctx, (const void*)kern, smem);
-                COV_LAUNCH(ctx, OTTOCOV_K_RLE, 8.0 * n, kern, (unsigned)n_buckets, HRB_THREADS, smem, k, (const u64*)bucket_bounds.p,
-                           rem_bits, hrb_round_bits(), mix, min_count, mirror ? 1 : 0, ok.p, oc.p, ctr, cap, flags);
-            } else {
-                auto kern = hash_reduce_buckets_kernel<false>;
-                cov_func_smem(ctx, (const void*)kern, smem);
-                COV_LAUNCH(ctx, OTTOCOV_K_RLE, 8.0 * n, kern, (unsigned)n_buckets, HRB_THREADS, smem, k, (const u64*)bucket_bounds.p,
-                           rem_bits, hrb_round_bits(), mix, min_count, 0, ok.p, oc.p, ctr, cap, flags);
-            }
+            const size_t smem = (size_t)HRB_CAP * 8 + (size_t)HRB_STAGE_KEYS * 4;
+#define HRB_LAUNCH(SYM_)                                                                                               \
+            do {                                                                                                       \
+                auto kern = hash_reduce_buckets_kernel<SYM_>;                                                          \
+                cov_func_smem(ctx, (const void*)kern, smem);                                                           \
+                COV_LAUNCH(ctx, OTTOCOV_K_RLE, 8.0 * n, kern, (unsigned)n_buckets, HRB_THREADS, smem, k,               \
+                           (const u64*)bucket_bounds.p, rem_bits, hrb_round_bits(), mix, min_count,                    \
+                           (SYM_ && mirror) ? 1 : 0, ok.p, oc.p, ctr, cap, flags);                                     \
+            } while (0)
+            if (sym) HRB_LAUNCH(true); else HRB_LAUNCH(false);
+#undef HRB_LAUNCH
         } else {
 #define HR_LAUNCH(SYM_, PACKED_)                                                                                      \
         do {                                                                                                          \

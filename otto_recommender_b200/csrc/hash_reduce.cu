@@ -499,14 +499,21 @@ hash_reduce_buckets_kernel(const u64* __restrict__ keys, const u64* __restrict__
             t[j] = ((u32)(j * HRB_THREADS + tid) < n32) ? (__ldcs(kp + 2 * j * HRB_THREADS) & low_mask) : 0u;
 #pragma unroll
         for (int j = 0; j < HRB_KPT; ++j) {
-            const bool valid = (u32)(j * HRB_THREADS + tid) < n32;
-            const bool front = valid && (t[j] >> rshift) == 0u;
-            const bool back = valid && !front;
-            const u32 mf = __ballot_sync(0xffffffffu, front), mb = __ballot_sync(0xffffffffu, back);
-            if (front) wq[n_front + __popc(mf & lt)] = t[j];
-            if (back) wq[HRB_KPT * 32 - 1 - (n_back + __popc(mb & lt))] = t[j];
-            n_front += __popc(mf);
-            n_back += __popc(mb);
+            const bool front = (t[j] >> rshift) == 0u;
+            if ((u32)((j + 1) * HRB_THREADS) <= n32) {                      // a full row (block-uniform): one ballot
+                const u32 mf = __ballot_sync(0xffffffffu, front);
+                const u32 pf = __popc(mf & lt), cf = __popc(mf);
+                wq[front ? n_front + pf : HRB_KPT * 32 - 1 - (n_back + (u32)lane - pf)] = t[j];
+                n_front += cf;
+                n_back += 32u - cf;
+            } else if ((u32)(j * HRB_THREADS) < n32) {                       // the last, partial row
+                const bool valid = (u32)(j * HRB_THREADS + tid) < n32;
+                const u32 mv = __ballot_sync(0xffffffffu, valid), mf = __ballot_sync(0xffffffffu, valid && front);
+                const u32 pf = __popc(mf & lt), pb = __popc(mv & lt) - pf;
+                if (valid) wq[front ? n_front + pf : HRB_KPT * 32 - 1 - (n_back + pb)] = t[j];
+                n_front += __popc(mf);
+                n_back += __popc(mv) - __popc(mf);
+            }
         }
         __syncwarp();
     }

@@ -541,6 +541,15 @@ def run_ours(args):
                    "algo_GBps": (v["algo_bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 else None}
                for k, v in stats_all.items() if v["launches"]}
     launches = sum(v["launches"] for v in stats.values())
+    # the family that takes the most time (from the extra, fully profiled step): since the whole-bucket reduce took a
+    # pass away, that is no longer the distribution pass the roofline object tracks
+    largest = None
+    timed = {k: v for k, v in kernels.items() if v.get("ms_per_step")}
+    if timed:
+        lk = max(timed, key=lambda k: timed[k]["ms_per_step"])
+        lv = timed[lk]
+        largest = {"family": lk, "ms_per_step": lv["ms_per_step"], "algo_GBps": lv["algo_GBps"],
+                   "frac_of_hbm_peak": (lv["algo_GBps"] / peak) if (peak and lv["algo_GBps"]) else None}
 
     # ---- CPU baseline on a bounded sample of the same workload + parity of the GPU path on that sample (N = 1) ----
     cpu, parity = None, None
@@ -582,7 +591,7 @@ def run_ours(args):
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                      "traffic": traffic, "peak_source": peak_src,
                      "algo_bytes_per_launch": per_launch_bytes, "ms_per_launch": per_launch_ms,
-                     "share_of_step": sp["ms"] / max(ms, 1e-9)},
+                     "share_of_step": sp["ms"] / max(ms, 1e-9), "largest_family": largest},
         "kernels": kernels,
         "clocks": clocks,
     }

@@ -21,7 +21,7 @@ for row in csv.DictReader(lines):
     total += ms
     n += 1
 OURS = ("rs_", "scan_onepass", "expand_kernel", "expand_scatter", "region_table", "publish_", "mirror_push", "rle_expand", "aid_max", "feat_", "sum_hist", "stripe_off", "init_minmax", "pop_", "hash_reduce", "rle_kernel", "ev_", "window", "tile_search", "topk",
-        "mix_", "unmix", "unpack", "order_keys", "table_stats", "pack_keys", "stamp", "strip", "unstamp")
+        "hr_", "mix_", "unmix", "unpack", "order_keys", "table_stats", "pack_keys", "stamp", "strip", "unstamp")
 ours = sum(v[0] for k, v in agg.items() if any(o in k for o in OURS))
 print(f"# ncu launch list summary of: {title}")
 print(f"# {n} launches, {total:.1f} ms total device time; cold-cache and serialised under ncu: compare SHARES, not absolutes")

@@ -31,6 +31,11 @@
 // keep), and hashed digits are uniform, so the expansion kernel itself scatters the keys into one slack region
 // per digit (expand.cu, expand_scatter_kernel).  hashed_reduce then starts from those regions (HashPre): the
 // remaining passes read them as segments.  HBM traffic: 8 P + (passes - 1) x 16 P + 8 P.
+//
+// Whole buckets (round 2, HashPre::big): with 16 bucket bits instead of 21 the fused pass + ONE more pass are
+// enough, and hash_reduce_buckets_kernel counts one whole ~11 k-key bucket per CTA (further down: "whole buckets").
+// Taken where it saves a pass (hashed_big_bucket_bits); steps 3-4 above describe the tile kernel, which still serves
+// everything else (small kinds, the owners' side of the multi-GPU exchange, the streamed ingest).
 #include "internal.cuh"
 #include "scan.cuh"
 
